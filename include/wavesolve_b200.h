@@ -1,0 +1,120 @@
+/*
+ * wavesolve_b200 -- C ABI of the B200-native FEM hot path (assembly + generalized sparse
+ * eigensolve) that sits behind wavesolve's Python functions.
+ *
+ * wavesolve has no FFI of its own (it is pure Python); the seams this library replaces are
+ * the reference *functions* (paths relative to /root/reference/src/wavesolve):
+ *
+ *   ws_edges_first_appearance    <- waveguide.py:10-43   get_unique_edges
+ *   ws_pattern_create / export   <- fe_solver.py:38-40,67-68 (COO -> CSR, scipy coo_tocsr +
+ *                                   sum_duplicates) and fe_solver.py:170-176,212-213 (lil -> csc)
+ *   ws_assemble_scalar_p2        <- fe_solver.py:47-55 + shape_funcs.py:192-246
+ *   ws_assemble_mass_p2          <- fe_solver.py:71-99   construct_B_order2
+ *   ws_assemble_vector_p1        <- fe_solver.py:178-210 + shape_funcs.py:310-428
+ *   ws_prune_zeros               <- the "exact zeros are not stored" behaviour of lil_matrix
+ *                                   behind fe_solver.py:196-199, 212-213
+ *   ws_spmv                      <- ARPACK reverse communication ido=2 (M_matvec) inside
+ *                                   eigsh (fe_solver.py:328)
+ *   ws_solver_*                  <- SuperLU splu/gssv inside eigsh sigma-mode and spsolve
+ *                                   (fe_solver.py:328, fe_solver.py:398)
+ *   ws_eig_*                     <- eigsh(A, M=B, k, which='SA', sigma)   (fe_solver.py:328) and
+ *                                   eigs((A - sigma B)^-1 B, k, which='SR') (fe_solver.py:398-400)
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name starts with h_ (host);
+ *   - the caller allocates every output array; opaque handles have explicit destroy;
+ *   - every call takes the CUDA device ordinal and a stream (cudaStream_t passed as void*);
+ *     work is enqueued on that stream; calls that must return a size to the host
+ *     (h_ outputs) synchronise that stream once, all others are asynchronous;
+ *   - return value: 0 ok, <0 argument error, >0 CUDA / numerical error; nothing throws across
+ *     the ABI; ws_last_error() returns a thread-local message for the last failure;
+ *   - connectivity is int32, values are fp64, CSR/CSC indices are int32 (as scipy produces
+ *     for these sizes);
+ *   - handles are not thread-safe; use one host thread (or process) per GPU.
+ */
+#ifndef WAVESOLVE_B200_H
+#define WAVESOLVE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WS_OK 0
+#define WS_ERR_ARG (-1)
+#define WS_ERR_STATE (-2)
+#define WS_ERR_CUDA 1
+#define WS_ERR_NUMERIC 2
+#define WS_ERR_NOCONV 3
+
+typedef struct ws_pattern ws_pattern; /* CSR pattern + row-incidence lists of one mesh   */
+typedef struct ws_solver ws_solver;   /* multifrontal LDL^T of A - sigma B               */
+typedef struct ws_eig ws_eig;         /* Krylov eigensolver workspace                    */
+
+int ws_version(void);
+const char* ws_last_error(void);
+/* number of kernels this library has launched so far in this process (bench.py: gpu_launches) */
+long long ws_launch_count(void);
+
+/* ---- K1: unique edges numbered by first appearance (waveguide.py:10-43) -------------
+ * tris      [Ne*3] vertex ids of the triangles in mesh order (cells[1].data)
+ * edges     [3*Ne*2] out, first Ntt rows valid: sorted vertex pair of edge id
+ * edge_idx  [Ne*3]  out: id of local edges (0,1),(1,2),(2,0) of every triangle
+ * h_Ntt     host out: number of unique edges                                        */
+int ws_edges_first_appearance(const int32_t* tris, int64_t Ne, int64_t Np, int32_t* edges,
+                              int32_t* edge_idx, int64_t* h_Ntt, int device, void* stream);
+
+/* ---- K2: sparsity pattern ------------------------------------------------------------
+ * dofs [Ne*6]: the six global unknowns of every element, elements in the order the
+ * reference assembles them (material-major, fe_solver.py:36 / :179).
+ *   scalar P2 : the six node ids (v0 v1 v2 m01 m12 m20)
+ *   vector P1 : edge ids e01 e12 e20, then Ntt + v0, Ntt + v1, Ntt + v2
+ * The pattern is the structural one (union of the 6x6 couplings), rows and columns sorted,
+ * int32 -- identical to what scipy builds at fe_solver.py:67-68 (explicit zeros kept).   */
+int ws_pattern_create(const int32_t* dofs, int64_t Ne, int64_t N, ws_pattern** out, int device,
+                      void* stream);
+int ws_pattern_query(const ws_pattern* p, int64_t* h_N, int64_t* h_nnz, int64_t* h_Ne);
+int ws_pattern_export(const ws_pattern* p, int32_t* indptr /*N+1*/, int32_t* indices /*nnz*/,
+                      int device, void* stream);
+/* device pointers owned by the pattern (valid until destroy) */
+int ws_pattern_arrays(const ws_pattern* p, const int32_t** indptr, const int32_t** indices);
+int ws_pattern_destroy(ws_pattern* p);
+
+/* ---- K3: scalar P2 assembly (fe_solver.py:47-55, shape_funcs.py:192-246) -----------------
+ * xy [Np*2] node coordinates, dofs as given to ws_pattern_create, elem_k2n2 [Ne] = k^2 n_e^2
+ * (fe_solver.py:51).  A_vals/B_vals [nnz] in the pattern's slot order.
+ * transpose != 0 writes slot (i,j) with the element entry (j,i) (CSC values of the same
+ * symmetric pattern).                                                                  */
+int ws_assemble_scalar_p2(const ws_pattern* p, const double* xy, const int32_t* dofs,
+                          const double* elem_k2n2, double* A_vals, double* B_vals, int transpose,
+                          int device, void* stream);
+/* mass matrix only, all elements (fe_solver.py:71-99) */
+int ws_assemble_mass_p2(const ws_pattern* p, const double* xy, const int32_t* dofs, double* B_vals,
+                        int device, void* stream);
+
+/* ---- K4: vector assembly, Whitney edges + P1 nodes (fe_solver.py:178-210) -----------------
+ * tris [Ne*3] vertex ids (element order = dofs order), Ntt = number of edge unknowns.
+ * A_vals/B_vals [nnz] on the pattern of B; A is non-zero only in the edge-edge block.  */
+int ws_assemble_vector_p1(const ws_pattern* p, const double* xy, const int32_t* tris,
+                          const double* elem_k2n2, int64_t Ntt, double* A_vals, double* B_vals,
+                          int transpose, int device, void* stream);
+
+/* ---- zero pruning (lil_matrix semantics behind fe_solver.py:196-199, 212-213) -------------
+ * Compacts (pattern, vals) to the entries with vals != 0.0.  out_* sized for nnz.        */
+int ws_prune_zeros(const ws_pattern* p, const double* vals, int32_t* out_indptr /*N+1*/,
+                   int32_t* out_indices, double* out_vals, int64_t* h_nnz_out, int device,
+                   void* stream);
+
+/* ---- K11: A(k) = k2scale * Mn2 - K on a shared pattern; y = alpha*x + beta*y on values --- */
+int ws_axpby(int64_t n, double alpha, const double* x, double beta, double* y, int device,
+             void* stream);
+
+/* ---- K5: y = CSR(pattern, vals) * x --------------------------------------------------- */
+int ws_spmv(const ws_pattern* p, const double* vals, const double* x, double* y, int device,
+            void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

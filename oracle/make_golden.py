@@ -1,0 +1,138 @@
+"""TEST INFRASTRUCTURE ONLY.  Generate ``tests/golden/*.npz`` from the LITERAL reference.
+
+Run in the build container (where ``/root/reference`` exists):
+
+    python -m oracle.make_golden
+
+Every fixture stores the input mesh arrays (so nothing depends on the mesh generator or on
+qhull being bit-reproducible elsewhere) and the outputs of the unmodified reference
+functions ``construct_AB`` (fe_solver.py:131), ``construct_B`` (fe_solver.py:101),
+``get_unique_edges`` (waveguide.py:10), ``construct_AB_vec`` (fe_solver.py:148),
+``solve_waveguide`` (fe_solver.py:292) and ``solve_waveguide_vec`` (fe_solver.py:350,
+sparse_solve_mode='transform').  The reference has no tests or golden vectors of its own
+(SURVEY.md section 4), so these reference-generated outputs are what pins the oracle.
+"""
+from __future__ import annotations
+
+import copy
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+
+from oracle import refshim  # noqa: E402
+from wavesolve_b200 import meshgen as mg  # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+WL = 1.55
+
+
+def mesh_arrays(mesh):
+    labels = list(mesh.cell_sets.keys())
+    d = {"points": mesh.points, "tris": np.asarray(mesh.cells[1].data),
+         "labels": np.array(labels)}
+    for i, lab in enumerate(labels):
+        d["set_%d" % i] = np.asarray(mesh.cell_sets[lab][1])
+    return d
+
+
+def csx(prefix, M):
+    M = M.copy()
+    M.sort_indices()
+    return {prefix + "_indptr": M.indptr, prefix + "_indices": M.indices, prefix + "_data": M.data,
+            prefix + "_shape": np.array(M.shape), prefix + "_format": np.array(M.format)}
+
+
+def scalar_case(fe, name, mesh, ior, Nmax=10, target_neff=None, store_v=True, with_B=False):
+    k = 2 * np.pi / WL
+    out = mesh_arrays(mesh)
+    out["ior"] = np.array([ior[l] for l in mesh.cell_sets.keys()])
+    out["wl"] = np.array(WL)
+    A, B = fe.construct_AB(mesh, ior, k, sparse=True, order=2)
+    out.update(csx("A", A))
+    out.update(csx("B", B))
+    if with_B:
+        out.update(csx("Bfull", fe.construct_B(mesh, sparse=True)))
+    if Nmax:
+        w, v, cnt = fe.solve_waveguide(mesh, WL, ior, sparse=True, Nmax=Nmax, order=2,
+                                       target_neff=target_neff)
+        out["w"] = np.array(w)
+        out["count"] = np.array(cnt)
+        out["Nmax"] = np.array(Nmax)
+        out["target_neff"] = np.array(np.nan if target_neff is None else target_neff)
+        if store_v:
+            out["v"] = np.ascontiguousarray(v)
+    np.savez_compressed(os.path.join(GOLD, name + ".npz"), **out)
+    print(name, "Ne", mesh.num_elements, "N", A.shape[0], "nnz", A.nnz,
+          "neff", (np.sqrt(out["w"]) / k)[:4] if Nmax else None, "count", out.get("count"))
+
+
+def vector_case(fe, wg, name, mesh, ior, Nmax=6, target_neff=None, solve=True):
+    k = 2 * np.pi / WL
+    out = mesh_arrays(mesh)
+    out["ior"] = np.array([ior[l] for l in mesh.cell_sets.keys()])
+    out["wl"] = np.array(WL)
+    m = copy.deepcopy(mesh)
+    edges, eidx = wg.get_unique_edges(m)
+    out["edges"] = edges
+    out["edge_indices"] = eidx
+    out["edge_flips"] = m.edge_flips
+    A, B = fe.construct_AB_vec(m, ior, k, sparse=True)
+    out.update(csx("A", A))
+    out.update(csx("B", B))
+    if solve:
+        w, v, cnt = fe.solve_waveguide_vec(m, WL, ior, sparse=True, Nmax=Nmax,
+                                           target_neff=target_neff,
+                                           sparse_solve_mode="transform", verbose=False)
+        out["w"] = np.array(w)
+        out["v"] = np.ascontiguousarray(v)
+        out["count"] = np.array(cnt)
+        out["Nmax"] = np.array(Nmax)
+        out["target_neff"] = np.array(np.nan if target_neff is None else target_neff)
+    np.savez_compressed(os.path.join(GOLD, name + ".npz"), **out)
+    print(name, "Ne", mesh.num_elements, "N", A.shape[0], "nnzA", A.nnz, "nnzB", B.nnz,
+          "neff", np.sqrt(out["w"].real) / k if solve else None, "count", out.get("count"))
+
+
+def main():
+    fe, sf, wg = refshim.load()
+    os.makedirs(GOLD, exist_ok=True)
+    ior = mg.FIBER_IOR
+    # ---- scalar P2 ----
+    scalar_case(fe, "scalar_sq8", mg.structured_square(8), ior, with_B=True)
+    scalar_case(fe, "scalar_disc600", mg.fiber_disc(600, seed=1), ior)
+    scalar_case(fe, "scalar_disc600_target", mg.fiber_disc(600, seed=1), ior, Nmax=4,
+                target_neff=1.447)
+    # uint64 connectivity as pygmsh/gmsh delivers it
+    scalar_case(fe, "scalar_sq5_uint64", mg.structured_square(5, dtype=np.uint64), ior, Nmax=3)
+    # ragged: one material empty, some elements in no set, one element in two sets
+    m = mg.structured_square(6)
+    cs = m.cell_sets
+    core = cs["core"][1]
+    clad = cs["cladding"][1]
+    m.cell_sets = {"core": [None, core, None],
+                   "void": [None, np.zeros(0, dtype=np.int64), None],
+                   "cladding": [None, np.concatenate([clad[:-5], core[:1]]), None]}
+    scalar_case(fe, "scalar_sq6_ragged", m, {"core": 1.46, "void": 1.0, "cladding": 1.444}, Nmax=0)
+    # config C1: ~5k elements, 10 modes (eigenvalues + count only, vectors are large)
+    scalar_case(fe, "scalar_c1_disc5k", mg.fiber_disc(5000, seed=0), ior, store_v=False)
+    # lantern-like three-material cross section
+    scalar_case(fe, "scalar_lantern2k", mg.lantern_cross_section(2000, seed=3), mg.LANTERN_IOR, Nmax=8,
+                store_v=False)
+    # ---- vector P1 + Whitney ----
+    vector_case(fe, wg, "vec_sq6", mg.structured_square(6, order=1), ior, Nmax=6)
+    vector_case(fe, wg, "vec_sq12", mg.structured_square(12, order=1), ior, Nmax=6)
+    vector_case(fe, wg, "vec_disc500", mg.fiber_disc(500, order=1, seed=2), ior, Nmax=6)
+    vector_case(fe, wg, "vec_disc1500", mg.fiber_disc(1500, order=1, seed=4), ior, Nmax=10)
+    vector_case(fe, wg, "vec_disc500_target", mg.fiber_disc(500, order=1, seed=2), ior, Nmax=4,
+                target_neff=1.448)
+    m = mg.structured_square(5, order=1, dtype=np.uint64)
+    vector_case(fe, wg, "vec_sq5_uint64", m, ior, solve=False)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,68 @@
+"""ctypes binding of ``libwavesolve_b200.so`` (the C ABI declared in
+``include/wavesolve_b200.h``).  There is no CPU fallback: if the library is missing or a call
+fails, this raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(PKG, "libwavesolve_b200.so")
+
+_lib = None
+
+c_i32p = C.c_void_p   # device pointers travel as integers
+c_f64p = C.c_void_p
+c_i64 = C.c_int64
+c_int = C.c_int
+c_vp = C.c_void_p
+
+_SIGNATURES = {
+    "ws_version": (c_int, []),
+    "ws_last_error": (C.c_char_p, []),
+    "ws_launch_count": (C.c_longlong, []),
+    "ws_edges_first_appearance": (c_int, [c_vp, c_i64, c_i64, c_vp, c_vp, C.POINTER(c_i64), c_int, c_vp]),
+    "ws_pattern_create": (c_int, [c_vp, c_i64, c_i64, C.POINTER(c_vp), c_int, c_vp]),
+    "ws_pattern_query": (c_int, [c_vp, C.POINTER(c_i64), C.POINTER(c_i64), C.POINTER(c_i64)]),
+    "ws_pattern_export": (c_int, [c_vp, c_vp, c_vp, c_int, c_vp]),
+    "ws_pattern_arrays": (c_int, [c_vp, C.POINTER(c_vp), C.POINTER(c_vp)]),
+    "ws_pattern_destroy": (c_int, [c_vp]),
+    "ws_assemble_scalar_p2": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_vp]),
+    "ws_assemble_mass_p2": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_vp]),
+    "ws_assemble_vector_p1": (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_int, c_int, c_vp]),
+    "ws_prune_zeros": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, C.POINTER(c_i64), c_int, c_vp]),
+    "ws_axpby": (c_int, [c_i64, C.c_double, c_vp, C.c_double, c_vp, c_int, c_vp]),
+    "ws_spmv": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_vp]),
+}
+
+
+class WavesolveB200Error(RuntimeError):
+    pass
+
+
+def lib():
+    """Load the library once.  Raises if it has not been built (no fallback path exists)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise WavesolveB200Error(
+                "%s is missing: build it with `python -m wavesolve_b200._build` "
+                "(or __graft_entry__.build()); wavesolve_b200 has no CPU fallback" % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(L, name)     # AttributeError if the ABI lost a symbol
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        msg = lib().ws_last_error()
+        raise WavesolveB200Error("wavesolve_b200 C-ABI call failed (%d): %s"
+                                 % (rc, msg.decode(errors="replace") if msg else "?"))
+
+
+def launch_count() -> int:
+    return int(lib().ws_launch_count())

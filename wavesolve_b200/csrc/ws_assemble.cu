@@ -1,0 +1,328 @@
+// K3 / K4: FEM element integration + assembly into the CSR pattern, fp64.
+//
+// Design (B200-first, not the reference's COO-triplet flow): the matrix is assembled by
+// ROWS.  The pattern object holds, for every matrix row, the list of (element, local index)
+// incidences sorted by element -- the reference's summation order -- and the position of
+// each of the element's six columns inside that row.  One thread owns one row, computes for
+// each incident element only the row of the 6x6 element matrices it needs, and accumulates
+// into a shared-memory tile that covers the CTA's contiguous slot range; the tile is then
+// written with coalesced 8-byte stores.  Every output value is written exactly once, there
+// are no atomics and no zero-fill pass, and the result is deterministic.
+//
+// Arithmetic follows the reference expression by expression (same association, true
+// divisions, separate multiply and subtract: this file is compiled with -fmad=false), so
+// element entries are bit-identical to numpy's and only the order in which scipy sums
+// duplicates can differ (scalar path); the vector path sums in the reference's element
+// order and reproduces the entries that cancel to exactly 0.0.
+//
+//   scalar P2 : shape_funcs.py:192-246 (compute_NN_dNdN_vec), fe_solver.py:51-54
+//   vector    : shape_funcs.py:310-428 (precompute, computeL_*), fe_solver.py:196-199
+#include "ws_common.cuh"
+
+namespace ws {
+
+constexpr int ROWS_PER_CTA = 128;
+constexpr int TILE_CAP = 3072;  // slots per CTA tile in shared memory (A and B: 48 KB -> 4 CTAs / SM);
+                                // denser row blocks fall back to accumulating in global memory
+
+struct RowCtx {
+    const int32_t* rowptr;
+    const int32_t* incptr;
+    const uint32_t* inc;
+    const uint16_t* pos;
+    int64_t N;
+};
+
+// ---- scalar P2 ---------------------------------------------------------------------------
+// Row `a` of the element matrices, using the cyclic symmetry of the P2 triangle: rotate the
+// vertices so that the row becomes row 0 (vertex) or row 3 (mid-side).  Rotation only negates
+// or renames the coordinate differences, and round-to-nearest is sign-symmetric, so each
+// entry has the same bits as the reference's un-rotated formula.  J is taken from the
+// un-rotated vertices (shape_funcs.py:202).
+struct ScalarP2 {
+    const double2* xy;
+    const int32_t* dofs;
+    const double* k2n2;   // nullptr -> mass only
+
+    __device__ __forceinline__ void row(uint32_t e, int a, double (&Av)[6], double (&Bv)[6], int (&cb)[6]) const {
+        const int32_t* d = dofs + (int64_t)e * 6;
+        double2 P0 = xy[d[0]], P1 = xy[d[1]], P2 = xy[d[2]];
+        const double J = (P1.x - P0.x) * (P2.y - P0.y) - (P2.x - P0.x) * (P1.y - P0.y);
+        const int rot = a < 3 ? a : a - 3;
+        if (rot == 1) { double2 t = P0; P0 = P1; P1 = P2; P2 = t; }
+        else if (rot == 2) { double2 t = P0; P0 = P2; P2 = P1; P1 = t; }
+        const double x21 = P1.x - P0.x, y21 = P1.y - P0.y;
+        const double x31 = P2.x - P0.x, y31 = P2.y - P0.y;
+        const double x32 = P2.x - P1.x, y32 = P2.y - P1.y;
+        // new-local column j -> original local column
+        const int r1 = rot == 2 ? 0 : rot + 1, r2 = rot == 0 ? 2 : rot - 1;
+        cb[0] = rot; cb[1] = r1; cb[2] = r2; cb[3] = 3 + rot; cb[4] = 3 + r1; cb[5] = 3 + r2;
+        double K[6], M[6];
+        if (a < 3) {
+            const double s01 = y32 * y31 + x32 * x31;
+            const double s02 = y21 * y32 + x21 * x32;
+            K[0] = (y32 * y32 + x32 * x32) / (2 * J);
+            K[1] = s01 / (6 * J);
+            K[2] = (-y21 * y32 - x21 * x32) / (6 * J);
+            K[3] = -2 * s01 / (3 * J);
+            K[4] = 0.0;
+            K[5] = 2 * s02 / (3 * J);
+            M[0] = J / 60;
+            M[1] = M[2] = -J / 360;
+            M[3] = M[5] = 0.0;
+            M[4] = -J / 90;
+        } else {
+            const double f = 4 / (3 * J);
+            const double s01 = y32 * y31 + x32 * x31;
+            K[0] = K[1] = -2 * s01 / (3 * J);
+            K[2] = 0.0;
+            K[3] = f * (y32 * y32 + y31 * y21 + x32 * x32 + x31 * x21);
+            K[4] = f * (y21 * y32 + x21 * x32);
+            K[5] = -f * (y31 * y21 + x31 * x21);
+            M[0] = M[1] = 0.0;
+            M[2] = -J / 90;
+            M[3] = 4 * J / 45;
+            M[4] = M[5] = 2 * J / 45;
+        }
+        if (k2n2) {
+            const double c = k2n2[e];
+#pragma unroll
+            for (int j = 0; j < 6; ++j) Av[j] = __dsub_rn(__dmul_rn(c, M[j]), K[j]);   // fe_solver.py:51
+        }
+#pragma unroll
+        for (int j = 0; j < 6; ++j) Bv[j] = M[j];                                        // fe_solver.py:54
+    }
+};
+
+// ---- vector: Whitney edge elements + P1 nodes ---------------------------------------------
+struct VectorP1 {
+    const double2* xy;
+    const int32_t* tris;
+    const double* k2n2;
+    int transpose;
+
+    __device__ __forceinline__ void row(uint32_t e, int a, double (&Av)[6], double (&Bv)[6], int (&cb)[6]) const {
+        const int32_t* t = tris + (int64_t)e * 3;
+        const int32_t t0 = t[0], t1 = t[1], t2 = t[2];
+        const double2 P0 = xy[t0], P1 = xy[t1], P2 = xy[t2];
+        const double x21 = P1.x - P0.x, y21 = P1.y - P0.y;          // shape_funcs.py:311-316
+        const double x31 = P2.x - P0.x, y31 = P2.y - P0.y;
+        const double x32 = P2.x - P1.x, y32 = P2.y - P1.y;
+        const double s1 = t0 < t1 ? 1.0 : -1.0;                      // shape_funcs.py:317-319
+        const double s2 = t1 < t2 ? 1.0 : -1.0;
+        const double s3 = t2 < t0 ? 1.0 : -1.0;
+        const double J = x21 * y31 - x31 * y21;                      // shape_funcs.py:323
+#pragma unroll
+        for (int j = 0; j < 6; ++j) { cb[j] = j; Av[j] = 0.0; Bv[j] = 0.0; }
+        const double c = k2n2[e];
+        const double xx = x21 * x31, yy = y21 * y31;
+        if (a < 3) {
+            const double l12 = sqrt(x21 * x21 + y21 * y21) * s1;     // shape_funcs.py:320-322
+            const double l23 = sqrt(x32 * x32 + y32 * y32) * s2;
+            const double l31 = sqrt(x31 * x31 + y31 * y31) * s3;
+            const double sq12 = l12 * l12, sq23 = l23 * l23, sq31 = l31 * l31;
+            const double x3 = (3 * x21) * x31, y3 = (3 * y21) * y31;
+            const double J12 = 12 * J, J6 = 6 * J, tJ = 2 / J;
+            double E[3], C[3], D[3];
+            if (a == 0) {
+                E[0] = sq12 * (sq12 - x3 + 3 * sq31 - y3) / J12;                  // :369
+                E[1] = l12 * l23 * (sq12 - xx - sq31 - yy) / J12;                 // :372
+                E[2] = l31 * l12 * (-sq12 + x3 - sq31 + y3) / J12;                // :374
+                D[0] = l12 * (-sq12 + x3 - 2 * sq31 + y3) / J6;                   // :393
+                D[1] = l12 * (-xx + 2 * sq31 - yy) / J6;                          // :396
+                D[2] = l12 * (sq12 - 2 * xx - 2 * yy) / J6;                       // :401
+            } else if (a == 1) {
+                E[0] = l12 * l23 * (sq12 - xx - sq31 - yy) / J12;                 // :372
+                E[1] = sq23 * (sq12 + xx + sq31 + yy) / J12;                      // :370
+                E[2] = l23 * l31 * (-sq12 - xx + sq31 - yy) / J12;                // :373
+                D[0] = l23 * (-sq12 + sq31) / J6;                                 // :397
+                D[1] = l23 * (-xx - sq31 - yy) / J6;                              // :394
+                D[2] = l23 * (sq12 + xx + yy) / J6;                               // :398
+            } else {
+                E[0] = l31 * l12 * (-sq12 + x3 - sq31 + y3) / J12;                // :374
+                E[1] = l23 * l31 * (-sq12 - xx + sq31 - yy) / J12;                // :373
+                E[2] = sq31 * (3 * sq12 - x3 + sq31 - y3) / J12;                  // :371
+                D[0] = l31 * (2 * sq12 - x3 + sq31 - y3) / J6;                    // :400
+                D[1] = l31 * (2 * xx + 2 * yy - sq31) / J6;                       // :399
+                D[2] = l31 * (-2 * sq12 + xx + yy) / J6;                          // :395
+            }
+            const double la = a == 0 ? l12 : (a == 1 ? l23 : l31);
+            const double lj[3] = {l12, l23, l31};
+#pragma unroll
+            for (int j = 0; j < 3; ++j)                                           // :382-383
+                C[j] = transpose ? (tJ * lj[j]) * la : (tJ * la) * lj[j];
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                Av[j] = __dsub_rn(__dmul_rn(c, E[j]), C[j]);                      // fe_solver.py:196
+                Bv[j] = E[j];                                                     // fe_solver.py:197
+                Bv[3 + j] = D[j];                                                 // fe_solver.py:198
+            }
+        } else {
+            const int i = a - 3;
+            // squared lengths as the reference forms them: (sqrt(.) * s)**2
+            const double l12 = sqrt(x21 * x21 + y21 * y21) * s1;
+            const double l31 = sqrt(x31 * x31 + y31 * y31) * s3;
+            const double sq12 = l12 * l12, sq31 = l31 * l31;
+            const double J6 = 6 * J, J2 = 2 * J;
+            double Dt[3], G[3];
+            const double Nd = J / 12, No = J / 24;                                // :410-411
+            if (i == 0) {
+                const double l23 = sqrt(x32 * x32 + y32 * y32) * s2;
+                const double x3 = (3 * x21) * x31, y3 = (3 * y21) * y31;
+                Dt[0] = l12 * (-sq12 + x3 - 2 * sq31 + y3) / J6;                  // D00 :393
+                Dt[1] = l23 * (-sq12 + sq31) / J6;                                // D10 :397
+                Dt[2] = l31 * (2 * sq12 - x3 + sq31 - y3) / J6;                   // D20 :400
+                G[0] = (sq12 + sq31 - 2 * xx - 2 * yy) / J2;                      // :421
+                G[1] = (-sq31 + xx + yy) / J2;                                    // :424
+                G[2] = (-sq12 + xx + yy) / J2;                                    // :426
+            } else if (i == 1) {
+                const double l23 = sqrt(x32 * x32 + y32 * y32) * s2;
+                Dt[0] = l12 * (-xx + 2 * sq31 - yy) / J6;                         // D01 :396
+                Dt[1] = l23 * (-xx - sq31 - yy) / J6;                             // D11 :394
+                Dt[2] = l31 * (2 * xx + 2 * yy - sq31) / J6;                      // D21 :399
+                G[0] = (-sq31 + xx + yy) / J2;                                    // :424
+                G[1] = sq31 / J2;                                                 // :422
+                G[2] = (-xx - yy) / J2;                                           // :425
+            } else {
+                const double l23 = sqrt(x32 * x32 + y32 * y32) * s2;
+                Dt[0] = l12 * (sq12 - 2 * xx - 2 * yy) / J6;                      // D02 :401
+                Dt[1] = l23 * (sq12 + xx + yy) / J6;                              // D12 :398
+                Dt[2] = l31 * (-2 * sq12 + xx + yy) / J6;                         // D22 :395
+                G[0] = (-sq12 + xx + yy) / J2;                                    // :426
+                G[1] = (-xx - yy) / J2;                                           // :425
+                G[2] = sq12 / J2;                                                 // :423
+            }
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                Bv[j] = Dt[j];                                                    // fe_solver.py:209
+                Bv[3 + j] = __dsub_rn(G[j], __dmul_rn(c, j == i ? Nd : No));      // fe_solver.py:199
+            }
+        }
+    }
+};
+
+template <class Op, bool WRITE_A>
+__global__ void __launch_bounds__(ROWS_PER_CTA)
+k_assemble_rows(RowCtx cx, Op op, double* __restrict__ A, double* __restrict__ B) {
+    extern __shared__ double tile[];
+    const int64_t r0 = (int64_t)blockIdx.x * ROWS_PER_CTA;
+    const int64_t r1 = min(r0 + ROWS_PER_CTA, cx.N);
+    const int s0 = cx.rowptr[r0], s1 = cx.rowptr[r1];
+    const int S = s1 - s0;
+    const bool in_smem = S <= TILE_CAP;
+    double* tB = in_smem ? tile : B + s0;
+    double* tA = in_smem ? tile + TILE_CAP : (WRITE_A ? A + s0 : nullptr);
+    for (int t = threadIdx.x; t < S; t += ROWS_PER_CTA) {
+        tB[t] = 0.0;
+        if (WRITE_A) tA[t] = 0.0;
+    }
+    __syncthreads();   // (global fallback: the zero-fill above is visible CTA-wide after the barrier)
+    const int64_t r = r0 + threadIdx.x;
+    if (r < r1) {
+        const int base = cx.rowptr[r] - s0;
+        const int i0 = cx.incptr[r], i1 = cx.incptr[r + 1];
+        for (int i = i0; i < i1; ++i) {
+            const uint32_t u = cx.inc[i];
+            double Av[6], Bv[6];
+            int cb[6];
+            op.row(u >> 3, (int)(u & 7u), Av, Bv, cb);
+            const uint16_t* p = cx.pos + (int64_t)i * 6;
+#pragma unroll
+            for (int j = 0; j < 6; ++j) {
+                const int q = base + p[cb[j]];
+                tB[q] += Bv[j];
+                if (WRITE_A) tA[q] += Av[j];
+            }
+        }
+    }
+    if (in_smem) {
+        __syncthreads();
+        for (int t = threadIdx.x; t < S; t += ROWS_PER_CTA) {
+            B[s0 + t] = tB[t];
+            if (WRITE_A) A[s0 + t] = tA[t];
+        }
+    }
+}
+
+template <class Op, bool WRITE_A>
+static void launch_rows(const ws_pattern* p, const Op& op, double* A, double* B, cudaStream_t st) {
+    if (p->N == 0 || p->nnz == 0) return;
+    RowCtx cx{p->rowptr.get(), p->incptr.get(), p->inc.get(), p->pos.get(), p->N};
+    size_t smem = (size_t)TILE_CAP * 8 * (WRITE_A ? 2 : 1);
+    auto kern = k_assemble_rows<Op, WRITE_A>;
+    static bool configured = false;
+    if (!configured) {
+        WS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    kern<<<ceil_div(p->N, ROWS_PER_CTA), ROWS_PER_CTA, smem, st>>>(cx, op, A, B);
+    WS_CUDA(cudaGetLastError());
+    count_launch(1);
+}
+
+__global__ void k_axpby(int64_t n, double alpha, const double* __restrict__ x, double beta, double* __restrict__ y) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) y[i] = __dadd_rn(__dmul_rn(alpha, x[i]), __dmul_rn(beta, y[i]));
+}
+
+}  // namespace ws
+
+using namespace ws;
+
+extern "C" {
+
+int ws_assemble_scalar_p2(const ws_pattern* p, const double* xy, const int32_t* dofs,
+                          const double* elem_k2n2, double* A_vals, double* B_vals, int transpose,
+                          int device, void* stream) {
+    WS_API_BEGIN
+    (void)transpose;   // P2 scalar element matrices are bit-symmetric
+    WS_REQUIRE(p, "pattern == NULL");
+    if (p->nnz == 0) return WS_OK;
+    WS_REQUIRE(xy && dofs && elem_k2n2 && A_vals && B_vals, "null pointer");
+    DeviceGuard g(device);
+    ScalarP2 op{(const double2*)xy, dofs, elem_k2n2};
+    launch_rows<ScalarP2, true>(p, op, A_vals, B_vals, (cudaStream_t)stream);
+    WS_API_END
+}
+
+int ws_assemble_mass_p2(const ws_pattern* p, const double* xy, const int32_t* dofs, double* B_vals,
+                        int device, void* stream) {
+    WS_API_BEGIN
+    WS_REQUIRE(p, "pattern == NULL");
+    if (p->nnz == 0) return WS_OK;
+    WS_REQUIRE(xy && dofs && B_vals, "null pointer");
+    DeviceGuard g(device);
+    ScalarP2 op{(const double2*)xy, dofs, nullptr};
+    launch_rows<ScalarP2, false>(p, op, nullptr, B_vals, (cudaStream_t)stream);
+    WS_API_END
+}
+
+int ws_assemble_vector_p1(const ws_pattern* p, const double* xy, const int32_t* tris,
+                          const double* elem_k2n2, int64_t Ntt, double* A_vals, double* B_vals,
+                          int transpose, int device, void* stream) {
+    WS_API_BEGIN
+    WS_REQUIRE(p, "pattern == NULL");
+    WS_REQUIRE(Ntt >= 0 && Ntt <= p->N, "0 <= Ntt <= N");
+    if (p->nnz == 0) return WS_OK;
+    WS_REQUIRE(xy && tris && elem_k2n2 && A_vals && B_vals, "null pointer");
+    DeviceGuard g(device);
+    VectorP1 op{(const double2*)xy, tris, elem_k2n2, transpose};
+    launch_rows<VectorP1, true>(p, op, A_vals, B_vals, (cudaStream_t)stream);
+    WS_API_END
+}
+
+int ws_axpby(int64_t n, double alpha, const double* x, double beta, double* y, int device, void* stream) {
+    WS_API_BEGIN
+    WS_REQUIRE(n >= 0, "n >= 0");
+    if (n == 0) return WS_OK;
+    WS_REQUIRE(x && y, "null pointer");
+    DeviceGuard g(device);
+    int blocks = (int)std::min<int64_t>((n + 255) / 256, (int64_t)kNumSMs * 16);
+    k_axpby<<<blocks, 256, 0, (cudaStream_t)stream>>>(n, alpha, x, beta, y);
+    WS_CUDA(cudaGetLastError());
+    count_launch(1);
+    WS_API_END
+}
+
+}  // extern "C"

@@ -1,0 +1,129 @@
+// Shared helpers for the wavesolve_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdio>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/wavesolve_b200.h"
+
+namespace ws {
+
+constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
+
+struct Error : std::runtime_error {
+    int code;
+    Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+void set_last_error(const std::string& s);
+
+#define WS_CUDA(call)                                                                        \
+    do {                                                                                     \
+        cudaError_t e__ = (call);                                                            \
+        if (e__ != cudaSuccess) {                                                            \
+            char buf__[512];                                                                 \
+            snprintf(buf__, sizeof buf__, "%s:%d: %s -> %s", __FILE__, __LINE__, #call,      \
+                     cudaGetErrorString(e__));                                               \
+            throw ws::Error(WS_ERR_CUDA, buf__);                                             \
+        }                                                                                    \
+    } while (0)
+
+#define WS_REQUIRE(cond, msg)                                                                \
+    do {                                                                                     \
+        if (!(cond)) throw ws::Error(WS_ERR_ARG, std::string("argument error: ") + (msg));   \
+    } while (0)
+
+#define WS_API_BEGIN try {
+#define WS_API_END                                                                           \
+    }                                                                                        \
+    catch (const ws::Error& e) {                                                             \
+        ws::set_last_error(e.what());                                                        \
+        return e.code;                                                                       \
+    }                                                                                        \
+    catch (const std::exception& e) {                                                        \
+        ws::set_last_error(e.what());                                                        \
+        return WS_ERR_CUDA;                                                                  \
+    }                                                                                        \
+    catch (...) {                                                                            \
+        ws::set_last_error("unknown exception");                                             \
+        return WS_ERR_CUDA;                                                                  \
+    }                                                                                        \
+    return WS_OK;
+
+// Stream-ordered device buffer (cudaMallocAsync: no implicit device synchronisation).
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    cudaStream_t st = nullptr;
+    DevBuf() = default;
+    DevBuf(size_t n_, cudaStream_t s) { alloc(n_, s); }
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n), st(o.st) { o.p = nullptr; o.n = 0; }
+    DevBuf& operator=(DevBuf&& o) noexcept {
+        if (this != &o) {
+            release();
+            p = o.p; n = o.n; st = o.st;
+            o.p = nullptr; o.n = 0;
+        }
+        return *this;
+    }
+    void alloc(size_t n_, cudaStream_t s) {
+        release();
+        n = n_;
+        st = s;
+        if (n) WS_CUDA(cudaMallocAsync((void**)&p, n * sizeof(T), s));
+    }
+    void release() {
+        if (p) cudaFreeAsync(p, st);
+        p = nullptr;
+        n = 0;
+    }
+    ~DevBuf() { release(); }
+    T* get() const { return p; }
+    size_t bytes() const { return n * sizeof(T); }
+};
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        WS_CUDA(cudaGetDevice(&prev));
+        if (dev != prev) WS_CUDA(cudaSetDevice(dev));
+        else prev = -1;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// global launch counter (bench.py reports how many of OUR kernels ran in the timed region)
+void count_launch(int n = 1);
+
+}  // namespace ws
+
+// ---------------------------------------------------------------------------------------
+// pattern object shared by the assembly / SpMV / solver translation units
+// ---------------------------------------------------------------------------------------
+struct ws_pattern {
+    int device = 0;
+    int64_t N = 0;     // rows
+    int64_t Ne = 0;    // elements (as assembled, material-major, duplicates allowed)
+    int64_t nnz = 0;
+    int max_row_len = 0;
+    ws::DevBuf<int32_t> rowptr;   // [N+1]
+    ws::DevBuf<int32_t> colidx;   // [nnz]
+    // row-incidence lists: for row r, entries incptr[r]..incptr[r+1] of inc[] hold
+    // (element << 3 | local index a), sorted by element (= reference summation order);
+    // pos[6*i + b] is the position inside row r of column dofs[e*6+b].
+    ws::DevBuf<int32_t> incptr;   // [N+1]
+    ws::DevBuf<uint32_t> inc;     // [6*Ne]
+    ws::DevBuf<uint16_t> pos;     // [36*Ne]
+};

@@ -1,0 +1,43 @@
+"""Host <-> device plumbing (PyTorch is used for device memory and streams only)."""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+def require_cuda(device=None) -> torch.device:
+    if not torch.cuda.is_available():
+        raise _lib.WavesolveB200Error(
+            "wavesolve_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    if device is None:
+        return torch.device("cuda", torch.cuda.current_device())
+    d = torch.device(device)
+    if d.type != "cuda":
+        raise _lib.WavesolveB200Error("device must be a CUDA device, got %r" % (device,))
+    if d.index is None:
+        d = torch.device("cuda", torch.cuda.current_device())
+    return d
+
+
+def stream_ptr(dev: torch.device) -> int:
+    return torch.cuda.current_stream(dev).cuda_stream
+
+
+def h2d(arr: np.ndarray, dev: torch.device) -> torch.Tensor:
+    """Pinned staging + async copy on the current stream."""
+    t = torch.from_numpy(np.ascontiguousarray(arr))
+    if t.numel() == 0:
+        return torch.empty(t.shape, dtype=t.dtype, device=dev)
+    return t.pin_memory().to(dev, non_blocking=True)
+
+
+def d2h(t: torch.Tensor) -> np.ndarray:
+    return t.detach().cpu().numpy()
+
+
+def ptr(t) -> int:
+    if t is None:
+        return 0
+    return t.data_ptr() if t.numel() else 0

@@ -1,0 +1,49 @@
+"""Drop-in for the hot-path function of reference ``waveguide.py``: ``get_unique_edges``."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib, device as _dev
+
+
+def unique_edges_device(tris_d: torch.Tensor, num_points: int):
+    """Device-side K1.  tris_d: (Ne,3) int32 CUDA tensor.  Returns (edges (Ntt,2) int32,
+    edge_indices (Ne,3) int32) CUDA tensors."""
+    dev = tris_d.device
+    ne = tris_d.shape[0]
+    edges = torch.empty((3 * ne, 2), dtype=torch.int32, device=dev)
+    eidx = torch.empty((ne, 3), dtype=torch.int32, device=dev)
+    ntt = C.c_int64(0)
+    L = _lib.lib()
+    _lib.check(L.ws_edges_first_appearance(_dev.ptr(tris_d), ne, int(num_points), _dev.ptr(edges),
+                                           _dev.ptr(eidx), C.byref(ntt), dev.index, _dev.stream_ptr(dev)))
+    return edges[: ntt.value], eidx
+
+
+def get_unique_edges(mesh, mutate=True, device=None):
+    """Reference ``waveguide.get_unique_edges`` (waveguide.py:10-43): unique edges numbered by
+    first appearance, per-triangle edge ids; with ``mutate`` the mesh gains ``cells[0].data``,
+    ``edge_indices`` (uint), ``edge_flips``, ``num_edges`` and ``num_points``.
+    The O(E^2) list scan is replaced by a device sort/unique/rank (csrc/ws_pattern.cu)."""
+    dev = _dev.require_cuda(device)
+    tris = np.asarray(mesh.cells[1].data)
+    if tris.size and int(tris[:, :3].max()) >= 2 ** 31:
+        raise ValueError("vertex ids must fit in int32")
+    t32 = np.ascontiguousarray(tris[:, :3].astype(np.int32))
+    with torch.cuda.device(dev):
+        td = _dev.h2d(t32, dev)
+        npts = int(t32.max()) + 1 if t32.size else 0
+        edges_d, eidx_d = unique_edges_device(td, max(npts, mesh.points.shape[0]))
+        edges = _dev.d2h(edges_d).astype(tris.dtype if tris.size else np.int64)
+        edge_indices = _dev.d2h(eidx_d).astype(np.uint)             # waveguide.py:16
+    if mutate:
+        loc = tris[:, [0, 1, 1, 2, 2, 0]].reshape(-1, 3, 2)
+        mesh.cells[0].data = edges                                  # waveguide.py:38-42
+        mesh.edge_indices = edge_indices
+        mesh.edge_flips = np.where(loc[..., 0] <= loc[..., 1], 1.0, -1.0)
+        mesh.num_edges = len(edges)
+        mesh.num_points = mesh.points.shape[0]
+    return edges, edge_indices
