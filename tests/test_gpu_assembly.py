@@ -171,8 +171,6 @@ def test_full_size_properties_vector_1M(ws):
     assert np.all(edges[:, 0] < edges[:, 1])
     # first-appearance numbering: ids are introduced in increasing order along the scan
     flat = eidx.astype(np.int64).ravel()
-    first = np.full(len(edges), -1, dtype=np.int64)
-    np.minimum.at(first, flat[::-1], np.arange(len(flat))[::-1])  # last write wins -> smallest index
     first = np.full(len(edges), len(flat), dtype=np.int64)
     np.minimum.at(first, flat, np.arange(len(flat)))
     assert np.all(np.diff(first) > 0)
@@ -188,8 +186,8 @@ def test_full_size_properties_vector_1M(ws):
     A1, B1 = ws.construct_AB_vec(mesh, one_ior, k, sparse=True)
     Ktt = (k ** 2) * B1[:Ntt, :Ntt] - A1[:Ntt, :Ntt]      # = curl-curl block
     phi = np.sin(0.3 * mesh.points[:, 0]) * np.cos(0.2 * mesh.points[:, 1])
-    # Whitney dof of grad(phi) on edge (a,b), a<b, with the reference's signed lengths:
-    # tangential integral scaled by 1/length => (phi_b - phi_a)/len * len ... use the discrete gradient
+    # Whitney dof of grad(phi) on edge (a,b), a<b (signed lengths, shape_funcs.py:317-322) is
+    # the tangential component of the piecewise-constant gradient: (phi_b - phi_a) / length
     lens = np.linalg.norm(mesh.points[edges[:, 1], :2] - mesh.points[edges[:, 0], :2], axis=1)
     g = (phi[edges[:, 1]] - phi[edges[:, 0]]) / lens
     r = Ktt @ g
