@@ -49,8 +49,8 @@ extern "C" {
 #define WS_ERR_NOCONV 3
 
 typedef struct ws_pattern ws_pattern; /* CSR pattern + row-incidence lists of one mesh   */
+typedef struct ws_symbolic ws_symbolic; /* host: nested-dissection ordering + front tree     */
 typedef struct ws_solver ws_solver;   /* multifrontal LDL^T of A - sigma B               */
-typedef struct ws_eig ws_eig;         /* Krylov eigensolver workspace                    */
 
 int ws_version(void);
 const char* ws_last_error(void);
@@ -113,6 +113,24 @@ int ws_axpby(int64_t n, double alpha, const double* x, double beta, double* y, i
 /* ---- K5: y = CSR(pattern, vals) * x --------------------------------------------------- */
 int ws_spmv(const ws_pattern* p, const double* vals, const double* x, double* y, int device,
             void* stream);
+
+/* ---- K8a: symbolic analysis of the sparse factorisation (host) ---------------------------
+ * Replaces the COLAMD ordering + symbolic phase of SuperLU inside scipy splu / spsolve
+ * (fe_solver.py:328 through eigsh sigma mode, fe_solver.py:398).  Element-based geometric
+ * nested dissection: h_dofs [Ne*6] as for ws_pattern_create, h_elem_xy [Ne*2] element
+ * centroids (both HOST arrays).  Unknowns with id >= first_class_start are eliminated first
+ * inside every front (vector problem: pass Ntt so nodes precede edges; scalar: pass 0).
+ * The result depends on the mesh only and is reusable across wavelengths and shifts.
+ * ws_symbolic_query: h_info[8] = N, depth, nfronts, nnz(L), sum q^2, max front, max pivot
+ * block, sum q;  h_dinfo[4] = factor flops, seconds k-d, seconds ordering, seconds boundaries.
+ * ws_symbolic_export: perm [N] (new -> old), p,q,start [nfronts] (heap ids, 0 unused),
+ * bndoff [nfronts+1], bnd / rel [sum q]. Any output pointer may be NULL.                  */
+int ws_symbolic_create(const int32_t* h_dofs, int64_t Ne, int64_t N, const double* h_elem_xy,
+                       int64_t first_class_start, int leaf_elems, ws_symbolic** out);
+int ws_symbolic_query(const ws_symbolic* s, int64_t* h_info, double* h_dinfo);
+int ws_symbolic_export(const ws_symbolic* s, int32_t* h_perm, int32_t* h_p, int32_t* h_q,
+                       int64_t* h_start, int64_t* h_bndoff, int32_t* h_bnd, int32_t* h_rel);
+int ws_symbolic_destroy(ws_symbolic* s);
 
 #ifdef __cplusplus
 }

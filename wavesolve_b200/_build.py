@@ -20,6 +20,7 @@ SOURCES = {
     "ws_pattern.cu": [],
     "ws_assemble.cu": ["-fmad=false"],
     "ws_spmv.cu": [],
+    "ws_symbolic.cu": [],
 }
 
 

@@ -1,0 +1,56 @@
+"""Python handles for the sparse direct solver (symbolic analysis on the host, numeric
+factorisation and solves on the device) and the Krylov eigensolver."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+DEFAULT_LEAF_ELEMS = 48
+
+
+class Symbolic:
+    """Host-side nested-dissection analysis (``ws_symbolic``)."""
+
+    def __init__(self, dofs: np.ndarray, elem_xy: np.ndarray, N: int, first_class_start: int = 0,
+                 leaf_elems: int = DEFAULT_LEAF_ELEMS):
+        dofs = np.ascontiguousarray(dofs, dtype=np.int32)
+        elem_xy = np.ascontiguousarray(elem_xy, dtype=np.float64)
+        assert dofs.ndim == 2 and dofs.shape[1] == 6 and elem_xy.shape == (dofs.shape[0], 2)
+        h = C.c_void_p()
+        _lib.check(_lib.lib().ws_symbolic_create(dofs.ctypes.data, dofs.shape[0], int(N),
+                                                 elem_xy.ctypes.data, int(first_class_start),
+                                                 int(leaf_elems), C.byref(h)))
+        self.handle = h
+        info = np.zeros(8, dtype=np.int64)
+        dinfo = np.zeros(4, dtype=np.float64)
+        _lib.check(_lib.lib().ws_symbolic_query(h, info.ctypes.data, dinfo.ctypes.data))
+        (self.N, self.depth, self.nfronts, self.nnzL, self.Utotal, self.maxfront, self.maxp,
+         self.sumq) = [int(x) for x in info]
+        self.flops, self.t_kd, self.t_order, self.t_bnd = [float(x) for x in dinfo]
+
+    def export(self):
+        perm = np.zeros(self.N, dtype=np.int32)
+        p = np.zeros(self.nfronts, dtype=np.int32)
+        q = np.zeros(self.nfronts, dtype=np.int32)
+        start = np.zeros(self.nfronts, dtype=np.int64)
+        bndoff = np.zeros(self.nfronts + 1, dtype=np.int64)
+        bnd = np.zeros(self.sumq, dtype=np.int32)
+        rel = np.zeros(self.sumq, dtype=np.int32)
+        _lib.check(_lib.lib().ws_symbolic_export(self.handle, perm.ctypes.data, p.ctypes.data,
+                                                 q.ctypes.data, start.ctypes.data, bndoff.ctypes.data,
+                                                 bnd.ctypes.data, rel.ctypes.data))
+        return dict(perm=perm, p=p, q=q, start=start, bndoff=bndoff, bnd=bnd, rel=rel)
+
+    def close(self):
+        if self.handle is not None and self.handle.value:
+            _lib.lib().ws_symbolic_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
