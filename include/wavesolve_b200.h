@@ -132,6 +132,40 @@ int ws_symbolic_export(const ws_symbolic* s, int32_t* h_perm, int32_t* h_p, int3
                        int64_t* h_start, int64_t* h_bndoff, int32_t* h_bnd, int32_t* h_rel);
 int ws_symbolic_destroy(ws_symbolic* s);
 
+/* ---- K8b: numeric factorisation and solves (device) ----------------------------------------
+ * ws_solver_create : binds a pattern to a symbolic analysis, allocates all fronts (they stay
+ *                    resident; ~6 kB per unknown at 1M elements) and uploads the task plan.
+ * ws_solver_factor : M = A_vals - sigma*B_vals (values on the pattern; B_vals may be NULL for
+ *                    M = A_vals), multifrontal LDL^T without pivoting + selective inversion.
+ *                    Synchronises the stream once to read the pivot statistics; returns
+ *                    WS_ERR_NUMERIC on a zero / non-finite pivot.
+ * ws_solver_solve  : x = M^-1 b, nrhs right-hand sides stored contiguously [nrhs*N]; asynchronous.
+ * ws_solver_stats  : h_info[8] = nnz(L), fronts, max front, bytes, negative pivots, positive
+ *                    pivots, bad pivots, tree depth; h_dinfo[3] = factor flops, min |pivot|,
+ *                    max |pivot|.  (negative / positive pivots = inertia of M: Sylvester's law
+ *                    gives the number of eigenvalues of (A,B) above sigma.)                    */
+int ws_solver_create(const ws_pattern* p, const ws_symbolic* sym, ws_solver** out, int device,
+                     void* stream);
+int ws_solver_factor(ws_solver* s, const double* A_vals, const double* B_vals, double sigma,
+                     int device, void* stream);
+int ws_solver_solve(ws_solver* s, const double* b, double* x, int nrhs, int device, void* stream);
+int ws_solver_stats(const ws_solver* s, int64_t* h_info, double* h_dinfo);
+int ws_solver_destroy(ws_solver* s);
+
+/* ---- vector problem: quasi-definite form ---------------------------------------------------
+ * The vector shift-invert matrix M = A - sigma*B is indefinite with singular pivot blocks
+ * (curl-curl null space).  With G the discrete gradient (edge i = (lo,hi): G[i,hi] = 1/len_i,
+ * G[i,lo] = -1/len_i) and T = [[I,-G],[0,I]], M' = T^T M T is symmetric quasi-definite:
+ *     M' = [[ (k2n2-sigma) NeNe - curlcurl , -k2n2 NedN ], [ . , k2n2 (dNdN + sigma NN) ]]
+ * so LDL^T needs no pivoting, and M^-1 = T M'^-1 T^T.
+ * ws_assemble_vector_qd writes M' on the pattern; ws_vector_T applies T (mode 0) or T^T (mode 1).
+ * edges [Ntt*2] as produced by ws_edges_first_appearance.                                    */
+int ws_assemble_vector_qd(const ws_pattern* p, const double* xy, const int32_t* tris,
+                          const double* elem_k2n2, int64_t Ntt, double sigma, double* M_vals,
+                          int device, void* stream);
+int ws_vector_T(const ws_pattern* p, const int32_t* edges, const double* xy, int64_t Ntt, int mode,
+                const double* in, double* out, int device, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,109 @@
+"""GPU: the sparse direct solver (K8) through the C ABI -- factor + solve against scipy's
+SuperLU on the same matrices, pivot inertia, the quasi-definite form of the vector problem."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import scipy.sparse.linalg as spla
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+K0 = 2 * np.pi / 1.55
+
+
+@pytest.fixture(scope="module")
+def ws():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import wavesolve_b200
+    return wavesolve_b200
+
+
+def _csr(prob, vals):
+    indptr, indices = prob.pattern.export()
+    return sp.csr_matrix((vals.cpu().numpy(), indices.cpu().numpy(), indptr.cpu().numpy()), shape=(prob.N,) * 2)
+
+
+@pytest.mark.parametrize("ne,leaf,target", [(800, 16, None), (20000, 48, None), (60000, 48, None), (20000, 32, 1.447)])
+def test_scalar_factor_solve(ws, ne, leaf, target):
+    from wavesolve_b200 import fe_solver as fs, solver as sv
+    mg = ws.meshgen
+    mesh = mg.fiber_disc(ne, seed=3)
+    prob = fs.ScalarProblem(mesh, mg.FIBER_IOR, K0)
+    A, B = prob.assemble()
+    sigma = (K0 * (max(mg.FIBER_IOR.values()) if target is None else target)) ** 2
+    sym = sv.Symbolic(prob.h_dofs, prob.centroids(), prob.N, 0, leaf)
+    S = sv.Solver(prob.pattern, sym)
+    st = S.factor(A, B, sigma)
+    M = (_csr(prob, A) - sigma * _csr(prob, B)).tocsc()
+    rng = np.random.default_rng(0)
+    b = rng.standard_normal(prob.N)
+    x = S.solve(torch.from_numpy(b).cuda()).cpu().numpy()
+    res = np.linalg.norm(M @ x - b) / np.linalg.norm(b)
+    xr = spla.splu(M).solve(b)
+    assert res <= 1e-11, res
+    assert np.linalg.norm(x - xr) <= 1e-9 * np.linalg.norm(xr)
+    assert st["bad_pivots"] == 0 and st["neg_pivots"] + st["pos_pivots"] == prob.N
+    if target is None:
+        assert st["pos_pivots"] == 0          # sigma*B - A is SPD at the default shift
+    else:
+        # Sylvester: positive pivots = eigenvalues of (A,B) above sigma
+        w = spla.eigsh(_csr(prob, A), M=_csr(prob, B), k=6, which="SA", sigma=(K0 * 1.46) ** 2)[0]
+        assert st["pos_pivots"] == int((w > sigma).sum())
+    # two right-hand sides in one call
+    b2 = rng.standard_normal((2, prob.N))
+    x2 = S.solve(torch.from_numpy(b2).cuda()).cpu().numpy()
+    for i in range(2):
+        assert np.linalg.norm(M @ x2[i] - b2[i]) <= 1e-11 * np.linalg.norm(b2[i])
+
+
+@pytest.mark.parametrize("gen,arg,target", [("fiber_disc", 20000, None), ("structured_square", 60, None),
+                                            ("fiber_disc", 20000, 1.448)])
+def test_vector_quasidefinite_factor_solve(ws, gen, arg, target):
+    from wavesolve_b200 import fe_solver as fs, solver as sv
+    mg = ws.meshgen
+    mesh = getattr(mg, gen)(arg, order=1)
+    ws.get_unique_edges(mesh)
+    prob = fs.VectorProblem(mesh, mg.FIBER_IOR, K0)
+    A, B = prob.assemble()
+    sigma = (K0 * (max(mg.FIBER_IOR.values()) if target is None else target)) ** 2
+    Am, Bm = _csr(prob, A), _csr(prob, B)
+    M = (Am - sigma * Bm).tocsc()
+    Ntt, N = prob.Ntt, prob.N
+    # the closed-form quasi-definite matrix equals T^T M T
+    edges = prob.h_edges.astype(np.int64)
+    L = np.linalg.norm(prob.h_xy[edges[:, 1]] - prob.h_xy[edges[:, 0]], axis=1)
+    G = sp.csr_matrix((np.r_[1 / L, -1 / L], (np.r_[np.arange(Ntt), np.arange(Ntt)], np.r_[edges[:, 1], edges[:, 0]])),
+                      shape=(Ntt, N - Ntt))
+    T = sp.bmat([[sp.identity(Ntt), -G], [None, sp.identity(N - Ntt)]]).tocsr()
+    Mq = prob.assemble_qd(sigma)
+    Mq_ref = (T.T @ M @ T).tocsr()
+    Mq_dev = _csr(prob, Mq)
+    assert abs(Mq_dev - Mq_ref).max() <= 1e-11 * abs(Mq_ref).max()
+    # T and T^T on the device
+    v = np.random.default_rng(1).standard_normal(N)
+    vd = torch.from_numpy(v).cuda()
+    assert np.allclose(prob.apply_T(vd).cpu().numpy(), T @ v, rtol=1e-13, atol=1e-13)
+    assert np.allclose(prob.apply_T(vd, transpose=True).cpu().numpy(), T.T @ v, rtol=1e-13, atol=1e-13)
+    # factor M' (nodes first inside every front), solve M x = b as x = T M'^-1 T^T b
+    sym = sv.Symbolic(prob.h_dofs, prob.centroids(), N, Ntt, 32)
+    S = sv.Solver(prob.pattern, sym)
+    st = S.factor(Mq)
+    b = np.random.default_rng(2).standard_normal(N)
+    y = S.solve(prob.apply_T(torch.from_numpy(b).cuda(), transpose=True))
+    x = prob.apply_T(y).cpu().numpy()
+    res = np.linalg.norm(M @ x - b) / np.linalg.norm(b)
+    assert res <= 1e-10, res
+    assert st["bad_pivots"] == 0
+    if target is None:
+        assert st["neg_pivots"] == Ntt and st["pos_pivots"] == N - Ntt
+
+
+def test_solver_rejects_use_before_factor(ws):
+    from wavesolve_b200 import fe_solver as fs, solver as sv, _lib
+    mg = ws.meshgen
+    prob = fs.ScalarProblem(mg.structured_square(6), mg.FIBER_IOR, K0)
+    sym = sv.Symbolic(prob.h_dofs, prob.centroids(), prob.N, 0, 8)
+    S = sv.Solver(prob.pattern, sym)
+    with pytest.raises(_lib.WavesolveB200Error):
+        S.solve(torch.zeros(prob.N, dtype=torch.float64, device="cuda"))

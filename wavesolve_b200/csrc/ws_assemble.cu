@@ -100,6 +100,8 @@ struct VectorP1 {
     const int32_t* tris;
     const double* k2n2;
     int transpose;
+    int qd;          // 1: write the quasi-definite shift-invert matrix M' = T^T (A - sigma B) T into Bv
+    double sigma;
 
     __device__ __forceinline__ void row(uint32_t e, int a, double (&Av)[6], double (&Bv)[6], int (&cb)[6]) const {
         const int32_t* t = tris + (int64_t)e * 3;
@@ -151,6 +153,14 @@ struct VectorP1 {
 #pragma unroll
             for (int j = 0; j < 3; ++j)                                           // :382-383
                 C[j] = transpose ? (tJ * lj[j]) * la : (tJ * la) * lj[j];
+            if (qd) {
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    Bv[j] = (c - sigma) * E[j] - C[j];
+                    Bv[3 + j] = -c * D[j];
+                }
+                return;
+            }
 #pragma unroll
             for (int j = 0; j < 3; ++j) {
                 Av[j] = __dsub_rn(__dmul_rn(c, E[j]), C[j]);                      // fe_solver.py:196
@@ -191,6 +201,14 @@ struct VectorP1 {
                 G[0] = (-sq12 + xx + yy) / J2;                                    // :426
                 G[1] = (-xx - yy) / J2;                                           // :425
                 G[2] = sq12 / J2;                                                 // :423
+            }
+            if (qd) {
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    Bv[j] = -c * Dt[j];
+                    Bv[3 + j] = c * (G[j] + sigma * (j == i ? Nd : No));
+                }
+                return;
             }
 #pragma unroll
             for (int j = 0; j < 3; ++j) {
@@ -307,8 +325,74 @@ int ws_assemble_vector_p1(const ws_pattern* p, const double* xy, const int32_t* 
     if (p->nnz == 0) return WS_OK;
     WS_REQUIRE(xy && tris && elem_k2n2 && A_vals && B_vals, "null pointer");
     DeviceGuard g(device);
-    VectorP1 op{(const double2*)xy, tris, elem_k2n2, transpose};
+    VectorP1 op{(const double2*)xy, tris, elem_k2n2, transpose, 0, 0.0};
     launch_rows<VectorP1, true>(p, op, A_vals, B_vals, (cudaStream_t)stream);
+    WS_API_END
+}
+
+int ws_assemble_vector_qd(const ws_pattern* p, const double* xy, const int32_t* tris,
+                          const double* elem_k2n2, int64_t Ntt, double sigma, double* M_vals,
+                          int device, void* stream) {
+    WS_API_BEGIN
+    WS_REQUIRE(p, "pattern == NULL");
+    WS_REQUIRE(Ntt >= 0 && Ntt <= p->N, "0 <= Ntt <= N");
+    if (p->nnz == 0) return WS_OK;
+    WS_REQUIRE(xy && tris && elem_k2n2 && M_vals, "null pointer");
+    DeviceGuard g(device);
+    VectorP1 op{(const double2*)xy, tris, elem_k2n2, 0, 1, sigma};
+    launch_rows<VectorP1, false>(p, op, nullptr, M_vals, (cudaStream_t)stream);
+    WS_API_END
+}
+
+// x = T y (mode 0):  x_t[i] = y_t[i] - (y_z[hi] - y_z[lo]) / len_i ,  x_z = y_z
+// y = T^T b (mode 1): y_t = b_t ,  y_z[j] = b_z[j] - sum_{i: hi=j} b_t[i]/len_i + sum_{i: lo=j} b_t[i]/len_i
+// The node rows gather over the pattern row (which lists every edge of the surrounding
+// triangles) so the sum order is fixed.
+__global__ void k_vector_T(int64_t N, int64_t Ntt, int mode, const int32_t* __restrict__ rowptr,
+                           const int32_t* __restrict__ colidx, const int2* __restrict__ edges,
+                           const double2* __restrict__ xy, const double* __restrict__ in, double* __restrict__ out) {
+    const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (r >= N) return;
+    if (r < Ntt) {
+        double v = in[r];
+        if (mode == 0) {
+            const int2 e = edges[r];
+            const double2 a = xy[e.x], b = xy[e.y];
+            const double len = sqrt((b.x - a.x) * (b.x - a.x) + (b.y - a.y) * (b.y - a.y));
+            v -= (in[Ntt + e.y] - in[Ntt + e.x]) / len;
+        }
+        out[r] = v;
+    } else {
+        double v = in[r];
+        if (mode == 1) {
+            const int j = (int)(r - Ntt);
+            for (int s = rowptr[r]; s < rowptr[r + 1]; ++s) {
+                const int c = colidx[s];
+                if (c >= Ntt) break;            // columns are sorted: edges first
+                const int2 e = edges[c];
+                if (e.x != j && e.y != j) continue;
+                const double2 a = xy[e.x], b = xy[e.y];
+                const double len = sqrt((b.x - a.x) * (b.x - a.x) + (b.y - a.y) * (b.y - a.y));
+                v += (e.y == j ? -in[c] : in[c]) / len;
+            }
+        }
+        out[r] = v;
+    }
+}
+
+int ws_vector_T(const ws_pattern* p, const int32_t* edges, const double* xy, int64_t Ntt, int mode,
+                const double* in, double* out, int device, void* stream) {
+    WS_API_BEGIN
+    WS_REQUIRE(p && edges && xy && in && out, "null pointer");
+    WS_REQUIRE(in != out, "in-place application is not supported");
+    WS_REQUIRE(Ntt >= 0 && Ntt <= p->N && (mode == 0 || mode == 1), "bad Ntt / mode");
+    DeviceGuard g(device);
+    if (p->N) {
+        k_vector_T<<<ceil_div(p->N, 256), 256, 0, (cudaStream_t)stream>>>(p->N, Ntt, mode, p->rowptr.get(), p->colidx.get(),
+                                                                          (const int2*)edges, (const double2*)xy, in, out);
+        WS_CUDA(cudaGetLastError());
+        count_launch(1);
+    }
     WS_API_END
 }
 

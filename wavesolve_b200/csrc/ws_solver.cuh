@@ -42,6 +42,14 @@ struct Symbolic {
     double t_kd = 0, t_order = 0, t_bnd = 0;
 };
 
+}  // namespace ws
+
+struct ws_symbolic {
+    ws::Symbolic S;
+};
+
+namespace ws {
+
 // ---- device task records ---------------------------------------------------------------------
 // C(m x n) = beta*C + alpha * A(m x k) * op(B), all column-major.
 //   NT: op(B)[kk][j] = B[j + kk*ldb] * (dscale ? dscale[kk] : 1)

@@ -22,10 +22,6 @@
 
 #include "ws_solver.cuh"
 
-struct ws_symbolic {
-    ws::Symbolic S;
-};
-
 namespace ws {
 
 namespace {

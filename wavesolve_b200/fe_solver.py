@@ -109,6 +109,7 @@ class ScalarProblem:
         # csr_matrix((data,(row,col))) infers the shape from the largest index (fe_solver.py:67)
         self.N = int(conn.max()) + 1 if conn.size else 0
         xy = np.ascontiguousarray(np.asarray(mesh.points, dtype=np.float64)[:, :2])
+        self.h_dofs, self.h_xy, self.first_class_start = conn, xy, 0
         with torch.cuda.device(dev):
             self.xy = _dev.h2d(xy, dev)
             self.dofs = _dev.h2d(conn, dev)
@@ -125,12 +126,19 @@ class ScalarProblem:
                                                     self.dev.index, _dev.stream_ptr(self.dev)))
         return A, B
 
+    def centroids(self):
+        return _element_centroids(self.h_xy, self.h_dofs[:, :3])
+
     def assemble_mass(self):
         p = self.pattern
         B = torch.empty(p.nnz, dtype=torch.float64, device=self.dev)
         _lib.check(_lib.lib().ws_assemble_mass_p2(p.handle, _dev.ptr(self.xy), _dev.ptr(self.dofs),
                                                   _dev.ptr(B), self.dev.index, _dev.stream_ptr(self.dev)))
         return B
+
+
+def _element_centroids(h_xy, vert_ids):
+    return np.ascontiguousarray(h_xy[vert_ids.astype(np.int64)].mean(axis=1))
 
 
 class VectorProblem:
@@ -147,13 +155,17 @@ class VectorProblem:
         self.N = self.Ntt + self.Nzz
         dofs = np.hstack([eidx, tris + np.int32(self.Ntt)]).astype(np.int32)
         xy = np.ascontiguousarray(np.asarray(mesh.points, dtype=np.float64)[:, :2])
+        self.h_dofs, self.h_xy, self.first_class_start = dofs, xy, self.Ntt
+        self.h_tris = tris
+        self.h_edges = _as_i32(np.asarray(mesh.cells[0].data), "edge table")
         with torch.cuda.device(dev):
             self.xy = _dev.h2d(xy, dev)
             self.tris = _dev.h2d(tris, dev)
             self.dofs = _dev.h2d(dofs, dev)
             self.k2n2 = _dev.h2d(k2, dev)
+            self.edges = _dev.h2d(self.h_edges, dev)
             self.pattern = DevicePattern(self.dofs, self.N)
-        self.h2d_bytes = xy.nbytes + tris.nbytes + dofs.nbytes + k2.nbytes
+        self.h2d_bytes = xy.nbytes + tris.nbytes + dofs.nbytes + k2.nbytes + self.h_edges.nbytes
 
     def assemble(self, transpose=False):
         p = self.pattern
@@ -164,6 +176,25 @@ class VectorProblem:
                                                     _dev.ptr(B), 1 if transpose else 0,
                                                     self.dev.index, _dev.stream_ptr(self.dev)))
         return A, B
+
+    def assemble_qd(self, sigma):
+        """Quasi-definite shift-invert matrix M' = T^T (A - sigma B) T on the pattern."""
+        p = self.pattern
+        M = torch.empty(p.nnz, dtype=torch.float64, device=self.dev)
+        _lib.check(_lib.lib().ws_assemble_vector_qd(p.handle, _dev.ptr(self.xy), _dev.ptr(self.tris),
+                                                    _dev.ptr(self.k2n2), self.Ntt, float(sigma), _dev.ptr(M),
+                                                    self.dev.index, _dev.stream_ptr(self.dev)))
+        return M
+
+    def apply_T(self, v, transpose=False):
+        out = torch.empty_like(v)
+        _lib.check(_lib.lib().ws_vector_T(self.pattern.handle, _dev.ptr(self.edges), _dev.ptr(self.xy), self.Ntt,
+                                          1 if transpose else 0, _dev.ptr(v), _dev.ptr(out),
+                                          self.dev.index, _dev.stream_ptr(self.dev)))
+        return out
+
+    def centroids(self):
+        return _element_centroids(self.h_xy, self.h_tris)
 
 
 def _to_scipy(cls, N, indptr, indices, data):

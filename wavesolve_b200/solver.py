@@ -54,3 +54,55 @@ class Symbolic:
             self.close()
         except Exception:
             pass
+
+
+class Solver:
+    """Device multifrontal LDL^T bound to a pattern and a symbolic analysis (``ws_solver``)."""
+
+    def __init__(self, pattern, symbolic: Symbolic):
+        import torch
+        from . import device as _dev
+        self._torch, self._dev = torch, _dev
+        self.pattern = pattern
+        self.symbolic = symbolic
+        self.dev = pattern.dev
+        h = C.c_void_p()
+        _lib.check(_lib.lib().ws_solver_create(pattern.handle, symbolic.handle, C.byref(h),
+                                               self.dev.index, _dev.stream_ptr(self.dev)))
+        self.handle = h
+        self.N = pattern.N
+
+    def factor(self, A_vals, B_vals=None, sigma=0.0):
+        d = self._dev
+        _lib.check(_lib.lib().ws_solver_factor(self.handle, d.ptr(A_vals), d.ptr(B_vals), float(sigma),
+                                               self.dev.index, d.stream_ptr(self.dev)))
+        return self.stats()
+
+    def solve(self, b, out=None):
+        torch, d = self._torch, self._dev
+        nrhs = 1 if b.dim() == 1 else b.shape[0]
+        if out is None:
+            out = torch.empty_like(b)
+        _lib.check(_lib.lib().ws_solver_solve(self.handle, d.ptr(b), d.ptr(out), nrhs,
+                                              self.dev.index, d.stream_ptr(self.dev)))
+        return out
+
+    def stats(self):
+        info = np.zeros(8, dtype=np.int64)
+        dinfo = np.zeros(3, dtype=np.float64)
+        _lib.check(_lib.lib().ws_solver_stats(self.handle, info.ctypes.data, dinfo.ctypes.data))
+        keys = ("nnzL", "fronts", "maxfront", "bytes", "neg_pivots", "pos_pivots", "bad_pivots", "depth")
+        out = {k: int(v) for k, v in zip(keys, info)}
+        out.update(flops=float(dinfo[0]), min_pivot=float(dinfo[1]), max_pivot=float(dinfo[2]))
+        return out
+
+    def close(self):
+        if self.handle is not None and self.handle.value:
+            _lib.lib().ws_solver_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
