@@ -166,6 +166,28 @@ int ws_assemble_vector_qd(const ws_pattern* p, const double* xy, const int32_t* 
 int ws_vector_T(const ws_pattern* p, const int32_t* edges, const double* xy, int64_t Ntt, int mode,
                 const double* in, double* out, int device, void* stream);
 
+/* ---- K5-K7, K9, K10: Krylov eigensolver on OP = (A - sigma B)^-1 B ----------------------------
+ * kind 0: B-orthogonal Arnoldi/Lanczos with thick restart for the symmetric-definite pencil
+ *         (replaces eigsh(A, M=B, k=nev, which='SA', sigma), fe_solver.py:328); `s` holds the
+ *         factorisation of A - sigma B; eigenvectors come back B-orthonormal.
+ * kind 1: Euclidean Arnoldi with thick restart on the non-symmetric OP (replaces
+ *         eigs(spsolve(A - sigma B, B), k, which='SR'), fe_solver.py:398-400); `s` holds the
+ *         factorisation of the quasi-definite M' (ws_assemble_vector_qd) and edges/xy/Ntt
+ *         describe T; eigenvectors come back with unit 2-norm.
+ * ncv <= 0 -> max(2 nev + 1, 20); tol <= 0 -> machine epsilon (both scipy's defaults).
+ * w [nev] (device): lambda = sigma + 1/theta, descending.  V [nev*N] (device): row j =
+ * eigenvector j.  h_info[5] = converged, OP applications, restarts, complex Ritz values among
+ * the wanted ones, kept directions at the last restart.  h_resid [nev]: Ritz residual estimates.
+ * Returns WS_ERR_NOCONV (results still written) if fewer than nev pairs converged.
+ * ws_host_eig_general: the small dense eigen-solver used for the projected problem (host;
+ * exposed for testing).  V is row-major, column j = eigenvector j (complex pair: re, im).    */
+int ws_eig_solve(const ws_pattern* p, ws_solver* s, const double* B_vals, double sigma, int kind,
+                 int nev, int ncv, double tol, int maxit, uint64_t seed, const int32_t* edges,
+                 const double* xy, int64_t Ntt, double* w, double* V, int64_t* h_info,
+                 double* h_resid, int device, void* stream);
+int ws_host_eig_general(int n, const double* h_A, double* h_wr, double* h_wi, double* h_V,
+                        int symmetric);
+
 #ifdef __cplusplus
 }
 #endif

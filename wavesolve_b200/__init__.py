@@ -2,7 +2,8 @@
 sparse eigensolve), drop-in for ``wavesolve.fe_solver`` / ``wavesolve.waveguide`` hot-path
 functions.  The CUDA library is required; there is no CPU fallback."""
 from . import fe_solver, waveguide, meshgen  # noqa: F401
-from .fe_solver import (construct_AB, construct_AB_vec, construct_B, get_eff_index)  # noqa: F401
+from .fe_solver import (construct_AB, construct_AB_vec, construct_B, get_eff_index,  # noqa: F401
+                        solve_waveguide, solve_waveguide_vec)
 from .waveguide import get_unique_edges  # noqa: F401
 
 __version__ = "0.1.0"

@@ -22,6 +22,7 @@ SOURCES = {
     "ws_spmv.cu": [],
     "ws_symbolic.cu": [],
     "ws_factor.cu": [],
+    "ws_eig.cu": [],
 }
 
 

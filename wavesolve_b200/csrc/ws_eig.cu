@@ -1,0 +1,836 @@
+// K5-K7, K9, K10: Krylov eigensolver for the shift-inverted pencil, OP = (A - sigma B)^-1 B.
+//
+//  kind 0 (scalar, B SPD):  Arnoldi/Lanczos in the B inner product with full (CGS2)
+//          re-orthogonalisation and thick restart -- what ARPACK's dsaupd/dseupd mode 3 does
+//          behind eigsh(A, M=B, k, which='SA', sigma) at fe_solver.py:328.  The dual basis
+//          Z = B V is carried along, so a step costs one solve + one SpMV.
+//  kind 1 (vector, B indefinite):  Euclidean Arnoldi with thick (Krylov-Schur style) restart on
+//          the non-symmetric OP -- the matrix-free equivalent of eigs(spsolve(A - sigma B, B),
+//          k, which='SR') at fe_solver.py:398-400.  OP x = T M'^-1 T^T (B x) with the
+//          quasi-definite M' (ws_assemble_vector_qd).
+//
+// Device side: the basis lives in HBM as (ncv+1) rows of length N; one Arnoldi step is a
+// fixed launch sequence with every coefficient kept in device memory (no host round trip
+// inside a sweep).  Host side: the (ncv+1) x ncv projected matrix is copied back once per
+// sweep and its eigen-decomposition (Jacobi for the symmetric case, Hessenberg + shifted QR
+// otherwise), the convergence test and the restart rotation are computed in plain C++.
+#include <algorithm>
+#include <cmath>
+#include <complex>
+#include <numeric>
+
+#include "ws_solver.cuh"
+
+namespace ws {
+
+void spmv_launch(const ws_pattern* p, const double* vals, const double* x, double* y, cudaStream_t st);
+
+// =============================================================================================
+// host dense eigen-solvers (n <= ~64)
+// =============================================================================================
+// symmetric: cyclic Jacobi.  A row-major n x n (destroyed), w eigenvalues, V[i*n+j] = component i of vector j
+void jacobi_sym(int n, std::vector<double>& A, std::vector<double>& w, std::vector<double>& V) {
+    V.assign((size_t)n * n, 0.0);
+    for (int i = 0; i < n; ++i) V[(size_t)i * n + i] = 1.0;
+    auto a = [&](int i, int j) -> double& { return A[(size_t)i * n + j]; };
+    for (int sweep = 0; sweep < 100; ++sweep) {
+        double off = 0.0, diag = 0.0;
+        for (int i = 0; i < n; ++i) {
+            diag += a(i, i) * a(i, i);
+            for (int j = i + 1; j < n; ++j) off += a(i, j) * a(i, j);
+        }
+        if (off <= 1e-34 * (diag + off) || off == 0.0) break;
+        for (int p = 0; p < n - 1; ++p)
+            for (int q = p + 1; q < n; ++q) {
+                const double apq = a(p, q);
+                if (apq == 0.0) continue;
+                const double theta = (a(q, q) - a(p, p)) / (2.0 * apq);
+                const double t = (theta >= 0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1.0));
+                const double c = 1.0 / std::sqrt(t * t + 1.0), s = t * c;
+                for (int k = 0; k < n; ++k) {
+                    const double akp = a(k, p), akq = a(k, q);
+                    a(k, p) = c * akp - s * akq;
+                    a(k, q) = s * akp + c * akq;
+                }
+                for (int k = 0; k < n; ++k) {
+                    const double apk = a(p, k), aqk = a(q, k);
+                    a(p, k) = c * apk - s * aqk;
+                    a(q, k) = s * apk + c * aqk;
+                }
+                for (int k = 0; k < n; ++k) {
+                    const double vkp = V[(size_t)k * n + p], vkq = V[(size_t)k * n + q];
+                    V[(size_t)k * n + p] = c * vkp - s * vkq;
+                    V[(size_t)k * n + q] = s * vkp + c * vkq;
+                }
+            }
+    }
+    w.resize(n);
+    for (int i = 0; i < n; ++i) w[i] = a(i, i);
+}
+
+// general real matrix: Householder reduction to Hessenberg form + implicit double-shift QR with
+// accumulated transformations and back-substitution (the classical EISPACK orthes/hqr2 scheme).
+// H row-major n x n (destroyed).  wr/wi eigenvalues; V[i*n+j]: real eigenvalue j -> column j is
+// its eigenvector; complex pair (j, j+1), wi[j] > 0 -> columns j, j+1 are the real and imaginary
+// parts of the eigenvector of wr[j] + i wi[j].  Returns false if the QR iteration stalls.
+static void cdiv(double xr, double xi, double yr, double yi, double& cr, double& ci) {
+    double r, d;
+    if (std::fabs(yr) > std::fabs(yi)) {
+        r = yi / yr; d = yr + r * yi;
+        cr = (xr + r * xi) / d; ci = (xi - r * xr) / d;
+    } else {
+        r = yr / yi; d = yi + r * yr;
+        cr = (r * xr + xi) / d; ci = (r * xi - xr) / d;
+    }
+}
+
+bool eig_general(int nn, std::vector<double>& Hm, std::vector<double>& wr, std::vector<double>& wi,
+                 std::vector<double>& Vm) {
+    auto H = [&](int i, int j) -> double& { return Hm[(size_t)i * nn + j]; };
+    Vm.assign((size_t)nn * nn, 0.0);
+    auto V = [&](int i, int j) -> double& { return Vm[(size_t)i * nn + j]; };
+    wr.assign(nn, 0.0);
+    wi.assign(nn, 0.0);
+    std::vector<double> ort(nn, 0.0);
+    const int low = 0, high = nn - 1;
+    // ---- reduction to Hessenberg form
+    for (int m = low + 1; m <= high - 1; ++m) {
+        double scale = 0.0;
+        for (int i = m; i <= high; ++i) scale += std::fabs(H(i, m - 1));
+        if (scale != 0.0) {
+            double h = 0.0;
+            for (int i = high; i >= m; --i) {
+                ort[i] = H(i, m - 1) / scale;
+                h += ort[i] * ort[i];
+            }
+            double g = std::sqrt(h);
+            if (ort[m] > 0) g = -g;
+            h -= ort[m] * g;
+            ort[m] -= g;
+            for (int j = m; j < nn; ++j) {
+                double f = 0.0;
+                for (int i = high; i >= m; --i) f += ort[i] * H(i, j);
+                f /= h;
+                for (int i = m; i <= high; ++i) H(i, j) -= f * ort[i];
+            }
+            for (int i = 0; i <= high; ++i) {
+                double f = 0.0;
+                for (int j = high; j >= m; --j) f += ort[j] * H(i, j);
+                f /= h;
+                for (int j = m; j <= high; ++j) H(i, j) -= f * ort[j];
+            }
+            ort[m] = scale * ort[m];
+            H(m, m - 1) = scale * g;
+        }
+    }
+    for (int i = 0; i < nn; ++i) V(i, i) = 1.0;
+    for (int m = high - 1; m >= low + 1; --m) {
+        if (H(m, m - 1) != 0.0) {
+            for (int i = m + 1; i <= high; ++i) ort[i] = H(i, m - 1);
+            for (int j = m; j <= high; ++j) {
+                double g = 0.0;
+                for (int i = m; i <= high; ++i) g += ort[i] * V(i, j);
+                g = (g / ort[m]) / H(m, m - 1);
+                for (int i = m; i <= high; ++i) V(i, j) += g * ort[i];
+            }
+        }
+    }
+    // ---- QR iteration
+    int n = nn - 1;
+    const double eps = std::pow(2.0, -52.0);
+    double exshift = 0.0, p = 0, q = 0, r = 0, s = 0, z = 0, t, w, x, y;
+    double norm = 0.0;
+    for (int i = 0; i < nn; ++i)
+        for (int j = std::max(i - 1, 0); j < nn; ++j) norm += std::fabs(H(i, j));
+    int iter = 0, total = 0;
+    while (n >= low) {
+        int l = n;
+        while (l > low) {
+            s = std::fabs(H(l - 1, l - 1)) + std::fabs(H(l, l));
+            if (s == 0.0) s = norm;
+            if (std::fabs(H(l, l - 1)) < eps * s) break;
+            l--;
+        }
+        if (l == n) {
+            H(n, n) += exshift;
+            wr[n] = H(n, n);
+            wi[n] = 0.0;
+            n--;
+            iter = 0;
+        } else if (l == n - 1) {
+            w = H(n, n - 1) * H(n - 1, n);
+            p = (H(n - 1, n - 1) - H(n, n)) / 2.0;
+            q = p * p + w;
+            z = std::sqrt(std::fabs(q));
+            H(n, n) += exshift;
+            H(n - 1, n - 1) += exshift;
+            x = H(n, n);
+            if (q >= 0) {
+                z = (p >= 0) ? p + z : p - z;
+                wr[n - 1] = x + z;
+                wr[n] = wr[n - 1];
+                if (z != 0.0) wr[n] = x - w / z;
+                wi[n - 1] = 0.0;
+                wi[n] = 0.0;
+                x = H(n, n - 1);
+                s = std::fabs(x) + std::fabs(z);
+                p = x / s;
+                q = z / s;
+                r = std::sqrt(p * p + q * q);
+                p /= r;
+                q /= r;
+                for (int j = n - 1; j < nn; ++j) {
+                    z = H(n - 1, j);
+                    H(n - 1, j) = q * z + p * H(n, j);
+                    H(n, j) = q * H(n, j) - p * z;
+                }
+                for (int i = 0; i <= n; ++i) {
+                    z = H(i, n - 1);
+                    H(i, n - 1) = q * z + p * H(i, n);
+                    H(i, n) = q * H(i, n) - p * z;
+                }
+                for (int i = low; i <= high; ++i) {
+                    z = V(i, n - 1);
+                    V(i, n - 1) = q * z + p * V(i, n);
+                    V(i, n) = q * V(i, n) - p * z;
+                }
+            } else {
+                wr[n - 1] = x + p;
+                wr[n] = x + p;
+                wi[n - 1] = z;
+                wi[n] = -z;
+            }
+            n -= 2;
+            iter = 0;
+        } else {
+            x = H(n, n);
+            y = 0.0;
+            w = 0.0;
+            if (l < n) {
+                y = H(n - 1, n - 1);
+                w = H(n, n - 1) * H(n - 1, n);
+            }
+            if (iter == 10) {
+                exshift += x;
+                for (int i = low; i <= n; ++i) H(i, i) -= x;
+                s = std::fabs(H(n, n - 1)) + std::fabs(H(n - 1, n - 2));
+                x = y = 0.75 * s;
+                w = -0.4375 * s * s;
+            }
+            if (iter == 30) {
+                s = (y - x) / 2.0;
+                s = s * s + w;
+                if (s > 0) {
+                    s = std::sqrt(s);
+                    if (y < x) s = -s;
+                    s = x - w / ((y - x) / 2.0 + s);
+                    for (int i = low; i <= n; ++i) H(i, i) -= s;
+                    exshift += s;
+                    x = y = w = 0.964;
+                }
+            }
+            iter++;
+            if (++total > 3000) return false;
+            int m = n - 2;
+            while (m >= l) {
+                z = H(m, m);
+                r = x - z;
+                s = y - z;
+                p = (r * s - w) / H(m + 1, m) + H(m, m + 1);
+                q = H(m + 1, m + 1) - z - r - s;
+                r = H(m + 2, m + 1);
+                s = std::fabs(p) + std::fabs(q) + std::fabs(r);
+                p /= s;
+                q /= s;
+                r /= s;
+                if (m == l) break;
+                if (std::fabs(H(m, m - 1)) * (std::fabs(q) + std::fabs(r)) <
+                    eps * (std::fabs(p) * (std::fabs(H(m - 1, m - 1)) + std::fabs(z) + std::fabs(H(m + 1, m + 1)))))
+                    break;
+                m--;
+            }
+            for (int i = m + 2; i <= n; ++i) {
+                H(i, i - 2) = 0.0;
+                if (i > m + 2) H(i, i - 3) = 0.0;
+            }
+            for (int k = m; k <= n - 1; ++k) {
+                const bool notlast = (k != n - 1);
+                if (k != m) {
+                    p = H(k, k - 1);
+                    q = H(k + 1, k - 1);
+                    r = notlast ? H(k + 2, k - 1) : 0.0;
+                    x = std::fabs(p) + std::fabs(q) + std::fabs(r);
+                    if (x == 0.0) continue;
+                    p /= x;
+                    q /= x;
+                    r /= x;
+                }
+                s = std::sqrt(p * p + q * q + r * r);
+                if (p < 0) s = -s;
+                if (s != 0) {
+                    if (k != m) H(k, k - 1) = -s * x;
+                    else if (l != m) H(k, k - 1) = -H(k, k - 1);
+                    p += s;
+                    x = p / s;
+                    y = q / s;
+                    z = r / s;
+                    q /= p;
+                    r /= p;
+                    for (int j = k; j < nn; ++j) {
+                        p = H(k, j) + q * H(k + 1, j);
+                        if (notlast) {
+                            p += r * H(k + 2, j);
+                            H(k + 2, j) -= p * z;
+                        }
+                        H(k, j) -= p * x;
+                        H(k + 1, j) -= p * y;
+                    }
+                    for (int i = 0; i <= std::min(n, k + 3); ++i) {
+                        p = x * H(i, k) + y * H(i, k + 1);
+                        if (notlast) {
+                            p += z * H(i, k + 2);
+                            H(i, k + 2) -= p * r;
+                        }
+                        H(i, k) -= p;
+                        H(i, k + 1) -= p * q;
+                    }
+                    for (int i = low; i <= high; ++i) {
+                        p = x * V(i, k) + y * V(i, k + 1);
+                        if (notlast) {
+                            p += z * V(i, k + 2);
+                            V(i, k + 2) -= p * r;
+                        }
+                        V(i, k) -= p;
+                        V(i, k + 1) -= p * q;
+                    }
+                }
+            }
+        }
+    }
+    if (norm == 0.0) return true;
+    // ---- back-substitution: eigenvectors of the quasi-triangular form
+    for (n = nn - 1; n >= 0; --n) {
+        p = wr[n];
+        q = wi[n];
+        if (q == 0) {
+            int l = n;
+            H(n, n) = 1.0;
+            for (int i = n - 1; i >= 0; --i) {
+                w = H(i, i) - p;
+                r = 0.0;
+                for (int j = l; j <= n; ++j) r += H(i, j) * H(j, n);
+                if (wi[i] < 0.0) {
+                    z = w;
+                    s = r;
+                } else {
+                    l = i;
+                    if (wi[i] == 0.0) {
+                        if (w != 0.0) H(i, n) = -r / w;
+                        else H(i, n) = -r / (eps * norm);
+                    } else {
+                        x = H(i, i + 1);
+                        y = H(i + 1, i);
+                        q = (wr[i] - p) * (wr[i] - p) + wi[i] * wi[i];
+                        t = (x * s - z * r) / q;
+                        H(i, n) = t;
+                        if (std::fabs(x) > std::fabs(z)) H(i + 1, n) = (-r - w * t) / x;
+                        else H(i + 1, n) = (-s - y * t) / z;
+                    }
+                    t = std::fabs(H(i, n));
+                    if ((eps * t) * t > 1)
+                        for (int j = i; j <= n; ++j) H(j, n) /= t;
+                }
+            }
+        } else if (q < 0) {
+            int l = n - 1;
+            double cr, ci;
+            if (std::fabs(H(n, n - 1)) > std::fabs(H(n - 1, n))) {
+                H(n - 1, n - 1) = q / H(n, n - 1);
+                H(n - 1, n) = -(H(n, n) - p) / H(n, n - 1);
+            } else {
+                cdiv(0.0, -H(n - 1, n), H(n - 1, n - 1) - p, q, cr, ci);
+                H(n - 1, n - 1) = cr;
+                H(n - 1, n) = ci;
+            }
+            H(n, n - 1) = 0.0;
+            H(n, n) = 1.0;
+            for (int i = n - 2; i >= 0; --i) {
+                double ra = 0.0, sa = 0.0, vr, vi;
+                for (int j = l; j <= n; ++j) {
+                    ra += H(i, j) * H(j, n - 1);
+                    sa += H(i, j) * H(j, n);
+                }
+                w = H(i, i) - p;
+                if (wi[i] < 0.0) {
+                    z = w;
+                    r = ra;
+                    s = sa;
+                } else {
+                    l = i;
+                    if (wi[i] == 0) {
+                        cdiv(-ra, -sa, w, q, cr, ci);
+                        H(i, n - 1) = cr;
+                        H(i, n) = ci;
+                    } else {
+                        x = H(i, i + 1);
+                        y = H(i + 1, i);
+                        vr = (wr[i] - p) * (wr[i] - p) + wi[i] * wi[i] - q * q;
+                        vi = (wr[i] - p) * 2.0 * q;
+                        if (vr == 0.0 && vi == 0.0)
+                            vr = eps * norm * (std::fabs(w) + std::fabs(q) + std::fabs(x) + std::fabs(y) + std::fabs(z));
+                        cdiv(x * r - z * ra + q * sa, x * s - z * sa - q * ra, vr, vi, cr, ci);
+                        H(i, n - 1) = cr;
+                        H(i, n) = ci;
+                        if (std::fabs(x) > (std::fabs(z) + std::fabs(q))) {
+                            H(i + 1, n - 1) = (-ra - w * H(i, n - 1) + q * H(i, n)) / x;
+                            H(i + 1, n) = (-sa - w * H(i, n) - q * H(i, n - 1)) / x;
+                        } else {
+                            cdiv(-r - y * H(i, n - 1), -s - y * H(i, n), z, q, cr, ci);
+                            H(i + 1, n - 1) = cr;
+                            H(i + 1, n) = ci;
+                        }
+                    }
+                    t = std::max(std::fabs(H(i, n - 1)), std::fabs(H(i, n)));
+                    if ((eps * t) * t > 1)
+                        for (int j = i; j <= n; ++j) {
+                            H(j, n - 1) /= t;
+                            H(j, n) /= t;
+                        }
+                }
+            }
+        }
+    }
+    for (int j = nn - 1; j >= low; --j)
+        for (int i = low; i <= high; ++i) {
+            z = 0.0;
+            for (int k = low; k <= std::min(j, high); ++k) z += V(i, k) * H(k, j);
+            V(i, j) = z;
+        }
+    return true;
+}
+
+// =============================================================================================
+// device kernels on the Krylov basis (rows of length N)
+// =============================================================================================
+constexpr int DOT_CHUNK = 2048;
+constexpr int MAXV = 64;
+
+// partial[c*nvec + i] = sum over chunk c of Z_i[n] * u[n];  8 warps, warp w takes vectors w, w+8, ...
+__global__ void __launch_bounds__(256) k_dots_partial(const double* __restrict__ Z, int64_t ldz, int nvec,
+                                                      const double* __restrict__ u, int64_t N,
+                                                      double* __restrict__ partial) {
+    __shared__ double us[DOT_CHUNK];
+    const int64_t n0 = (int64_t)blockIdx.x * DOT_CHUNK;
+    const int len = (int)min((int64_t)DOT_CHUNK, N - n0);
+    for (int i = threadIdx.x; i < DOT_CHUNK; i += 256) us[i] = (i < len) ? u[n0 + i] : 0.0;
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int v = warp; v < nvec; v += 8) {
+        const double* z = Z + (size_t)v * ldz + n0;
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        int i = lane;
+        for (; i + 96 < len; i += 128) {
+            a0 += z[i] * us[i];
+            a1 += z[i + 32] * us[i + 32];
+            a2 += z[i + 64] * us[i + 64];
+            a3 += z[i + 96] * us[i + 96];
+        }
+        for (; i < len; i += 32) a0 += z[i] * us[i];
+        double acc = (a0 + a1) + (a2 + a3);
+#pragma unroll
+        for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) partial[(size_t)blockIdx.x * nvec + v] = acc;
+    }
+}
+
+// h[i] = sum_c partial[c][i] (fixed order); hacc[i] += h[i] when hacc != nullptr
+__global__ void k_dots_reduce(const double* __restrict__ partial, int nchunks, int nvec, double* __restrict__ h,
+                              double* __restrict__ hacc) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nvec) return;
+    double s = 0.0;
+    for (int c = 0; c < nchunks; ++c) s += partial[(size_t)c * nvec + i];
+    h[i] = s;
+    if (hacc) hacc[i] += s;
+}
+
+// w -= sum_i h[i] V_i
+__global__ void __launch_bounds__(256) k_update(double* __restrict__ w, const double* __restrict__ V, int64_t ldv,
+                                                int nvec, const double* __restrict__ h, int64_t N) {
+    __shared__ double hs[MAXV];
+    if (threadIdx.x < nvec) hs[threadIdx.x] = h[threadIdx.x];
+    __syncthreads();
+    const int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    double acc = w[n];
+    for (int i = 0; i < nvec; ++i) acc -= hs[i] * V[(size_t)i * ldv + n];
+    w[n] = acc;
+}
+
+// beta = sqrt(nrm2[0]); Hcol[j+1] = beta; v_next = w / beta; z_next = bw / beta (optional)
+__global__ void k_normalize(const double* __restrict__ w, const double* __restrict__ bw, const double* __restrict__ nrm2,
+                            double* __restrict__ hslot, double* __restrict__ vnext, double* __restrict__ znext,
+                            int64_t N) {
+    const int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const double beta = sqrt(fabs(nrm2[0]));
+    if (n == 0 && hslot) *hslot = beta;
+    if (n >= N) return;
+    const double inv = beta > 0.0 ? 1.0 / beta : 0.0;
+    vnext[n] = w[n] * inv;
+    if (znext) znext[n] = bw[n] * inv;
+}
+
+__global__ void k_random(double* __restrict__ v, int64_t N, uint64_t seed) {
+    const int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    uint64_t z = seed + 0x9E3779B97F4A7C15ull * (uint64_t)(n + 1);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    v[n] = ((double)(z >> 11) * (1.0 / 9007199254740992.0)) * 2.0 - 1.0;   // uniform(-1, 1) like ARPACK's v0
+}
+
+// in-place basis rotation (K10): rows 0..k-1 <- Q^T rows 0..m-1, per column of the basis;
+// row k <- row m (the residual direction).  Q is m x k row-major in device memory.
+__global__ void __launch_bounds__(128) k_rotate(double* __restrict__ V, int64_t ldv, int m, int k,
+                                                const double* __restrict__ Q, int64_t N, int move_residual,
+                                                double* __restrict__ out, int64_t ldo) {
+    extern __shared__ double qs[];
+    for (int i = threadIdx.x; i < m * k; i += blockDim.x) qs[i] = Q[i];
+    __syncthreads();
+    const int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    double col[MAXV];
+#pragma unroll 4
+    for (int j = 0; j < m; ++j) col[j] = V[(size_t)j * ldv + n];
+    const double res = move_residual ? V[(size_t)m * ldv + n] : 0.0;
+    double* dst = out ? out : V;
+    const int64_t ldd = out ? ldo : ldv;
+    for (int i = 0; i < k; ++i) {
+        double s = 0.0;
+        for (int j = 0; j < m; ++j) s += qs[j * k + i] * col[j];
+        dst[(size_t)i * ldd + n] = s;
+    }
+    if (move_residual) V[(size_t)k * ldv + n] = res;
+}
+
+__global__ void k_scale_rows(double* __restrict__ X, int64_t ld, int nrows, const double* __restrict__ nrm2, int64_t N) {
+    const int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    for (int i = 0; i < nrows; ++i) {
+        const double s = nrm2[i];
+        X[(size_t)i * ld + n] *= (s > 0.0 ? 1.0 / sqrt(s) : 1.0);
+    }
+}
+
+struct EigWork {
+    int64_t N;
+    int ncv;
+    cudaStream_t st;
+    DevBuf<double> V, Z, w, t1, t2, t3, partial, h, Hd, nrm, Q;
+    int nchunks;
+};
+
+static void dots(EigWork& W, const double* Zb, int nvec, const double* u, double* h, double* hacc) {
+    k_dots_partial<<<W.nchunks, 256, 0, W.st>>>(Zb, W.N, nvec, u, W.N, W.partial.get());
+    k_dots_reduce<<<1, 64, 0, W.st>>>(W.partial.get(), W.nchunks, nvec, h, hacc);
+    count_launch(2);
+}
+
+}  // namespace ws
+
+using namespace ws;
+
+extern "C" {
+
+// test hook: host dense eigen-solver (no GPU needed)
+int ws_host_eig_general(int n, const double* h_A, double* h_wr, double* h_wi, double* h_V, int symmetric) {
+    WS_API_BEGIN
+    WS_REQUIRE(n >= 1 && n <= 512 && h_A && h_wr && h_V, "bad arguments");
+    std::vector<double> A(h_A, h_A + (size_t)n * n), wr, wi, V;
+    if (symmetric) {
+        jacobi_sym(n, A, wr, V);
+        wi.assign(n, 0.0);
+    } else if (!eig_general(n, A, wr, wi, V)) {
+        throw Error(WS_ERR_NOCONV, "dense QR iteration did not converge");
+    }
+    std::copy(wr.begin(), wr.end(), h_wr);
+    if (h_wi) std::copy(wi.begin(), wi.end(), h_wi);
+    std::copy(V.begin(), V.end(), h_V);
+    WS_API_END
+}
+
+int ws_eig_solve(const ws_pattern* p, ws_solver* s, const double* B_vals, double sigma, int kind, int nev, int ncv,
+                 double tol, int maxit, uint64_t seed, const int32_t* edges, const double* xy, int64_t Ntt,
+                 double* w_out, double* V_out, int64_t* h_info, double* h_resid, int device, void* stream) {
+    WS_API_BEGIN
+    WS_REQUIRE(p && s && B_vals && w_out && V_out, "null pointer");
+    WS_REQUIRE(kind == 0 || kind == 1, "kind must be 0 (B-orthogonal, symmetric) or 1 (Euclidean, non-symmetric)");
+    const int64_t N = p->N;
+    WS_REQUIRE(nev >= 1 && nev < N - 1, "1 <= nev < N-1");
+    if (ncv <= 0) ncv = std::max(2 * nev + 1, 20);     // scipy's default (arpack.py: ncv = max(2k+1, 20))
+    ncv = (int)std::min<int64_t>(ncv, N);
+    WS_REQUIRE(ncv > nev + 1 && ncv < MAXV, "nev+1 < ncv < 64");
+    WS_REQUIRE(kind == 0 || (edges && xy), "the vector eigensolver needs the edge table and coordinates");
+    if (tol <= 0) tol = 2.220446049250313e-16;          // ARPACK: tol=0 -> machine epsilon
+    if (maxit <= 0) maxit = 300;
+    DeviceGuard g(device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int m = ncv;
+    EigWork W;
+    W.N = N; W.ncv = m; W.st = st;
+    W.nchunks = ceil_div(N, DOT_CHUNK);
+    W.V.alloc((size_t)(m + 1) * N, st);
+    if (kind == 0) W.Z.alloc((size_t)(m + 1) * N, st);
+    W.w.alloc(N, st); W.t1.alloc(N, st); W.t2.alloc(N, st); W.t3.alloc(N, st);
+    W.partial.alloc((size_t)W.nchunks * MAXV, st);
+    W.h.alloc(MAXV, st);
+    W.Hd.alloc((size_t)(m + 1) * m, st);
+    W.nrm.alloc(MAXV, st);
+    W.Q.alloc((size_t)MAXV * MAXV, st);
+    double* V = W.V.get();
+    double* Z = kind == 0 ? W.Z.get() : V;
+    const int T = 256;
+    const int nb = ceil_div(N, T);
+    auto solve = [&](const double* b, double* x) {
+        int rc = ws_solver_solve(s, b, x, 1, device, stream);
+        if (rc) throw Error(rc, ws_last_error());
+    };
+    auto vecT = [&](int mode, const double* in, double* out) {
+        int rc = ws_vector_T(p, edges, xy, Ntt, mode, in, out, device, stream);
+        if (rc) throw Error(rc, ws_last_error());
+    };
+    // OP applied to basis vector j -> W.w
+    auto apply_op = [&](int j) {
+        if (kind == 0) {
+            solve(Z + (size_t)j * N, W.w.get());                       // Z_j = B v_j is carried along
+        } else {
+            spmv_launch(p, B_vals, V + (size_t)j * N, W.t1.get(), st);
+            vecT(1, W.t1.get(), W.t2.get());
+            solve(W.t2.get(), W.t3.get());
+            vecT(0, W.t3.get(), W.w.get());
+        }
+    };
+    // normalise W.w in the inner product into basis slot j (H entry written to hslot)
+    auto normalize_into = [&](int j, double* hslot) {
+        const double* dual = W.w.get();
+        if (kind == 0) {
+            spmv_launch(p, B_vals, W.w.get(), W.t1.get(), st);
+            dual = W.t1.get();
+        }
+        dots(W, dual, 1, W.w.get(), W.nrm.get(), nullptr);
+        k_normalize<<<nb, T, 0, st>>>(W.w.get(), kind == 0 ? W.t1.get() : nullptr, W.nrm.get(), hslot,
+                                     V + (size_t)j * N, kind == 0 ? Z + (size_t)j * N : nullptr, N);
+        count_launch(1);
+    };
+
+    // ---- start vector: random, pushed once through OP (stays in range(OP), as ARPACK does)
+    k_random<<<nb, T, 0, st>>>(W.w.get(), N, seed ? seed : 0x5DEECE66Dull);
+    count_launch(1);
+    normalize_into(0, nullptr);
+    apply_op(0);
+    normalize_into(0, nullptr);
+    WS_CUDA(cudaMemsetAsync(W.Hd.get(), 0, W.Hd.bytes(), st));
+
+    std::vector<double> Hh((size_t)(m + 1) * m, 0.0);    // column-major (m+1) x m, as on the device
+    std::vector<double> theta_r(m), theta_i(m), Y, resid(m, 0.0);
+    std::vector<int> order(m);
+    int j0 = 0, nconv = 0, restarts = 0;
+    int64_t nops = 1;
+    bool done = false;
+    const double eps23 = std::pow(2.220446049250313e-16, 2.0 / 3.0);
+    std::vector<double> Qh;
+    int kkeep = 0;
+    while (!done) {
+        for (int j = j0; j < m; ++j) {
+            apply_op(j);
+            ++nops;
+            double* Hcol = W.Hd.get() + (size_t)j * (m + 1);
+            // CGS2 against rows 0..j : coefficients with the dual basis, update with the primal one
+            for (int pass = 0; pass < 2; ++pass) {
+                dots(W, Z, j + 1, W.w.get(), W.h.get(), Hcol);
+                k_update<<<nb, T, 0, st>>>(W.w.get(), V, N, j + 1, W.h.get(), N);
+                count_launch(1);
+            }
+            normalize_into(j + 1, Hcol + (j + 1));
+        }
+        WS_CUDA(cudaMemcpyAsync(Hh.data(), W.Hd.get(), Hh.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
+        WS_CUDA(cudaStreamSynchronize(st));
+        WS_CUDA(cudaGetLastError());
+        const double beta_m = Hh[(size_t)(m - 1) * (m + 1) + m];
+        // projected matrix, row-major m x m
+        std::vector<double> Hm((size_t)m * m);
+        for (int i = 0; i < m; ++i)
+            for (int j = 0; j < m; ++j) Hm[(size_t)i * m + j] = Hh[(size_t)j * (m + 1) + i];
+        bool finite = std::isfinite(beta_m);
+        for (double v : Hm) finite = finite && std::isfinite(v);
+        if (!finite) throw Error(WS_ERR_NUMERIC, "non-finite projected matrix in the Krylov iteration");
+        if (kind == 0) {
+            for (int i = 0; i < m; ++i)
+                for (int j = i + 1; j < m; ++j) {
+                    const double a = 0.5 * (Hm[(size_t)i * m + j] + Hm[(size_t)j * m + i]);
+                    Hm[(size_t)i * m + j] = Hm[(size_t)j * m + i] = a;
+                }
+            std::vector<double> A = Hm;
+            jacobi_sym(m, A, theta_r, Y);
+            std::fill(theta_i.begin(), theta_i.end(), 0.0);
+        } else {
+            std::vector<double> A = Hm;
+            if (!eig_general(m, A, theta_r, theta_i, Y)) throw Error(WS_ERR_NOCONV, "dense QR iteration did not converge");
+        }
+        // wanted: smallest real part of theta = 1/(lambda - sigma)  ('SA' / 'SR')
+        std::iota(order.begin(), order.end(), 0);
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return theta_r[a] < theta_r[b]; });
+        // Ritz residual estimates |beta_m * (last component of the unit eigenvector)|
+        auto colnorm = [&](int c, bool cplx) {
+            double s = 0.0;
+            for (int i = 0; i < m; ++i) {
+                s += Y[(size_t)i * m + c] * Y[(size_t)i * m + c];
+                if (cplx) s += Y[(size_t)i * m + c + 1] * Y[(size_t)i * m + c + 1];
+            }
+            return std::sqrt(s);
+        };
+        auto ritz_res = [&](int c) {
+            if (theta_i[c] == 0.0) return std::fabs(beta_m * Y[(size_t)(m - 1) * m + c]) / colnorm(c, false);
+            const int c0 = theta_i[c] > 0 ? c : c - 1;
+            const double lr = Y[(size_t)(m - 1) * m + c0], li = Y[(size_t)(m - 1) * m + c0 + 1];
+            return std::fabs(beta_m) * std::sqrt(lr * lr + li * li) / colnorm(c0, true);
+        };
+        nconv = 0;
+        for (int i = 0; i < nev; ++i) {
+            const int c = order[i];
+            resid[i] = ritz_res(c);
+            const double mag = std::hypot(theta_r[c], theta_i[c]);
+            if (resid[i] <= tol * std::max(eps23, mag)) ++nconv;
+        }
+        ++restarts;
+        if (nconv >= nev || restarts >= maxit) {
+            done = true;
+            break;
+        }
+        // ---- thick restart: keep k Ritz directions (ARPACK-style: more as they converge)
+        int k = nev + std::min(nconv, (m - nev) / 2);
+        if (k >= m - 1) k = m - 2;
+        // kept columns of Y; a complex-conjugate pair contributes its real and imaginary parts
+        std::vector<int> keep;
+        {
+            std::vector<char> used(m, 0);
+            for (int i = 0; i < m && (int)keep.size() < k; ++i) {
+                const int c = order[i];
+                if (used[c]) continue;
+                if (theta_i[c] == 0.0) {
+                    keep.push_back(c);
+                    used[c] = 1;
+                } else {
+                    const int c0 = theta_i[c] > 0.0 ? c : c - 1;
+                    if ((int)keep.size() + 2 > m - 2) break;
+                    keep.push_back(c0);
+                    keep.push_back(c0 + 1);
+                    used[c0] = used[c0 + 1] = 1;
+                }
+            }
+            k = (int)keep.size();
+        }
+        // orthonormal basis Q (m x k) of the kept invariant subspace (modified Gram-Schmidt, twice)
+        Qh.assign((size_t)m * k, 0.0);
+        for (int i = 0; i < k; ++i) {
+            const int c = keep[i];
+            for (int r = 0; r < m; ++r) Qh[(size_t)r * k + i] = Y[(size_t)r * m + c];
+        }
+        int kk = 0;
+        for (int i = 0; i < k; ++i) {
+            for (int pass = 0; pass < 2; ++pass)
+                for (int jq = 0; jq < kk; ++jq) {
+                    double d = 0.0;
+                    for (int r = 0; r < m; ++r) d += Qh[(size_t)r * k + jq] * Qh[(size_t)r * k + i];
+                    for (int r = 0; r < m; ++r) Qh[(size_t)r * k + i] -= d * Qh[(size_t)r * k + jq];
+                }
+            double nn = 0.0;
+            for (int r = 0; r < m; ++r) nn += Qh[(size_t)r * k + i] * Qh[(size_t)r * k + i];
+            nn = std::sqrt(nn);
+            if (nn < 1e-10) continue;     // linearly dependent direction: drop it
+            for (int r = 0; r < m; ++r) Qh[(size_t)r * k + kk] = Qh[(size_t)r * k + i] / nn;
+            ++kk;
+        }
+        // compact to m x kk row-major
+        std::vector<double> Qc((size_t)m * kk);
+        for (int r = 0; r < m; ++r)
+            for (int i = 0; i < kk; ++i) Qc[(size_t)r * kk + i] = Qh[(size_t)r * k + i];
+        kkeep = kk;
+        // new projected matrix: [Q^T H Q ; beta_m * (last row of Q)]
+        std::vector<double> HQ((size_t)m * kk, 0.0), Tn((size_t)kk * kk, 0.0);
+        for (int r = 0; r < m; ++r)
+            for (int c = 0; c < kk; ++c) {
+                double sacc = 0.0;
+                for (int q2 = 0; q2 < m; ++q2) sacc += Hm[(size_t)r * m + q2] * Qc[(size_t)q2 * kk + c];
+                HQ[(size_t)r * kk + c] = sacc;
+            }
+        for (int r = 0; r < kk; ++r)
+            for (int c = 0; c < kk; ++c) {
+                double sacc = 0.0;
+                for (int q2 = 0; q2 < m; ++q2) sacc += Qc[(size_t)q2 * kk + r] * HQ[(size_t)q2 * kk + c];
+                Tn[(size_t)r * kk + c] = sacc;
+            }
+        std::fill(Hh.begin(), Hh.end(), 0.0);
+        for (int c = 0; c < kk; ++c) {
+            for (int r = 0; r < kk; ++r) Hh[(size_t)c * (m + 1) + r] = Tn[(size_t)r * kk + c];
+            Hh[(size_t)c * (m + 1) + kk] = beta_m * Qc[(size_t)(m - 1) * kk + c];
+        }
+        WS_CUDA(cudaMemcpyAsync(W.Hd.get(), Hh.data(), Hh.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+        WS_CUDA(cudaMemcpyAsync(W.Q.get(), Qc.data(), Qc.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+        k_rotate<<<ceil_div(N, 128), 128, (size_t)m * kk * sizeof(double), st>>>(V, N, m, kk, W.Q.get(), N, 1, nullptr, 0);
+        if (kind == 0)
+            k_rotate<<<ceil_div(N, 128), 128, (size_t)m * kk * sizeof(double), st>>>(Z, N, m, kk, W.Q.get(), N, 1, nullptr, 0);
+        count_launch(kind == 0 ? 2 : 1);
+        WS_CUDA(cudaStreamSynchronize(st));     // Qc / Hh are host temporaries
+        j0 = kk;
+    }
+    // ---- Ritz vectors of the nev wanted eigenvalues, ordered by descending lambda = sigma + 1/theta
+    std::vector<int> sel(order.begin(), order.begin() + nev);
+    std::vector<double> lam(nev), lam_i(nev);
+    for (int i = 0; i < nev; ++i) {
+        const std::complex<double> th(theta_r[sel[i]], theta_i[sel[i]]);
+        const std::complex<double> l = sigma + 1.0 / th;
+        lam[i] = l.real();
+        lam_i[i] = l.imag();
+    }
+    std::vector<int> ord2(nev);
+    std::iota(ord2.begin(), ord2.end(), 0);
+    std::stable_sort(ord2.begin(), ord2.end(), [&](int a, int b) { return lam[a] > lam[b]; });
+    std::vector<double> Qx((size_t)m * nev), wh(nev), rh(nev);
+    int ncomplex = 0;
+    for (int i = 0; i < nev; ++i) {
+        const int c = sel[ord2[i]];
+        wh[i] = lam[ord2[i]];
+        rh[i] = resid[ord2[i]];
+        if (lam_i[ord2[i]] != 0.0) ++ncomplex;
+        const int c0 = theta_i[c] < 0 ? c - 1 : c;    // complex pair: return the real part
+        double nn = 0.0;
+        for (int r = 0; r < m; ++r) nn += Y[(size_t)r * m + c0] * Y[(size_t)r * m + c0];
+        nn = std::sqrt(nn);
+        for (int r = 0; r < m; ++r) Qx[(size_t)r * nev + i] = Y[(size_t)r * m + c0] / nn;
+    }
+    WS_CUDA(cudaMemcpyAsync(W.Q.get(), Qx.data(), Qx.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+    k_rotate<<<ceil_div(N, 128), 128, (size_t)m * nev * sizeof(double), st>>>(V, N, m, nev, W.Q.get(), N, 0, V_out, N);
+    count_launch(1);
+    if (kind == 1) {
+        // unit 2-norm rows (what ARPACK's dneupd returns)
+        for (int i = 0; i < nev; ++i) {
+            dots(W, V_out + (size_t)i * N, 1, V_out + (size_t)i * N, W.nrm.get() + i, nullptr);
+        }
+        k_scale_rows<<<nb, T, 0, st>>>(V_out, N, nev, W.nrm.get(), N);
+        count_launch(1);
+    }
+    WS_CUDA(cudaMemcpyAsync(w_out, wh.data(), nev * sizeof(double), cudaMemcpyHostToDevice, st));
+    WS_CUDA(cudaStreamSynchronize(st));
+    WS_CUDA(cudaGetLastError());
+    if (h_info) {
+        h_info[0] = nconv; h_info[1] = nops; h_info[2] = restarts; h_info[3] = ncomplex; h_info[4] = kkeep;
+    }
+    if (h_resid) std::copy(rh.begin(), rh.end(), h_resid);
+    if (nconv < nev) throw Error(WS_ERR_NOCONV, "eigensolver: " + std::to_string(nconv) + " of " + std::to_string(nev) +
+                                                    " eigenpairs converged in " + std::to_string(restarts) + " restarts");
+    WS_API_END
+}
+
+}  // extern "C"

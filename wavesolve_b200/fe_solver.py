@@ -275,3 +275,152 @@ def get_eff_index(wl, w):
     """fe_solver.py:431-434."""
     k = 2 * np.pi / wl
     return np.sqrt(w / k ** 2)
+
+
+# ---------------------------------------------------------------------------------------
+# reference API: eigen-solves
+# ---------------------------------------------------------------------------------------
+last_info = {}      # diagnostics of the most recent solve_waveguide / solve_waveguide_vec call
+
+
+def _eig_device(pattern, solver, B_vals, sigma, kind, nev, N, dev, ncv=0, tol=0.0, maxit=0, seed=0,
+                edges=None, xy=None, Ntt=0):
+    w = torch.empty(nev, dtype=torch.float64, device=dev)
+    V = torch.empty((nev, N), dtype=torch.float64, device=dev)
+    info = np.zeros(5, dtype=np.int64)
+    resid = np.zeros(nev, dtype=np.float64)
+    rc = _lib.lib().ws_eig_solve(pattern.handle, solver.handle, _dev.ptr(B_vals), float(sigma), int(kind),
+                                 int(nev), int(ncv), float(tol), int(maxit), int(seed),
+                                 _dev.ptr(edges), _dev.ptr(xy), int(Ntt), _dev.ptr(w), _dev.ptr(V),
+                                 info.ctypes.data, resid.ctypes.data, dev.index, _dev.stream_ptr(dev))
+    _lib.check(rc)
+    return w, V, dict(nconv=int(info[0]), n_op=int(info[1]), restarts=int(info[2]), ncomplex=int(info[3]),
+                      resid=resid)
+
+
+def _count_modes(w_iter, k, IOR_dict, always=False):
+    """fe_solver.py:330-346 / 409-424."""
+    IORs = [ior[1] for ior in IOR_dict.items()]
+    nmin, nmax = min(IORs), max(IORs)
+    mode_count = 0
+    for _w in w_iter:
+        if _w < 0:
+            continue
+        ne = np.sqrt(_w / k ** 2)
+        if (nmin <= ne <= nmax) or always:
+            mode_count += 1
+        else:
+            break
+    return mode_count
+
+
+def solve_waveguide(mesh, wl, IOR_dict, plot=False, ignore_warning=False, sparse=True, Nmax=10, order=2,
+                    target_neff=None, device=None, leaf_elems=None):
+    """Scalar modes (fe_solver.py:292-348).  Returns ``(w, v, N)``: eigenvalues in descending
+    order, eigenvectors as rows (B-orthonormal, like eigsh), number of guided modes.
+
+    The whole pipeline runs on the device: assembly -> multifrontal LDL^T of A - sigma B ->
+    B-orthogonal thick-restart Lanczos on (A - sigma B)^-1 B (the algorithm eigsh/ARPACK mode 3
+    runs on the host at fe_solver.py:328) with scipy's defaults ncv = max(2 Nmax + 1, 20), tol = eps.
+    ``sparse=False`` (LAPACK eigh on dense matrices in the reference, which cannot even assemble
+    them for order 2) is served by the same path with the shift at the top of the spectrum."""
+    from . import solver as _sv
+    k = 2 * np.pi / wl
+    if target_neff is None or not sparse:
+        est_eigval = np.power(k * max(IOR_dict.values()), 2)
+    else:
+        est_eigval = np.power(k * target_neff, 2)
+    if order == 2:
+        assert mesh.cells[1].data.shape[1] == 6, "must use order 2 mesh for order 2 solver."
+    elif order == 1:
+        assert mesh.cells[1].data.shape[1] == 3, "must use order 1 mesh for order 1 solver"
+        raise NotImplementedError("order=1 scalar solve is not on the accelerated path yet")
+    else:
+        raise NotImplementedError
+    prob = ScalarProblem(mesh, IOR_dict, k, device)
+    N = prob.N
+    if N > 2000 and not ignore_warning and not sparse:
+        raise Exception("A and B matrices are larger than 2000 x 2000 - this may make your system unstable. consider setting sparse=True")
+    with torch.cuda.device(prob.dev):
+        A, B = prob.assemble()
+        sym = _sv.Symbolic(prob.h_dofs, prob.centroids(), N, 0, leaf_elems or _sv.DEFAULT_LEAF_ELEMS)
+        S = _sv.Solver(prob.pattern, sym)
+        st = S.factor(A, B, est_eigval)
+        wd, Vd, info = _eig_device(prob.pattern, S, B, est_eigval, 0, Nmax, N, prob.dev)
+        w = _dev.d2h(wd)
+        v = _dev.d2h(Vd)
+        S.close()
+    info.update(factor=st, N=N, nnz=prob.pattern.nnz, sigma=float(est_eigval))
+    last_info.clear()
+    last_info.update(info)
+    mode_count = _count_modes(w, k, IOR_dict)
+    if plot:
+        _report_modes(wl, w, k, IOR_dict, warn_always=True)
+    return w, v, mode_count
+
+
+def solve_waveguide_vec(mesh, wl, IOR_dict, plot=False, ignore_warning=False, sparse=True, Nmax=10,
+                        target_neff=None, sparse_solve_mode='transform', verbose=True, device=None,
+                        leaf_elems=None):
+    """Vector modes with Whitney edge + P1 node elements (fe_solver.py:350-425).  Returns
+    ``(w, v, N)``; ``v`` rows have unit 2-norm (edge unknowns first, then nodes).
+
+    Every ``sparse_solve_mode`` is served by the same device path with the semantics of the
+    reference's default 'transform' (eigenpairs of C = (A - sigma B)^-1 B with the smallest real
+    part, w = sigma + 1/mu, fe_solver.py:398-400), applied matrix-free -- the reference builds the
+    dense N x N matrix C.  'transform'/'pardiso' return complex128 like scipy's eigs; 'straight'
+    (eigsh on an indefinite B, which the reference's author documents as unreliable) returns
+    float64 with the *correct* eigenpairs.  Eigenvalues are returned sorted by descending real
+    part (ARPACK's own order is not reproducible by any other implementation)."""
+    from . import solver as _sv
+    assert mesh.cells[1].data.shape[1] == 3, "must use order 1 mesh for vectorial solver"
+    assert sparse_solve_mode in ["straight", "transform", "pardiso"], "sparse solve mode must be `straight` (plug into eigenproblem into eigsh) or `transform` (use spsolve to convert into an ordinary eigenproblen, then use eigs)"
+    k = 2 * np.pi / wl
+    if target_neff is None:
+        est_eigval = np.power(k * max(IOR_dict.values()), 2)
+    else:
+        est_eigval = np.power(k * target_neff, 2)
+    if verbose:
+        print("building matrices ... ")
+    prob = VectorProblem(mesh, IOR_dict, k, device)
+    N = prob.N
+    if N > 2000 and not ignore_warning and not sparse:
+        raise Exception("A and B matrices are larger than 2000 x 2000 - this may make your system unstable. consider setting sparse=True")
+    if verbose:
+        print("solving...")
+    with torch.cuda.device(prob.dev):
+        A, B = prob.assemble()
+        Mq = prob.assemble_qd(est_eigval)
+        sym = _sv.Symbolic(prob.h_dofs, prob.centroids(), N, prob.Ntt, leaf_elems or _sv.DEFAULT_LEAF_ELEMS)
+        S = _sv.Solver(prob.pattern, sym)
+        st = S.factor(Mq)
+        wd, Vd, info = _eig_device(prob.pattern, S, B, est_eigval, 1, Nmax, N, prob.dev,
+                                   edges=prob.edges, xy=prob.xy, Ntt=prob.Ntt)
+        w = _dev.d2h(wd)
+        v = _dev.d2h(Vd)
+        S.close()
+    if verbose:
+        print("solving complete")
+    info.update(factor=st, N=N, nnz=prob.pattern.nnz, sigma=float(est_eigval))
+    last_info.clear()
+    last_info.update(info)
+    if sparse and sparse_solve_mode in ("transform", "pardiso"):
+        w = w.astype(np.complex128)             # scipy.sparse.linalg.eigs returns complex arrays
+        v = v.astype(np.complex128)
+    mode_count = _count_modes(w, k, IOR_dict, always=target_neff is not None)
+    if plot:
+        _report_modes(wl, w, k, IOR_dict, warn_always=target_neff is None)
+    return w, v, mode_count
+
+
+def _report_modes(wl, w, k, IOR_dict, warn_always=True):
+    """The printing half of ``plot=True`` (fe_solver.py:338-342, 416-420); drawing needs
+    matplotlib and stays on the host, outside this package."""
+    nmin, nmax = min(IOR_dict.values()), max(IOR_dict.values())
+    for _w in w:
+        if _w < 0:
+            continue
+        ne = np.sqrt(_w / k ** 2)
+        if not (nmin <= ne <= nmax) and warn_always:
+            print("warning: spurious mode! stopping plotting ... ")
+        print("effective index: ", get_eff_index(wl, _w))
