@@ -1,19 +1,23 @@
 #!/usr/bin/env python
-"""bench.py -- wavesolve FEM hot path on B200: assembly (+ eigensolve when built).
+"""bench.py -- wavesolve FEM hot path on B200: assembly + generalized sparse eigensolve.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
-One "step" = one pass of the hot path over one synthetic problem per GPU:
-workload c4 = vector (Whitney edge + P1 node) problem on a ~1M-triangle step-index-fibre
-mesh (BASELINE.json configs[3], the configuration the metric is quoted on).  At N>1 every
-rank runs its own problem of the same size (a sweep point: one problem per GPU, no data-path
-collective) -> weak scaling; value = work of all ranks / max-over-ranks time.
+Workload c4 (BASELINE.json configs[3], the configuration the metric is quoted on): vector
+modes (Whitney edge + P1 node elements) of a step-index fibre on a ~1M-triangle mesh, 10 modes.
+One "step" = one complete eigensolve from the mesh arrays: edge table (K1), CSR pattern (K2),
+assembly of A/B and of the quasi-definite shift-invert matrix (K4), nested-dissection analysis,
+multifrontal LDL^T (K8), Krylov iteration (K5-K10).  `value` = eigensolves/s with the mesh
+arrays resident in HBM; `e2e` = the same through the public API (get_unique_edges +
+solve_waveguide_vec) with host numpy in/out.  At N>1 every rank solves its own problem of the
+same size (sweep point: one problem per GPU, no data-path collective) -> weak scaling.
 
-Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for the byte accounting.
+Prints ONE JSON line (rank 0).  DESIGN.md "Measurement" states the byte/flop accounting.
 """
 from __future__ import annotations
 
 import argparse
+import copy
 import json
 import os
 import subprocess
@@ -27,16 +31,19 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WL = 1.55
+NMAX = 10
+METRIC = "eigensolves/s (10 vector modes, ~1M-triangle mesh, assembly + factorisation + Krylov iteration)"
+WORKLOAD = "c4: solve_waveguide_vec, step-index fibre r_core=5 r_clad=10, ~1M P1 triangles, Nmax=10 (BASELINE.json configs[3])"
 
 
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--elements", type=int, default=1_000_000)
-    ap.add_argument("--cpu-sample-elements", type=int, default=200_000)
+    ap.add_argument("--cpu-sample-elements", type=int, default=50_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -45,7 +52,7 @@ def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         try:
-            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
         except Exception:
             pass
     return 6650.0, "fallback (B200_PROFILING.md)"
@@ -104,24 +111,30 @@ def make_mesh(n_elements, seed=0):
 # reference arm / cpu baseline: the oracle port on the host cores
 # ---------------------------------------------------------------------------------------------
 def cpu_port_run(n_elements, steps=1, warmup=0):
-    """Times the numpy/scipy restatement of the reference path (oracle/restated.py: vectorised
-    get_unique_edges + construct_AB_vec; the literal reference is O(E^2)/dense and cannot run
-    these sizes) on a bounded sample."""
+    """The reference's algorithm for this path restated in numpy/scipy (oracle/restated.py:
+    vectorised get_unique_edges + construct_AB_vec + matrix-free 'transform' eigs with SuperLU),
+    timed on the host.  The literal reference cannot run the vector path beyond ~5k elements
+    (O(E^2) edge search, dense N x N matrices), and the 1M-element workload would
+    take well over ten minutes per solve on the CPU, so this is a BOUNDED sample: the same
+    geometry at `n_elements` triangles."""
     from oracle import restated as R
     mesh, ior = make_mesh(n_elements, seed=1)
-    k = 2 * np.pi / WL
-    ts = []
+    ts, info = [], None
     for it in range(warmup + steps):
+        m = copy.copy(mesh)
+        m.cells = [copy.copy(c) for c in mesh.cells]
         t0 = time.perf_counter()
-        R.get_unique_edges(mesh)
-        A, B = R.construct_AB_vec(mesh, ior, k)
+        R.get_unique_edges(m)
+        w, v, cnt, info = R.solve_waveguide_vec(m, WL, ior, Nmax=NMAX, return_info=True)
         dt = time.perf_counter() - t0
         if it >= warmup:
             ts.append(dt)
     t = float(np.mean(ts))
-    return {"value": mesh.num_elements / t, "unit": "elements/s", "cores": 1, "kind": "port",
-            "sample": "oracle/restated.py get_unique_edges + construct_AB_vec on a %d-triangle fibre mesh "
-                      "(numpy/scipy, single-threaded); %.2f s per pass" % (mesh.num_elements, t),
+    return {"value": 1.0 / t, "unit": "eigensolves/s", "cores": 1, "kind": "port",
+            "sample": "oracle/restated.py (numpy + scipy SuperLU/ARPACK, single-threaded like the reference's "
+                      "scipy path) on the same fibre at %d triangles instead of ~1M: %.2f s per solve, %d OP "
+                      "applications; CPU cost grows faster than linearly with size, so the 1M-triangle "
+                      "figure would be lower still" % (mesh.num_elements, t, info["n_op"]),
             "seconds": t, "elements": mesh.num_elements}
 
 
@@ -131,21 +144,17 @@ def run_reference(args):
         return
     r = cpu_port_run(args.cpu_sample_elements, steps=max(1, args.steps), warmup=min(1, args.warmup))
     line = {
-        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": "elements/s",
+        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": "eigensolves/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": r["seconds"] * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD, "elements": r["elements"],
-                   "note": "bounded CPU sample of the workload"},
+                   "note": "bounded CPU sample of the workload (see cpu_baseline.sample)"},
         "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
-        "e2e": {"value": r["value"], "unit": "elements/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "e2e": {"value": r["value"], "unit": "eigensolves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
-
-
-METRIC = "FEM elements/s assembled (vector Whitney+P1: edge table + CSR pattern + A,B values)"
-WORKLOAD = "c4: vector problem, step-index fibre, ~1M triangles (BASELINE.json configs[3])"
 
 
 # ---------------------------------------------------------------------------------------------
@@ -167,41 +176,32 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
 
     import wavesolve_b200 as ws
-    from wavesolve_b200 import _lib, fe_solver as fs, waveguide as wg, device as dv
+    from wavesolve_b200 import _lib, fe_solver as fs, waveguide as wg, device as dv, solver as sv
 
     mesh, ior = make_mesh(args.elements, seed=rank)
     k = 2 * np.pi / WL
+    sigma = float(np.power(k * max(ior.values()), 2))
     ne = mesh.num_elements
     tris_h = np.ascontiguousarray(np.asarray(mesh.cells[1].data)[:, :3].astype(np.int32))
     npts = mesh.points.shape[0]
-
-    # ---- device-resident step: inputs (mesh arrays) already in HBM -------------------------
-    tris_d = dv.h2d(tris_h, dev)
-    # (the mesh object needs the edge table for the material-major marshalling; get it once)
-    wg.get_unique_edges(mesh)
     ev = lambda: torch.cuda.Event(enable_timing=True)
-    asm_ms = []
 
-    def device_step(prob, record):
-        # K1 edge table on device
-        edges_d, eidx_d = wg.unique_edges_device(tris_d, npts)
-        # K2 pattern + K4 assembly
-        pat = fs.DevicePattern(prob.dofs, prob.N)
-        old = prob.pattern
-        prob.pattern = pat
-        old.close()
-        if record:
-            e0, e1 = ev(), ev()
-            e0.record()
-        A, B = prob.assemble()
-        if record:
-            e1.record()
-            asm_ms.append((e0, e1))
-        return A, B
+    # ---- resident inputs (mesh arrays in HBM before the timed region) ------------------------
+    mesh_e = copy.copy(mesh)
+    mesh_e.cells = [copy.copy(c) for c in mesh.cells]
+    wg.get_unique_edges(mesh_e)
+    base = fs.VectorProblem(mesh_e, ior, k, device=dev)
+    tris_d = dv.h2d(tris_h, dev)
+    N, Ntt = base.N, base.Ntt
+    stats = {}
 
-    prob = fs.VectorProblem(mesh, ior, k, device=dev)
-    nnz = prob.pattern.nnz
-    N = prob.N
+    def device_step():
+        wg.unique_edges_device(tris_d, npts)                       # K1
+        prob = base.fresh_pattern()                                # K2
+        wd, Vd, info = fs.solve_vector_resident(prob, sigma, NMAX)  # K4, K8, K5-K10
+        prob.pattern.close()
+        stats.update(info)
+        return wd, Vd
 
     def barrier():
         torch.cuda.synchronize()
@@ -210,22 +210,60 @@ def run_ours(args):
             torch.cuda.synchronize()
 
     for _ in range(args.warmup):
-        device_step(prob, False)
+        device_step()
     barrier()
     l0 = _lib.launch_count()
     with ClockSampler(local) as clk:
         t0e, t1e = ev(), ev()
         t0e.record()
         for _ in range(args.steps):
-            device_step(prob, True)
+            wd, Vd = device_step()
         t1e.record()
         barrier()
         dev_ms = t0e.elapsed_time(t1e) / args.steps
-    launches = _lib.launch_count() - l0
-    k_ms = float(np.mean([a.elapsed_time(b) for a, b in asm_ms]))
+    launches = (_lib.launch_count() - l0) // max(1, args.steps)
+    nnz = base.pattern.nnz
+    fstat = stats["factor"]
 
-    # ---- end to end through the public API with host buffers -------------------------------
-    import copy
+    # ---- dominant kernel family: the two solve sweeps (k_fwd_gemv + k_bwd_gemvT), timed live ---
+    prob = base.fresh_pattern()
+    A, B = prob.assemble()
+    Mq = prob.assemble_qd(sigma)
+    sym = sv.Symbolic(prob.h_dofs, prob.centroids(), N, Ntt)
+    S = sv.Solver(prob.pattern, sym)
+    e0, e1 = ev(), ev()
+    e0.record()
+    S.factor(Mq)
+    e1.record()
+    torch.cuda.synchronize()
+    factor_ms = e0.elapsed_time(e1)
+    b = torch.randn(N, dtype=torch.float64, device=dev)
+    x = S.solve(b)
+    nrep = 20
+    e0.record()
+    for _ in range(nrep):
+        S.solve(b, out=x)
+    e1.record()
+    torch.cuda.synchronize()
+    solve_ms = e0.elapsed_time(e1) / nrep
+    y = torch.empty_like(b)
+    prob.pattern.spmv(B, b, out=y)
+    e0.record()
+    for _ in range(nrep):
+        prob.pattern.spmv(B, b, out=y)
+    e1.record()
+    torch.cuda.synchronize()
+    spmv_ms = e0.elapsed_time(e1) / nrep
+    e0.record()
+    for _ in range(nrep):
+        prob.assemble()
+    e1.record()
+    torch.cuda.synchronize()
+    asm_ms = e0.elapsed_time(e1) / nrep
+    S.close()
+    prob.pattern.close()
+
+    # ---- end to end through the public API with host buffers ---------------------------------
     e2e_t = []
     h2d_b = d2h_b = 0
     for it in range(max(1, min(args.steps, 3)) + 1):
@@ -234,46 +272,52 @@ def run_ours(args):
         barrier()
         t0 = time.perf_counter()
         edges, eidx = ws.get_unique_edges(m)
-        A, B = ws.construct_AB_vec(m, ior, k, sparse=True)
+        w, v, cnt = ws.solve_waveguide_vec(m, WL, ior, Nmax=NMAX, verbose=False)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         if it > 0:
             e2e_t.append(dt)
-        h2d_b = tris_h.nbytes + (mesh.points[:, :2].nbytes + tris_h.nbytes * 3 + 8 * ne)
-        d2h_b = edges.nbytes // 2 + eidx.nbytes // 2 + A.data.nbytes + A.indices.nbytes + A.indptr.nbytes \
-            + B.data.nbytes + B.indices.nbytes + B.indptr.nbytes
+        h2d_b = tris_h.nbytes + base.h2d_bytes
+        d2h_b = edges.shape[0] * 2 * 4 + eidx.size * 4 + NMAX * 8 + NMAX * N * 8
     e2e_s = float(np.mean(e2e_t))
 
-    # max over ranks
+    total = float(world)
     if world > 1:
-        t = torch.tensor([dev_ms, e2e_s, k_ms], dtype=torch.float64, device=dev)
+        t = torch.tensor([dev_ms, e2e_s, solve_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dev_ms, e2e_s, k_ms = [float(x) for x in t.tolist()]
-        tot = torch.tensor([float(ne)], dtype=torch.float64, device=dev)
-        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-        total_elems = float(tot.item())
-    else:
-        total_elems = float(ne)
+        dev_ms, e2e_s, solve_ms = [float(x_) for x_ in t.tolist()]
 
     peak, peak_src = peaks()
-    # algorithmic bytes of the vector assembly kernel: connectivity 12 B +
-    # k^2n^2 8 B per element, vertex coordinates 16 B per vertex, 8 B per stored value of A and B
-    algo_bytes = ne * (12 + 8) + 16 * npts + 8 * 2 * nnz
-    achieved = algo_bytes / (k_ms * 1e-3) / 1e9
+    # algorithmic bytes of one solve (both sweeps): the inverted panels are read once per sweep
+    solve_bytes = 2 * 8 * fstat["nnzL"]
+    achieved = solve_bytes / (solve_ms * 1e-3) / 1e9
+    n_op = int(stats.get("n_op", 0))
     line = {
-        "metric": METRIC, "value": total_elems / (dev_ms * 1e-3), "unit": "elements/s",
+        "metric": METRIC, "value": total / (dev_ms * 1e-3), "unit": "eigensolves/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": WORKLOAD, "elements_per_gpu": ne, "N": N, "nnz": nnz,
-                   "l2": "inputs_larger_than_l2 (%.0f MB touched per step)" % ((algo_bytes + 96 * ne) / 1e6),
+        "config": {"workload": WORKLOAD, "elements_per_gpu": ne, "N": N, "nnz": nnz, "Nmax": NMAX,
+                   "ncv": max(2 * NMAX + 1, 20), "tol": "eps (scipy default tol=0)",
+                   "l2": "inputs_larger_than_l2 (factor panels %.1f GB, basis %.2f GB per step)"
+                         % (8 * fstat["nnzL"] / 1e9, 8 * 22 * N / 1e9),
                    "parallelism": "one problem per GPU"},
-        "roofline": {"bound": "hbm", "kernel": "k_assemble_rows<VectorP1>", "achieved": achieved,
-                     "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
-                     "algorithmic_bytes": algo_bytes, "kernel_ms": k_ms, "traffic": None},
-        "e2e": {"value": total_elems / e2e_s, "unit": "elements/s", "h2d_bytes_per_step": int(h2d_b),
+        "assembly": {"elements_per_s": ne / (asm_ms * 1e-3), "kernel_ms": asm_ms,
+                     "algorithmic_bytes": ne * 20 + 16 * npts + 16 * nnz,
+                     "GBps": (ne * 20 + 16 * npts + 16 * nnz) / (asm_ms * 1e-3) / 1e9,
+                     "frac_of_peak": (ne * 20 + 16 * npts + 16 * nnz) / (asm_ms * 1e-3) / 1e9 / peak},
+        "spmv": {"kernel_ms": spmv_ms, "GBps": (12 * nnz + 20 * N) / (spmv_ms * 1e-3) / 1e9,
+                 "frac_of_peak": (12 * nnz + 20 * N) / (spmv_ms * 1e-3) / 1e9 / peak},
+        "factor": {"ms": factor_ms, "flops": fstat["flops"], "TFLOPs": fstat["flops"] / (factor_ms * 1e-3) / 1e12,
+                   "nnzL": fstat["nnzL"], "fronts": fstat["fronts"], "max_front": fstat["maxfront"]},
+        "eig": {"op_applications": n_op, "restarts": int(stats.get("restarts", 0)), "converged": int(stats.get("nconv", 0))},
+        "roofline": {"bound": "hbm", "kernel": "k_fwd_gemv + k_bwd_gemvT (one shift-invert solve: both sweeps over the inverted panels; "
+                                               "%d solves per eigensolve, the largest share of the step)" % n_op,
+                     "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
+                     "algorithmic_bytes": solve_bytes, "kernel_ms": solve_ms, "traffic": None},
+        "e2e": {"value": total / e2e_s, "unit": "eigensolves/s", "h2d_bytes_per_step": int(h2d_b),
                 "d2h_bytes_per_step": int(d2h_b), "seconds": e2e_s,
-                "api": "get_unique_edges + construct_AB_vec(sparse=True) with host numpy in/out"},
+                "api": "get_unique_edges(mesh) + solve_waveguide_vec(mesh, wl, IOR_dict, Nmax=10) with host numpy in/out"},
         "gpu_launches": int(launches),
         "clocks": clk.summary(),
     }

@@ -104,6 +104,11 @@ struct DeviceGuard {
 
 inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
+// keep freed stream-ordered allocations cached in the device's default pool (the solver
+// allocates ~12 GB per 1M-element problem; returning it to the OS after every solve costs
+// ~100 ms per call).  Idempotent, called by the handle constructors.
+void configure_mempool(int device);
+
 // global launch counter (bench.py reports how many of OUR kernels ran in the timed region)
 void count_launch(int n = 1);
 

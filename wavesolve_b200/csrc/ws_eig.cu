@@ -15,8 +15,10 @@
 // sweep and its eigen-decomposition (Jacobi for the symmetric case, Hessenberg + shifted QR
 // otherwise), the convergence test and the restart rotation are computed in plain C++.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <complex>
+#include <cstdlib>
 #include <numeric>
 
 #include "ws_solver.cuh"
@@ -624,6 +626,15 @@ int ws_eig_solve(const ws_pattern* p, ws_solver* s, const double* B_vals, double
         count_launch(1);
     };
 
+    // optional phase timing (WS_TRACE=1): synchronises after every phase, diagnostic only
+    const bool trace = getenv("WS_TRACE") != nullptr;
+    double tr_op = 0, tr_orth = 0, tr_norm = 0, tr_host = 0, tr_rot = 0, tr_t0 = 0;
+    auto tick = [&]() {
+        if (!trace) return 0.0;
+        cudaStreamSynchronize(st);
+        return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+    };
+    tr_t0 = tick();
     // ---- start vector: random, pushed once through OP (stays in range(OP), as ARPACK does)
     k_random<<<nb, T, 0, st>>>(W.w.get(), N, seed ? seed : 0x5DEECE66Dull);
     count_launch(1);
@@ -643,8 +654,11 @@ int ws_eig_solve(const ws_pattern* p, ws_solver* s, const double* B_vals, double
     int kkeep = 0;
     while (!done) {
         for (int j = j0; j < m; ++j) {
+            double ta = tick();
             apply_op(j);
             ++nops;
+            double tb = tick();
+            tr_op += tb - ta;
             double* Hcol = W.Hd.get() + (size_t)j * (m + 1);
             // CGS2 against rows 0..j : coefficients with the dual basis, update with the primal one
             for (int pass = 0; pass < 2; ++pass) {
@@ -652,8 +666,12 @@ int ws_eig_solve(const ws_pattern* p, ws_solver* s, const double* B_vals, double
                 k_update<<<nb, T, 0, st>>>(W.w.get(), V, N, j + 1, W.h.get(), N);
                 count_launch(1);
             }
+            double tc = tick();
+            tr_orth += tc - tb;
             normalize_into(j + 1, Hcol + (j + 1));
+            tr_norm += tick() - tc;
         }
+        double th0 = tick();
         WS_CUDA(cudaMemcpyAsync(Hh.data(), W.Hd.get(), Hh.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
         WS_CUDA(cudaStreamSynchronize(st));
         WS_CUDA(cudaGetLastError());
@@ -776,6 +794,8 @@ int ws_eig_solve(const ws_pattern* p, ws_solver* s, const double* B_vals, double
             for (int r = 0; r < kk; ++r) Hh[(size_t)c * (m + 1) + r] = Tn[(size_t)r * kk + c];
             Hh[(size_t)c * (m + 1) + kk] = beta_m * Qc[(size_t)(m - 1) * kk + c];
         }
+        double th1 = tick();
+        tr_host += th1 - th0;
         WS_CUDA(cudaMemcpyAsync(W.Hd.get(), Hh.data(), Hh.size() * sizeof(double), cudaMemcpyHostToDevice, st));
         WS_CUDA(cudaMemcpyAsync(W.Q.get(), Qc.data(), Qc.size() * sizeof(double), cudaMemcpyHostToDevice, st));
         k_rotate<<<ceil_div(N, 128), 128, (size_t)m * kk * sizeof(double), st>>>(V, N, m, kk, W.Q.get(), N, 1, nullptr, 0);
@@ -783,6 +803,7 @@ int ws_eig_solve(const ws_pattern* p, ws_solver* s, const double* B_vals, double
             k_rotate<<<ceil_div(N, 128), 128, (size_t)m * kk * sizeof(double), st>>>(Z, N, m, kk, W.Q.get(), N, 1, nullptr, 0);
         count_launch(kind == 0 ? 2 : 1);
         WS_CUDA(cudaStreamSynchronize(st));     // Qc / Hh are host temporaries
+        tr_rot += tick() - th1;
         j0 = kk;
     }
     // ---- Ritz vectors of the nev wanted eigenvalues, ordered by descending lambda = sigma + 1/theta
@@ -824,6 +845,10 @@ int ws_eig_solve(const ws_pattern* p, ws_solver* s, const double* B_vals, double
     WS_CUDA(cudaMemcpyAsync(w_out, wh.data(), nev * sizeof(double), cudaMemcpyHostToDevice, st));
     WS_CUDA(cudaStreamSynchronize(st));
     WS_CUDA(cudaGetLastError());
+    if (trace)
+        fprintf(stderr, "[ws_eig] kind=%d N=%lld ops=%lld restarts=%d total=%.1f ms: op=%.1f orth=%.1f norm=%.1f host=%.1f rotate=%.1f\n",
+                kind, (long long)N, (long long)nops, restarts, (tick() - tr_t0) * 1e3, tr_op * 1e3, tr_orth * 1e3, tr_norm * 1e3,
+                tr_host * 1e3, tr_rot * 1e3);
     if (h_info) {
         h_info[0] = nconv; h_info[1] = nops; h_info[2] = restarts; h_info[3] = ncomplex; h_info[4] = kkeep;
     }

@@ -16,7 +16,9 @@
 //
 // Replaces SuperLU (scipy splu / spsolve) behind fe_solver.py:328 and fe_solver.py:398.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
+#include <cstdlib>
 
 #include "ws_solver.cuh"
 
@@ -723,8 +725,15 @@ int ws_solver_create(const ws_pattern* p, const ws_symbolic* sym, ws_solver** ou
     WS_REQUIRE(p && sym, "null handle");
     WS_REQUIRE(p->N == sym->S.N, "pattern and symbolic analysis have different sizes");
     DeviceGuard g(device);
+    configure_mempool(device);
     cudaStream_t st = (cudaStream_t)stream;
     auto* s = new ws_solver();
+    const bool trace = getenv("WS_TRACE") != nullptr;
+    auto tnow = [&]() {
+        if (trace) cudaStreamSynchronize(st);
+        return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+    };
+    const double tc0 = tnow();
     try {
         const Symbolic& Y = sym->S;
         s->device = device;
@@ -758,6 +767,7 @@ int ws_solver_create(const ws_pattern* p, const ws_symbolic* sym, ws_solver** ou
         s->stats.alloc(4, st);
         s->dest.alloc(p->nnz, st);
         s->bytes = (3 * Y.Ltotal + Y.Utotal + Y.Wtotal + 5 * Y.N) * 8 + p->nnz * 8;
+        const double tc1 = tnow();
         const int T = 128;
         k_dest_map<<<ceil_div(Y.N, T), T, 0, st>>>(Y.N, p->rowptr.get(), p->colidx.get(), s->iperm.get(),
                                                      s->node_of_new.get(), view(s), s->dest.get());
@@ -766,7 +776,11 @@ int ws_solver_create(const ws_pattern* p, const ws_symbolic* sym, ws_solver** ou
         unsigned long long bad = 0;
         WS_CUDA(cudaMemcpyAsync(&bad, s->stats.get(), sizeof bad, cudaMemcpyDeviceToHost, st));
         count_launch(2);
+        const double tc2 = tnow();
         build_plan(s, st);   // synchronises the stream
+        if (trace)
+            fprintf(stderr, "[ws_solver_create] copy+upload+alloc %.1f ms, dest map %.1f ms, plan %.1f ms\n",
+                    (tc1 - tc0) * 1e3, (tc2 - tc1) * 1e3, (tnow() - tc2) * 1e3);
         WS_CUDA(cudaGetLastError());
         if (bad) throw Error(WS_ERR_STATE, "pattern and symbolic analysis are inconsistent (matrix entry outside its front)");
     } catch (...) {

@@ -17,6 +17,17 @@ void set_last_error(const std::string& s) { g_last_error = s; }
 static long long g_launches = 0;
 void count_launch(int n) { g_launches += n; }
 
+void configure_mempool(int device) {
+    static bool done[64] = {false};
+    if (device < 0 || device >= 64 || done[device]) return;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        unsigned long long thr = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    done[device] = true;
+}
+
 // ---------------------------------------------------------------------------------------
 // small kernels
 // ---------------------------------------------------------------------------------------
@@ -257,6 +268,7 @@ int ws_pattern_create(const int32_t* dofs, int64_t Ne, int64_t N, ws_pattern** o
     WS_REQUIRE(N < ((int64_t)1 << 31), "N must fit int32");
     WS_REQUIRE(Ne * 36 < ((int64_t)1 << 31), "36*Ne must fit int32 (scipy int32 index arrays)");
     DeviceGuard g(device);
+    configure_mempool(device);
     cudaStream_t st = (cudaStream_t)stream;
     auto* P = new ws_pattern();
     try {

@@ -78,12 +78,6 @@ void parallel_for(int64_t n, int nthreads, F f) {
     for (auto& x : th) x.join();
 }
 
-inline int level_of(int64_t node) {
-    int l = 0;
-    while ((node >> (l + 1)) != 0) ++l;
-    return l;
-}
-
 }  // namespace
 
 void analyse_host(Symbolic& S, const int32_t* dofs, int64_t Ne, int64_t N, const double* exy,
@@ -115,54 +109,108 @@ void analyse_host(Symbolic& S, const int32_t* dofs, int64_t Ne, int64_t N, const
         for (int64_t i = leaf_lo[j]; i < leaf_lo[j + 1]; ++i) leaf_of[pts[i].id] = (int32_t)j;
     S.t_kd = now() - t0;
 
-    // ---- 2. owners
+    // ---- 2. owners (parallel over elements; min / max leaf per unknown with relaxed CAS)
     t0 = now();
     std::vector<int32_t> lo(N, INT_MAX), hi(N, -1);
-    for (int64_t e = 0; e < Ne; ++e) {
-        const int32_t lf = leaf_of[e];
-        for (int a = 0; a < 6; ++a) {
-            const int32_t d = dofs[e * 6 + a];
-            WS_REQUIRE(d >= 0 && d < N, "analyse: unknown id out of range");
-            if (lf < lo[d]) lo[d] = lf;
-            if (lf > hi[d]) hi[d] = lf;
-        }
+    {
+        int32_t* plo = lo.data();
+        int32_t* phi = hi.data();
+        std::vector<int> bad(nthreads, 0);
+        std::vector<std::thread> th;
+        for (int t = 0; t < nthreads; ++t)
+            th.emplace_back([&, t]() {
+                const int64_t e0 = Ne * t / nthreads, e1 = Ne * (t + 1) / nthreads;
+                for (int64_t e = e0; e < e1; ++e) {
+                    const int32_t lf = leaf_of[e];
+                    for (int a = 0; a < 6; ++a) {
+                        const int32_t d = dofs[e * 6 + a];
+                        if (d < 0 || d >= N) { bad[t] = 1; continue; }
+                        int32_t cur = __atomic_load_n(plo + d, __ATOMIC_RELAXED);
+                        while (lf < cur && !__atomic_compare_exchange_n(plo + d, &cur, lf, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
+                        cur = __atomic_load_n(phi + d, __ATOMIC_RELAXED);
+                        while (lf > cur && !__atomic_compare_exchange_n(phi + d, &cur, lf, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
+                    }
+                }
+            });
+        for (auto& x : th) x.join();
+        for (int b : bad) WS_REQUIRE(!b, "analyse: unknown id out of range");
     }
-    std::vector<int32_t> node(N);
-    for (int64_t d = 0; d < N; ++d) {
-        if (hi[d] < 0)
-            throw Error(WS_ERR_NUMERIC, "matrix is singular: unknown " + std::to_string(d) +
-                                            " belongs to no element (empty row)");
-        uint32_t x = (uint32_t)(lo[d] ^ hi[d]);
-        int hb = x ? 32 - __builtin_clz(x) : 0;
-        node[d] = (int32_t)((((int64_t)1 << depth) + lo[d]) >> hb);
-    }
-    // ---- 3. elimination order: level-major bottom-up, class, old index
+    // ---- 3. elimination order: level-major bottom-up, class, old index (stable parallel counting sort)
     std::vector<int64_t> levelbase(depth + 2, 0);
     for (int l = depth; l >= 1; --l) levelbase[l - 1] = levelbase[l] + ((int64_t)1 << l);
-    auto prank = [&](int64_t nd) { int l = level_of(nd); return levelbase[l] + nd - ((int64_t)1 << l); };
-    std::vector<int64_t> cnt2(2 * nfronts + 1, 0);
-    for (int64_t d = 0; d < N; ++d) cnt2[2 * prank(node[d]) + (d >= cls_start ? 0 : 1) + 1]++;
-    for (size_t i = 1; i < cnt2.size(); ++i) cnt2[i] += cnt2[i - 1];
+    auto prank = [&](int64_t nd) { int l = 63 - __builtin_clzll((unsigned long long)nd); return levelbase[l] + nd - ((int64_t)1 << l); };
+    const int64_t nbuckets = 2 * nfronts;
+    std::vector<int32_t> bucket(N);
+    std::vector<std::vector<int64_t>> hist(nthreads);
+    std::vector<int64_t> missing(nthreads, -1);
+    {
+        std::vector<std::thread> th;
+        for (int t = 0; t < nthreads; ++t)
+            th.emplace_back([&, t]() {
+                hist[t].assign(nbuckets, 0);
+                const int64_t d0 = N * t / nthreads, d1 = N * (t + 1) / nthreads;
+                for (int64_t d = d0; d < d1; ++d) {
+                    if (hi[d] < 0) { if (missing[t] < 0) missing[t] = d; bucket[d] = 0; continue; }
+                    const uint32_t x = (uint32_t)(lo[d] ^ hi[d]);
+                    const int hb = x ? 32 - __builtin_clz(x) : 0;
+                    const int64_t nd = (((int64_t)1 << depth) + lo[d]) >> hb;
+                    const int32_t b = (int32_t)(2 * prank(nd) + (d >= cls_start ? 0 : 1));
+                    bucket[d] = b;
+                    hist[t][b]++;
+                }
+            });
+        for (auto& x : th) x.join();
+    }
+    for (int t = 0; t < nthreads; ++t)
+        if (missing[t] >= 0)
+            throw Error(WS_ERR_NUMERIC, "matrix is singular: unknown " + std::to_string(missing[t]) +
+                                            " belongs to no element (empty row)");
+    // exclusive prefix over (bucket, thread)
+    std::vector<int64_t> bstart(nbuckets + 1, 0);
+    {
+        int64_t run = 0;
+        for (int64_t b = 0; b < nbuckets; ++b) {
+            bstart[b] = run;
+            for (int t = 0; t < nthreads; ++t) {
+                const int64_t c = hist[t][b];
+                hist[t][b] = run;
+                run += c;
+            }
+        }
+        bstart[nbuckets] = run;
+    }
     S.p.assign(nfronts, 0);
     S.q.assign(nfronts, 0);
     S.start.assign(nfronts, 0);
     for (int64_t nd = 1; nd < nfronts; ++nd) {
-        int64_t r = prank(nd);
-        S.start[nd] = cnt2[2 * r];
-        S.p[nd] = (int32_t)(cnt2[2 * r + 2] - cnt2[2 * r]);
+        const int64_t r = prank(nd);
+        S.start[nd] = bstart[2 * r];
+        S.p[nd] = (int32_t)(bstart[2 * r + 2] - bstart[2 * r]);
     }
     S.perm.resize(N);
     S.iperm.resize(N);
     S.node_of_new.resize(N);
     {
-        std::vector<int64_t> cur(cnt2.begin(), cnt2.end() - 1);
-        for (int64_t d = 0; d < N; ++d) {
-            int64_t slot = 2 * prank(node[d]) + (d >= cls_start ? 0 : 1);
-            int64_t nw = cur[slot]++;
-            S.iperm[d] = (int32_t)nw;
-            S.perm[nw] = (int32_t)d;
-            S.node_of_new[nw] = node[d];
+        // bucket -> front id (inverse of prank)
+        std::vector<int32_t> node_of_bucket(nbuckets);
+        for (int64_t nd = 1; nd < nfronts; ++nd) {
+            const int64_t r = prank(nd);
+            node_of_bucket[2 * r] = node_of_bucket[2 * r + 1] = (int32_t)nd;
         }
+        std::vector<std::thread> th;
+        for (int t = 0; t < nthreads; ++t)
+            th.emplace_back([&, t]() {
+                const int64_t d0 = N * t / nthreads, d1 = N * (t + 1) / nthreads;
+                int64_t* cur = hist[t].data();
+                for (int64_t d = d0; d < d1; ++d) {
+                    const int32_t b = bucket[d];
+                    const int64_t nw = cur[b]++;
+                    S.iperm[d] = (int32_t)nw;
+                    S.perm[nw] = (int32_t)d;
+                    S.node_of_new[nw] = node_of_bucket[b];
+                }
+            });
+        for (auto& x : th) x.join();
     }
     S.t_order = now() - t0;
 

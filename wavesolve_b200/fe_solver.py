@@ -144,6 +144,15 @@ def _element_centroids(h_xy, vert_ids):
 class VectorProblem:
     """Device-resident vector (Whitney + P1) problem."""
 
+    def fresh_pattern(self):
+        """A new problem object that shares the resident input arrays (coordinates,
+        connectivity, material data) but rebuilds the pattern -- bench.py's device-resident step."""
+        o = object.__new__(VectorProblem)
+        o.__dict__.update(self.__dict__)
+        with torch.cuda.device(self.dev):
+            o.pattern = DevicePattern(o.dofs, o.N)
+        return o
+
     def __init__(self, mesh, IOR_dict, k, device=None):
         self.dev = dev = _dev.require_cuda(device)
         tris, k2 = _material_major(mesh, IOR_dict, k)
@@ -359,6 +368,26 @@ def solve_waveguide(mesh, wl, IOR_dict, plot=False, ignore_warning=False, sparse
     return w, v, mode_count
 
 
+def solve_vector_resident(prob, sigma, Nmax, leaf_elems=None, symbolic=None):
+    """Device part of the vector solve on a resident VectorProblem: assembly of B and of the
+    quasi-definite M', symbolic analysis (host), factorisation, Krylov iteration.  Returns
+    device tensors (w, V) and diagnostics."""
+    from . import solver as _sv
+    A, B = prob.assemble()
+    Mq = prob.assemble_qd(sigma)
+    sym = symbolic or _sv.Symbolic(prob.h_dofs, prob.centroids(), prob.N, prob.Ntt,
+                                   leaf_elems or _sv.DEFAULT_LEAF_ELEMS)
+    S = _sv.Solver(prob.pattern, sym)
+    try:
+        st = S.factor(Mq)
+        wd, Vd, info = _eig_device(prob.pattern, S, B, sigma, 1, Nmax, prob.N, prob.dev,
+                                   edges=prob.edges, xy=prob.xy, Ntt=prob.Ntt)
+    finally:
+        S.close()
+    info.update(factor=st, N=prob.N, nnz=prob.pattern.nnz, sigma=float(sigma))
+    return wd, Vd, info
+
+
 def solve_waveguide_vec(mesh, wl, IOR_dict, plot=False, ignore_warning=False, sparse=True, Nmax=10,
                         target_neff=None, sparse_solve_mode='transform', verbose=True, device=None,
                         leaf_elems=None):
@@ -389,19 +418,11 @@ def solve_waveguide_vec(mesh, wl, IOR_dict, plot=False, ignore_warning=False, sp
     if verbose:
         print("solving...")
     with torch.cuda.device(prob.dev):
-        A, B = prob.assemble()
-        Mq = prob.assemble_qd(est_eigval)
-        sym = _sv.Symbolic(prob.h_dofs, prob.centroids(), N, prob.Ntt, leaf_elems or _sv.DEFAULT_LEAF_ELEMS)
-        S = _sv.Solver(prob.pattern, sym)
-        st = S.factor(Mq)
-        wd, Vd, info = _eig_device(prob.pattern, S, B, est_eigval, 1, Nmax, N, prob.dev,
-                                   edges=prob.edges, xy=prob.xy, Ntt=prob.Ntt)
+        wd, Vd, info = solve_vector_resident(prob, est_eigval, Nmax, leaf_elems)
         w = _dev.d2h(wd)
         v = _dev.d2h(Vd)
-        S.close()
     if verbose:
         print("solving complete")
-    info.update(factor=st, N=N, nnz=prob.pattern.nnz, sigma=float(est_eigval))
     last_info.clear()
     last_info.update(info)
     if sparse and sparse_solve_mode in ("transform", "pardiso"):
