@@ -117,16 +117,19 @@ int ws_spmv(const ws_pattern* p, const double* vals, const double* x, double* y,
 /* ---- K8a: symbolic analysis of the sparse factorisation (host) ---------------------------
  * Replaces the COLAMD ordering + symbolic phase of SuperLU inside scipy splu / spsolve
  * (fe_solver.py:328 through eigsh sigma mode, fe_solver.py:398).  Element-based geometric
- * nested dissection: h_dofs [Ne*6] as for ws_pattern_create, h_elem_xy [Ne*2] element
- * centroids (both HOST arrays).  Unknowns with id >= first_class_start are eliminated first
+ * nested dissection: h_dofs [Ne*6] as for ws_pattern_create, h_xy [Np*2] node coordinates
+ * (both HOST arrays); the element centroids are formed from the three vertex ids stored at
+ * h_dofs[e*6 + vert_col + 0..2] - vert_offset (scalar P2: vert_col 0, offset 0; vector:
+ * vert_col 3, offset Ntt).  Unknowns with id >= first_class_start are eliminated first
  * inside every front (vector problem: pass Ntt so nodes precede edges; scalar: pass 0).
  * The result depends on the mesh only and is reusable across wavelengths and shifts.
  * ws_symbolic_query: h_info[8] = N, depth, nfronts, nnz(L), sum q^2, max front, max pivot
  * block, sum q;  h_dinfo[4] = factor flops, seconds k-d, seconds ordering, seconds boundaries.
  * ws_symbolic_export: perm [N] (new -> old), p,q,start [nfronts] (heap ids, 0 unused),
  * bndoff [nfronts+1], bnd / rel [sum q]. Any output pointer may be NULL.                  */
-int ws_symbolic_create(const int32_t* h_dofs, int64_t Ne, int64_t N, const double* h_elem_xy,
-                       int64_t first_class_start, int leaf_elems, ws_symbolic** out);
+int ws_symbolic_create(const int32_t* h_dofs, int64_t Ne, int64_t N, const double* h_xy, int64_t Np,
+                       int vert_col, int64_t vert_offset, int64_t first_class_start, int leaf_elems,
+                       ws_symbolic** out);
 int ws_symbolic_query(const ws_symbolic* s, int64_t* h_info, double* h_dinfo);
 int ws_symbolic_export(const ws_symbolic* s, int32_t* h_perm, int32_t* h_p, int32_t* h_q,
                        int64_t* h_start, int64_t* h_bndoff, int32_t* h_bnd, int32_t* h_rel);

@@ -32,7 +32,7 @@ def test_scalar_factor_solve(ws, ne, leaf, target):
     prob = fs.ScalarProblem(mesh, mg.FIBER_IOR, K0)
     A, B = prob.assemble()
     sigma = (K0 * (max(mg.FIBER_IOR.values()) if target is None else target)) ** 2
-    sym = sv.Symbolic(prob.h_dofs, prob.centroids(), prob.N, 0, leaf)
+    sym = sv.Symbolic(prob.h_dofs, prob.h_xy, prob.N, 0, leaf)
     S = sv.Solver(prob.pattern, sym)
     st = S.factor(A, B, sigma)
     M = (_csr(prob, A) - sigma * _csr(prob, B)).tocsc()
@@ -86,7 +86,7 @@ def test_vector_quasidefinite_factor_solve(ws, gen, arg, target):
     assert np.allclose(prob.apply_T(vd).cpu().numpy(), T @ v, rtol=1e-13, atol=1e-13)
     assert np.allclose(prob.apply_T(vd, transpose=True).cpu().numpy(), T.T @ v, rtol=1e-13, atol=1e-13)
     # factor M' (nodes first inside every front), solve M x = b as x = T M'^-1 T^T b
-    sym = sv.Symbolic(prob.h_dofs, prob.centroids(), N, Ntt, 32)
+    sym = sv.Symbolic(prob.h_dofs, prob.h_xy, N, Ntt, 32)
     S = sv.Solver(prob.pattern, sym)
     st = S.factor(Mq)
     b = np.random.default_rng(2).standard_normal(N)
@@ -103,7 +103,7 @@ def test_solver_rejects_use_before_factor(ws):
     from wavesolve_b200 import fe_solver as fs, solver as sv, _lib
     mg = ws.meshgen
     prob = fs.ScalarProblem(mg.structured_square(6), mg.FIBER_IOR, K0)
-    sym = sv.Symbolic(prob.h_dofs, prob.centroids(), prob.N, 0, 8)
+    sym = sv.Symbolic(prob.h_dofs, prob.h_xy, prob.N, 0, 8)
     S = sv.Solver(prob.pattern, sym)
     with pytest.raises(_lib.WavesolveB200Error):
         S.solve(torch.zeros(prob.N, dtype=torch.float64, device="cuda"))

@@ -18,7 +18,7 @@ K0 = 2 * np.pi / 1.55
 def scalar_setup(ne, seed=7):
     mesh = mg.fiber_disc(ne, order=2, seed=seed)
     conn, _, _ = R.material_major(mesh)
-    cxy = mesh.points[conn[:, :3].astype(np.int64), :2].mean(axis=1)
+    cxy = np.ascontiguousarray(mesh.points[:, :2])
     return mesh, conn.astype(np.int32), cxy, int(conn.max()) + 1
 
 
@@ -29,7 +29,7 @@ def vector_setup(ne, seed=7, gen="disc"):
     e, _, _ = R.material_major(mesh, np.asarray(mesh.edge_indices))
     Ntt = len(mesh.cells[0].data)
     dofs = np.hstack([e.astype(np.int64), conn.astype(np.int64) + Ntt]).astype(np.int32)
-    cxy = mesh.points[conn.astype(np.int64), :2].mean(axis=1)
+    cxy = np.ascontiguousarray(mesh.points[:, :2])
     return mesh, dofs, cxy, Ntt, Ntt + len(mesh.points)
 
 

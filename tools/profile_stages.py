@@ -55,7 +55,7 @@ def main():
             Mq = prob.assemble_qd(sigma)
             T["assemble_qd"] = sync() - t0
         t0 = sync()
-        sym = sv.Symbolic(prob.h_dofs, prob.centroids(), prob.N, prob.first_class_start, leaf)
+        sym = sv.Symbolic(prob.h_dofs, prob.h_xy, prob.N, prob.first_class_start, leaf)
         T["symbolic(host)"] = sync() - t0
         T["sym.kd(1)"], T["sym.order(1)"], T["sym.bnd(1)"] = sym.t_kd, sym.t_order, sym.t_bnd
         t0 = sync()

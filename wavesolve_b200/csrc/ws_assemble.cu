@@ -103,6 +103,10 @@ struct VectorP1 {
     int qd;          // 1: write the quasi-definite shift-invert matrix M' = T^T (A - sigma B) T into Bv
     double sigma;
 
+    // Branch-free in the local index: the (cheap) numerators of all rows are formed and the ones
+    // of row `a` are picked with selects, so a warp whose lanes hold different local rows does not
+    // serialise three copies of the expensive part (3 sqrt + 7-8 IEEE divisions per incidence).
+    // Every expression keeps the reference's association (shape_funcs.py line cited per entry).
     __device__ __forceinline__ void row(uint32_t e, int a, double (&Av)[6], double (&Bv)[6], int (&cb)[6]) const {
         const int32_t* t = tris + (int64_t)e * 3;
         const int32_t t0 = t[0], t1 = t[1], t2 = t[2];
@@ -114,107 +118,85 @@ struct VectorP1 {
         const double s2 = t1 < t2 ? 1.0 : -1.0;
         const double s3 = t2 < t0 ? 1.0 : -1.0;
         const double J = x21 * y31 - x31 * y21;                      // shape_funcs.py:323
-#pragma unroll
-        for (int j = 0; j < 6; ++j) { cb[j] = j; Av[j] = 0.0; Bv[j] = 0.0; }
         const double c = k2n2[e];
         const double xx = x21 * x31, yy = y21 * y31;
+        const double l12 = sqrt(x21 * x21 + y21 * y21) * s1;         // shape_funcs.py:320-322
+        const double l23 = sqrt(x32 * x32 + y32 * y32) * s2;
+        const double l31 = sqrt(x31 * x31 + y31 * y31) * s3;
+        const double sq12 = l12 * l12, sq23 = l23 * l23, sq31 = l31 * l31;
+        const double x3 = (3 * x21) * x31, y3 = (3 * y21) * y31;
+        const double J6 = 6 * J;
+#pragma unroll
+        for (int j = 0; j < 6; ++j) { cb[j] = j; Av[j] = 0.0; }
+        // numerators of NedN (D_ij, i = edge, j = node), shape_funcs.py:393-401
+        const double nD00 = l12 * (-sq12 + x3 - 2 * sq31 + y3);       // :393
+        const double nD01 = l12 * (-xx + 2 * sq31 - yy);              // :396
+        const double nD02 = l12 * (sq12 - 2 * xx - 2 * yy);           // :401
+        const double nD10 = l23 * (-sq12 + sq31);                     // :397
+        const double nD11 = l23 * (-xx - sq31 - yy);                  // :394
+        const double nD12 = l23 * (sq12 + xx + yy);                   // :398
+        const double nD20 = l31 * (2 * sq12 - x3 + sq31 - y3);        // :400
+        const double nD21 = l31 * (2 * xx + 2 * yy - sq31);           // :399
+        const double nD22 = l31 * (-2 * sq12 + xx + yy);              // :395
         if (a < 3) {
-            const double l12 = sqrt(x21 * x21 + y21 * y21) * s1;     // shape_funcs.py:320-322
-            const double l23 = sqrt(x32 * x32 + y32 * y32) * s2;
-            const double l31 = sqrt(x31 * x31 + y31 * y31) * s3;
-            const double sq12 = l12 * l12, sq23 = l23 * l23, sq31 = l31 * l31;
-            const double x3 = (3 * x21) * x31, y3 = (3 * y21) * y31;
-            const double J12 = 12 * J, J6 = 6 * J, tJ = 2 / J;
-            double E[3], C[3], D[3];
-            if (a == 0) {
-                E[0] = sq12 * (sq12 - x3 + 3 * sq31 - y3) / J12;                  // :369
-                E[1] = l12 * l23 * (sq12 - xx - sq31 - yy) / J12;                 // :372
-                E[2] = l31 * l12 * (-sq12 + x3 - sq31 + y3) / J12;                // :374
-                D[0] = l12 * (-sq12 + x3 - 2 * sq31 + y3) / J6;                   // :393
-                D[1] = l12 * (-xx + 2 * sq31 - yy) / J6;                          // :396
-                D[2] = l12 * (sq12 - 2 * xx - 2 * yy) / J6;                       // :401
-            } else if (a == 1) {
-                E[0] = l12 * l23 * (sq12 - xx - sq31 - yy) / J12;                 // :372
-                E[1] = sq23 * (sq12 + xx + sq31 + yy) / J12;                      // :370
-                E[2] = l23 * l31 * (-sq12 - xx + sq31 - yy) / J12;                // :373
-                D[0] = l23 * (-sq12 + sq31) / J6;                                 // :397
-                D[1] = l23 * (-xx - sq31 - yy) / J6;                              // :394
-                D[2] = l23 * (sq12 + xx + yy) / J6;                               // :398
-            } else {
-                E[0] = l31 * l12 * (-sq12 + x3 - sq31 + y3) / J12;                // :374
-                E[1] = l23 * l31 * (-sq12 - xx + sq31 - yy) / J12;                // :373
-                E[2] = sq31 * (3 * sq12 - x3 + sq31 - y3) / J12;                  // :371
-                D[0] = l31 * (2 * sq12 - x3 + sq31 - y3) / J6;                    // :400
-                D[1] = l31 * (2 * xx + 2 * yy - sq31) / J6;                       // :399
-                D[2] = l31 * (-2 * sq12 + xx + yy) / J6;                          // :395
-            }
-            const double la = a == 0 ? l12 : (a == 1 ? l23 : l31);
-            const double lj[3] = {l12, l23, l31};
-#pragma unroll
-            for (int j = 0; j < 3; ++j)                                           // :382-383
-                C[j] = transpose ? (tJ * lj[j]) * la : (tJ * la) * lj[j];
+            const double J12 = 12 * J, tJ = 2 / J;
+            // numerators of NeNe (symmetric), shape_funcs.py:369-374
+            const double nE00 = sq12 * (sq12 - x3 + 3 * sq31 - y3);          // :369
+            const double nE11 = sq23 * (sq12 + xx + sq31 + yy);              // :370
+            const double nE22 = sq31 * (3 * sq12 - x3 + sq31 - y3);          // :371
+            const double nE01 = l12 * l23 * (sq12 - xx - sq31 - yy);         // :372
+            const double nE12 = l23 * l31 * (-sq12 - xx + sq31 - yy);        // :373
+            const double nE02 = l31 * l12 * (-sq12 + x3 - sq31 + y3);        // :374
+            const bool a0 = a == 0, a1 = a == 1;
+            const double E0 = (a0 ? nE00 : (a1 ? nE01 : nE02)) / J12;
+            const double E1 = (a0 ? nE01 : (a1 ? nE11 : nE12)) / J12;
+            const double E2 = (a0 ? nE02 : (a1 ? nE12 : nE22)) / J12;
+            const double D0 = (a0 ? nD00 : (a1 ? nD10 : nD20)) / J6;
+            const double D1 = (a0 ? nD01 : (a1 ? nD11 : nD21)) / J6;
+            const double D2 = (a0 ? nD02 : (a1 ? nD12 : nD22)) / J6;
+            const double la = a0 ? l12 : (a1 ? l23 : l31);
+            // curl-curl ((2/J) l_i) l_j, shape_funcs.py:382-383 (row i = a; transposed: column i = a)
+            const double C0 = transpose ? (tJ * l12) * la : (tJ * la) * l12;
+            const double C1 = transpose ? (tJ * l23) * la : (tJ * la) * l23;
+            const double C2 = transpose ? (tJ * l31) * la : (tJ * la) * l31;
             if (qd) {
-#pragma unroll
-                for (int j = 0; j < 3; ++j) {
-                    Bv[j] = (c - sigma) * E[j] - C[j];
-                    Bv[3 + j] = -c * D[j];
-                }
+                Bv[0] = (c - sigma) * E0 - C0; Bv[1] = (c - sigma) * E1 - C1; Bv[2] = (c - sigma) * E2 - C2;
+                Bv[3] = -c * D0; Bv[4] = -c * D1; Bv[5] = -c * D2;
                 return;
             }
-#pragma unroll
-            for (int j = 0; j < 3; ++j) {
-                Av[j] = __dsub_rn(__dmul_rn(c, E[j]), C[j]);                      // fe_solver.py:196
-                Bv[j] = E[j];                                                     // fe_solver.py:197
-                Bv[3 + j] = D[j];                                                 // fe_solver.py:198
-            }
+            Av[0] = __dsub_rn(__dmul_rn(c, E0), C0);                              // fe_solver.py:196
+            Av[1] = __dsub_rn(__dmul_rn(c, E1), C1);
+            Av[2] = __dsub_rn(__dmul_rn(c, E2), C2);
+            Bv[0] = E0; Bv[1] = E1; Bv[2] = E2;                                    // fe_solver.py:197
+            Bv[3] = D0; Bv[4] = D1; Bv[5] = D2;                                    // fe_solver.py:198
         } else {
             const int i = a - 3;
-            // squared lengths as the reference forms them: (sqrt(.) * s)**2
-            const double l12 = sqrt(x21 * x21 + y21 * y21) * s1;
-            const double l31 = sqrt(x31 * x31 + y31 * y31) * s3;
-            const double sq12 = l12 * l12, sq31 = l31 * l31;
-            const double J6 = 6 * J, J2 = 2 * J;
-            double Dt[3], G[3];
-            const double Nd = J / 12, No = J / 24;                                // :410-411
-            if (i == 0) {
-                const double l23 = sqrt(x32 * x32 + y32 * y32) * s2;
-                const double x3 = (3 * x21) * x31, y3 = (3 * y21) * y31;
-                Dt[0] = l12 * (-sq12 + x3 - 2 * sq31 + y3) / J6;                  // D00 :393
-                Dt[1] = l23 * (-sq12 + sq31) / J6;                                // D10 :397
-                Dt[2] = l31 * (2 * sq12 - x3 + sq31 - y3) / J6;                   // D20 :400
-                G[0] = (sq12 + sq31 - 2 * xx - 2 * yy) / J2;                      // :421
-                G[1] = (-sq31 + xx + yy) / J2;                                    // :424
-                G[2] = (-sq12 + xx + yy) / J2;                                    // :426
-            } else if (i == 1) {
-                const double l23 = sqrt(x32 * x32 + y32 * y32) * s2;
-                Dt[0] = l12 * (-xx + 2 * sq31 - yy) / J6;                         // D01 :396
-                Dt[1] = l23 * (-xx - sq31 - yy) / J6;                             // D11 :394
-                Dt[2] = l31 * (2 * xx + 2 * yy - sq31) / J6;                      // D21 :399
-                G[0] = (-sq31 + xx + yy) / J2;                                    // :424
-                G[1] = sq31 / J2;                                                 // :422
-                G[2] = (-xx - yy) / J2;                                           // :425
-            } else {
-                const double l23 = sqrt(x32 * x32 + y32 * y32) * s2;
-                Dt[0] = l12 * (sq12 - 2 * xx - 2 * yy) / J6;                      // D02 :401
-                Dt[1] = l23 * (sq12 + xx + yy) / J6;                              // D12 :398
-                Dt[2] = l31 * (-2 * sq12 + xx + yy) / J6;                         // D22 :395
-                G[0] = (-sq12 + xx + yy) / J2;                                    // :426
-                G[1] = (-xx - yy) / J2;                                           // :425
-                G[2] = sq12 / J2;                                                 // :423
-            }
+            const bool i0 = i == 0, i1 = i == 1;
+            const double J2 = 2 * J;
+            const double Nd = J / 12, No = J / 24;                                // shape_funcs.py:410-411
+            // numerators of dNdN (symmetric), shape_funcs.py:421-426
+            const double nG00 = sq12 + sq31 - 2 * xx - 2 * yy;                    // :421
+            const double nG11 = sq31;                                             // :422
+            const double nG22 = sq12;                                             // :423
+            const double nG01 = -sq31 + xx + yy;                                  // :424
+            const double nG12 = -xx - yy;                                         // :425
+            const double nG02 = -sq12 + xx + yy;                                  // :426
+            const double Dt0 = (i0 ? nD00 : (i1 ? nD01 : nD02)) / J6;             // column i of NedN
+            const double Dt1 = (i0 ? nD10 : (i1 ? nD11 : nD12)) / J6;
+            const double Dt2 = (i0 ? nD20 : (i1 ? nD21 : nD22)) / J6;
+            const double G0 = (i0 ? nG00 : (i1 ? nG01 : nG02)) / J2;
+            const double G1 = (i0 ? nG01 : (i1 ? nG11 : nG12)) / J2;
+            const double G2 = (i0 ? nG02 : (i1 ? nG12 : nG22)) / J2;
+            const double N0 = i0 ? Nd : No, N1 = i1 ? Nd : No, N2 = (i == 2) ? Nd : No;
             if (qd) {
-#pragma unroll
-                for (int j = 0; j < 3; ++j) {
-                    Bv[j] = -c * Dt[j];
-                    Bv[3 + j] = c * (G[j] + sigma * (j == i ? Nd : No));
-                }
+                Bv[0] = -c * Dt0; Bv[1] = -c * Dt1; Bv[2] = -c * Dt2;
+                Bv[3] = c * (G0 + sigma * N0); Bv[4] = c * (G1 + sigma * N1); Bv[5] = c * (G2 + sigma * N2);
                 return;
             }
-#pragma unroll
-            for (int j = 0; j < 3; ++j) {
-                Bv[j] = Dt[j];                                                    // fe_solver.py:209
-                Bv[3 + j] = __dsub_rn(G[j], __dmul_rn(c, j == i ? Nd : No));      // fe_solver.py:199
-            }
+            Bv[0] = Dt0; Bv[1] = Dt1; Bv[2] = Dt2;                                // fe_solver.py:209
+            Bv[3] = __dsub_rn(G0, __dmul_rn(c, N0));                              // fe_solver.py:199
+            Bv[4] = __dsub_rn(G1, __dmul_rn(c, N1));
+            Bv[5] = __dsub_rn(G2, __dmul_rn(c, N2));
         }
     }
 };

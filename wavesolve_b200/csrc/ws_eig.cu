@@ -445,15 +445,19 @@ __global__ void __launch_bounds__(256) k_dots_partial(const double* __restrict__
     }
 }
 
-// h[i] = sum_c partial[c][i] (fixed order); hacc[i] += h[i] when hacc != nullptr
-__global__ void k_dots_reduce(const double* __restrict__ partial, int nchunks, int nvec, double* __restrict__ h,
-                              double* __restrict__ hacc) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nvec) return;
+// h[i] = sum_c partial[c][i]; one warp per vector, fixed lane/shuffle order (deterministic);
+// hacc[i] += h[i] when hacc != nullptr
+__global__ void __launch_bounds__(32) k_dots_reduce(const double* __restrict__ partial, int nchunks, int nvec,
+                                                    double* __restrict__ h, double* __restrict__ hacc) {
+    const int i = blockIdx.x, lane = threadIdx.x;
     double s = 0.0;
-    for (int c = 0; c < nchunks; ++c) s += partial[(size_t)c * nvec + i];
-    h[i] = s;
-    if (hacc) hacc[i] += s;
+    for (int c = lane; c < nchunks; c += 32) s += partial[(size_t)c * nvec + i];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) {
+        h[i] = s;
+        if (hacc) hacc[i] += s;
+    }
 }
 
 // w -= sum_i h[i] V_i
@@ -535,7 +539,7 @@ struct EigWork {
 
 static void dots(EigWork& W, const double* Zb, int nvec, const double* u, double* h, double* hacc) {
     k_dots_partial<<<W.nchunks, 256, 0, W.st>>>(Zb, W.N, nvec, u, W.N, W.partial.get());
-    k_dots_reduce<<<1, 64, 0, W.st>>>(W.partial.get(), W.nchunks, nvec, h, hacc);
+    k_dots_reduce<<<nvec, 32, 0, W.st>>>(W.partial.get(), W.nchunks, nvec, h, hacc);
     count_launch(2);
 }
 

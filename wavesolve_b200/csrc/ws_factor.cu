@@ -38,9 +38,11 @@ struct InvTask {
 };
 
 struct LevelPlan {
-    std::vector<Range> upd, pan;   // per block column
+    std::vector<Range> upd, pan, trail;   // per block column (upd: left-looking, trail: right-looking)
     Range syrk, ext_left, ext_right, fwd, bwd;
     int64_t first_front = 0, nfronts = 0;
+    bool small = false;                   // every front fits the single-CTA solve kernels
+    bool right_looking = false;
 };
 
 }  // namespace ws
@@ -85,12 +87,32 @@ __device__ __forceinline__ void dmma8x8x4(double& c0, double& c1, double a, doub
 }
 
 constexpr int KC = 16;
+constexpr int GSTAGES = 3;
 
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc, bool valid) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    const int sz = valid ? 8 : 0;                       // src-size 0 -> the 8 bytes are zero-filled
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(gsrc), "r"(sz));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
+
+template <int BN>
+constexpr size_t gemm_smem_bytes() {
+    return (size_t)GSTAGES * (KC * (GT + 4) + KC * (BN + 4) + KC) * sizeof(double);
+}
+
+// One CTA = one GemmTask = one (<=64) x (<=BN) output tile.  3-stage cp.async pipeline over
+// k-chunks of 16, fp64 tensor-core MMA (mma.sync m8n8k4) from shared memory, 2x2 warps.
 template <int BN>
 __global__ void __launch_bounds__(128) k_gemm_tiles(const GemmTask* __restrict__ tasks) {
     const GemmTask t = tasks[blockIdx.x];
-    __shared__ double As[KC][GT + 4];
-    __shared__ double Bs[KC][BN + 4];
+    extern __shared__ double gsm[];
+    constexpr int AS = KC * (GT + 4), BS = KC * (BN + 4);
+    double* As = gsm;
+    double* Bs = gsm + GSTAGES * AS;
+    double* Ds = Bs + GSTAGES * BS;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, tq = lane & 3;
     const int wm = warp & 1, wn = warp >> 1;
     constexpr int NBLK = BN / 16;
@@ -101,49 +123,75 @@ __global__ void __launch_bounds__(128) k_gemm_tiles(const GemmTask* __restrict__
 #pragma unroll
         for (int b = 0; b < NBLK; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
     const bool bn = (t.flags & GF_BN) != 0;
-    for (int kc = 0; kc < t.k; kc += KC) {
+    const int nk = (t.k + KC - 1) / KC;
+
+    auto load_stage = [&](int stage, int kc) {
+        double* as = As + stage * AS;
+        double* bs = Bs + stage * BS;
         {
             const int i = tid & 63;
 #pragma unroll
             for (int r = 0; r < 8; ++r) {
                 const int kk = (tid >> 6) + 2 * r;
-                double v = 0.0;
-                if (i < t.m && kc + kk < t.k) v = t.A[i + (size_t)(kc + kk) * t.lda];
-                As[kk][i] = v;
+                const bool ok = i < t.m && kc + kk < t.k;
+                cp_async8(as + kk * (GT + 4) + i, ok ? t.A + i + (size_t)(kc + kk) * t.lda : t.A, ok);
             }
         }
         if (!bn) {
-            for (int idx = tid; idx < KC * BN; idx += 128) {
-                const int kk = idx / BN, j = idx % BN;
-                double v = 0.0;
-                if (j < t.n && kc + kk < t.k) {
-                    v = t.B[j + (size_t)(kc + kk) * t.ldb];
-                    if (t.dscale) v *= t.dscale[kc + kk];
-                }
-                Bs[kk][j] = v;
+#pragma unroll
+            for (int r = 0; r < KC * BN / 128; ++r) {
+                const int idx = tid + 128 * r;
+                const int kk = idx / BN, jj = idx % BN;
+                const bool ok = jj < t.n && kc + kk < t.k;
+                cp_async8(bs + kk * (BN + 4) + jj, ok ? t.B + jj + (size_t)(kc + kk) * t.ldb : t.B, ok);
             }
         } else {
-            for (int idx = tid; idx < KC * BN; idx += 128) {
-                const int kk = idx % KC, j = idx / KC;
-                double v = 0.0;
-                if (j < t.n && kc + kk < t.k) v = t.B[(kc + kk) + (size_t)j * t.ldb];
-                Bs[kk][j] = v;
+#pragma unroll
+            for (int r = 0; r < KC * BN / 128; ++r) {
+                const int idx = tid + 128 * r;
+                const int kk = idx % KC, jj = idx / KC;
+                const bool ok = jj < t.n && kc + kk < t.k;
+                cp_async8(bs + kk * (BN + 4) + jj, ok ? t.B + (kc + kk) + (size_t)jj * t.ldb : t.B, ok);
             }
         }
+        if (tid < KC) {
+            if (t.dscale) {
+                const bool ok = kc + tid < t.k;
+                cp_async8(Ds + stage * KC + tid, ok ? t.dscale + kc + tid : t.dscale, ok);
+            } else {
+                Ds[stage * KC + tid] = 1.0;
+            }
+        }
+    };
+
+#pragma unroll
+    for (int s = 0; s < GSTAGES; ++s) {
+        if (s < nk) load_stage(s, s * KC);
+        cp_async_commit();
+    }
+    for (int it = 0; it < nk; ++it) {
+        cp_async_wait<GSTAGES - 1>();
         __syncthreads();
+        const int stage = it % GSTAGES;
+        const double* as = As + stage * AS;
+        const double* bs = Bs + stage * BS;
+        const double* ds = Ds + stage * KC;
 #pragma unroll
         for (int ks = 0; ks < KC / 4; ++ks) {
             double a[4], b[NBLK];
+            const double dk = ds[ks * 4 + tq];
 #pragma unroll
-            for (int mb = 0; mb < 4; ++mb) a[mb] = As[ks * 4 + tq][wm * 32 + mb * 8 + g];
+            for (int mb = 0; mb < 4; ++mb) a[mb] = as[(ks * 4 + tq) * (GT + 4) + wm * 32 + mb * 8 + g];
 #pragma unroll
-            for (int nb = 0; nb < NBLK; ++nb) b[nb] = Bs[ks * 4 + tq][wn * WN + nb * 8 + g];
+            for (int nb = 0; nb < NBLK; ++nb) b[nb] = bs[(ks * 4 + tq) * (BN + 4) + wn * WN + nb * 8 + g] * dk;
 #pragma unroll
             for (int mb = 0; mb < 4; ++mb)
 #pragma unroll
                 for (int nb = 0; nb < NBLK; ++nb) dmma8x8x4(acc[mb][nb][0], acc[mb][nb][1], a[mb], b[nb]);
         }
         __syncthreads();
+        if (it + GSTAGES < nk) load_stage(stage, (it + GSTAGES) * KC);
+        cp_async_commit();
     }
     const bool neg = (t.flags & GF_NEG) != 0, accum = (t.flags & GF_ACCUM) != 0;
 #pragma unroll
@@ -182,21 +230,25 @@ __global__ void __launch_bounds__(PANEL_ROWS) k_panel(const PanelTask* __restric
     }
     __syncthreads();
     if (tid < 32) {
+        // warp 0: lane r holds row r of the (symmetric) block in registers; column c is eliminated
+        // with shuffles: A[r][c2] -= (A[r][c] / A[c][c]) * A[c][c2]  for r, c2 > c.
         const int lane = tid;
-        for (int c = 0; c < t.nb; ++c) {
-            const double dc = Dg[c][c];
-            const bool act = lane > c && lane < t.nb;
-            double lr = 0.0;
-            if (act) lr = Dg[lane][c] / dc;
-            __syncwarp();
-            if (act)
-                for (int c2 = c + 1; c2 <= lane; ++c2) Dg[lane][c2] -= lr * Dg[c2][c];
-            __syncwarp();
+        double row[NB];
+#pragma unroll
+        for (int c = 0; c < NB; ++c) row[c] = (lane >= c) ? Dg[lane][c] : Dg[c][lane];
+#pragma unroll
+        for (int c = 0; c < NB; ++c) {
+            const double dc = __shfl_sync(0xffffffffu, row[c], c);
+            const bool act = lane > c;
+            const double lr = act ? row[c] / dc : 0.0;
+#pragma unroll
+            for (int c2 = c + 1; c2 < NB; ++c2) {
+                const double pc = __shfl_sync(0xffffffffu, row[c2], c);
+                row[c2] -= lr * pc;
+            }
             if (act) Dg[lane][c] = lr;
             if (lane == c) dd[c] = dc;
-            __syncwarp();
         }
-        if (lane >= t.nb) dd[lane] = 1.0;
     }
     __syncthreads();
     if (tid < t.nr) {
@@ -366,10 +418,14 @@ __global__ void __launch_bounds__(256) k_fwd_gather(int64_t first, int has_child
     }
 }
 
-// rows [r0, r0+nr) of  out = S * w_own ;  own rows -> y, boundary rows: w_bnd -= out
-__global__ void __launch_bounds__(256) k_fwd_gemv(const GemvTask* __restrict__ tasks) {
+// rows [r0, r0+nr) of  out = S * w_own ;  own rows -> y, boundary rows: w_bnd -= out.
+// 32 rows x 32 k-lanes per CTA: every thread keeps 4 independent loads in flight.
+// FWD_KL = 8 (256 threads) when a level has thousands of tiles, 32 (1024 threads) for the few
+// large fronts near the root, where a tile's k loop would otherwise be long and serial.
+template <int FWD_KL>
+__global__ void __launch_bounds__(GEMV_ROWS * FWD_KL) k_fwd_gemv(const GemvTask* __restrict__ tasks) {
     const GemvTask t = tasks[blockIdx.x];
-    __shared__ double red[8][GEMV_ROWS + 1];
+    __shared__ double red[FWD_KL][GEMV_ROWS + 1];
     const int lr = threadIdx.x & 31, kl = threadIdx.x >> 5;
     const int r = t.r0 + lr;
     const bool valid = lr < t.nr;
@@ -380,19 +436,19 @@ __global__ void __launch_bounds__(256) k_fwd_gemv(const GemvTask* __restrict__ t
         const double* Sr = t.S + r;
         const size_t ld = (size_t)t.ld;
         int k = kl;
-        for (; k + 24 < kend; k += 32) {
-            const double s0 = Sr[(size_t)k * ld], s1 = Sr[(size_t)(k + 8) * ld];
-            const double s2 = Sr[(size_t)(k + 16) * ld], s3 = Sr[(size_t)(k + 24) * ld];
-            acc += s0 * t.w[k] + s1 * t.w[k + 8] + s2 * t.w[k + 16] + s3 * t.w[k + 24];
+        for (; k + 3 * FWD_KL < kend; k += 4 * FWD_KL) {
+            const double s0 = Sr[(size_t)k * ld], s1 = Sr[(size_t)(k + FWD_KL) * ld];
+            const double s2 = Sr[(size_t)(k + 2 * FWD_KL) * ld], s3 = Sr[(size_t)(k + 3 * FWD_KL) * ld];
+            acc += s0 * t.w[k] + s1 * t.w[k + FWD_KL] + s2 * t.w[k + 2 * FWD_KL] + s3 * t.w[k + 3 * FWD_KL];
         }
-        for (; k < kend; k += 8) acc += Sr[(size_t)k * ld] * t.w[k];
+        for (; k < kend; k += FWD_KL) acc += Sr[(size_t)k * ld] * t.w[k];
     }
     red[kl][lr] = acc;
     __syncthreads();
     if (kl == 0 && valid) {
         double s = 0.0;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) s += red[j][lr];
+        for (int j = 0; j < FWD_KL; ++j) s += red[j][lr];
         if (r < t.p) t.y[r] = s;
         else t.w[r] -= s;
     }
@@ -409,26 +465,109 @@ __global__ void __launch_bounds__(256) k_bwd_gather(int64_t first, FrontView fv,
     for (int i = threadIdx.x; i < m; i += blockDim.x) g[i] = (i < p) ? y[st + i] * dinv[st + i] : -x[b[i - p]];
 }
 
-// columns [c0, c0+nc): x_own[c] = sum_{r>=c} S[r,c] * g[r]   (one warp per column)
-__global__ void __launch_bounds__(32 * GEMVT_COLS) k_bwd_gemvT(const GemvTTask* __restrict__ tasks) {
+// columns [c0, c0+nc): x_own[c] = sum_{r>=c} S[r,c] * g[r].  4 warps share one column (each a
+// quarter of the rows, 4 independent accumulators per lane), 8 columns per CTA.
+template <int BWD_WPC>
+__global__ void __launch_bounds__(32 * GEMVT_COLS * BWD_WPC) k_bwd_gemvT(const GemvTTask* __restrict__ tasks) {
     const GemvTTask t = tasks[blockIdx.x];
-    const int lane = threadIdx.x & 31, wc = threadIdx.x >> 5;
-    if (wc >= t.nc) return;
-    const int c = t.c0 + wc;
-    const double* Sc = t.S + (size_t)c * t.ld;
-    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-    int r = c + lane;
-    for (; r + 96 < t.m; r += 128) {
-        a0 += Sc[r] * t.g[r];
-        a1 += Sc[r + 32] * t.g[r + 32];
-        a2 += Sc[r + 64] * t.g[r + 64];
-        a3 += Sc[r + 96] * t.g[r + 96];
-    }
-    for (; r < t.m; r += 32) a0 += Sc[r] * t.g[r];
-    double acc = (a0 + a1) + (a2 + a3);
+    __shared__ double red[GEMVT_COLS][BWD_WPC];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int wc = warp / BWD_WPC, part = warp % BWD_WPC;
+    double acc = 0.0;
+    if (wc < t.nc) {
+        const int c = t.c0 + wc;
+        const double* Sc = t.S + (size_t)c * t.ld;
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        const int step = 32 * BWD_WPC;
+        int r = c + part * 32 + lane;
+        for (; r + 3 * step < t.m; r += 4 * step) {
+            a0 += Sc[r] * t.g[r];
+            a1 += Sc[r + step] * t.g[r + step];
+            a2 += Sc[r + 2 * step] * t.g[r + 2 * step];
+            a3 += Sc[r + 3 * step] * t.g[r + 3 * step];
+        }
+        for (; r < t.m; r += step) a0 += Sc[r] * t.g[r];
+        acc = (a0 + a1) + (a2 + a3);
 #pragma unroll
-    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (lane == 0) t.x[c] = acc;
+        for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    }
+    if (lane == 0 && wc < GEMVT_COLS) red[wc][part] = acc;
+    __syncthreads();
+    if (threadIdx.x < t.nc) {
+        double sacc = 0.0;
+#pragma unroll
+        for (int j = 0; j < BWD_WPC; ++j) sacc += red[threadIdx.x][j];
+        t.x[t.c0 + threadIdx.x] = sacc;
+    }
+}
+
+// ---- small fronts (m <= SMALL_M): one CTA does a whole front, work vector in shared memory ----
+constexpr int SMALL_M = 256;
+__global__ void __launch_bounds__(128) k_fwd_small(int64_t first, int has_children, FrontView fv,
+                                                   const double* __restrict__ bperm, double* __restrict__ Wb,
+                                                   const double* __restrict__ Sb, double* __restrict__ y) {
+    const int64_t t = first + blockIdx.x;
+    const int p = fv.p[t], q = fv.q[t], m = p + q;
+    __shared__ double sw[SMALL_M];
+    double* w = Wb + fv.woff[t];
+    const int64_t st = fv.start[t];
+    for (int i = threadIdx.x; i < m; i += 128) sw[i] = (i < p) ? bperm[st + i] : 0.0;
+    if (has_children) {
+        for (int cc = 0; cc < 2; ++cc) {
+            __syncthreads();
+            const int64_t c = 2 * t + cc;
+            const int pc = fv.p[c], qc = fv.q[c];
+            const double* wc = Wb + fv.woff[c] + pc;
+            const int32_t* rel = fv.rel + fv.bndoff[c];
+            for (int j = threadIdx.x; j < qc; j += 128) sw[rel[j]] += wc[j];
+        }
+    }
+    __syncthreads();
+    const double* S = Sb + fv.Loff[t];
+    for (int r = threadIdx.x; r < m; r += 128) {
+        const int kend = (r < p) ? r + 1 : p;
+        const double* Sr = S + r;
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        int k = 0;
+        for (; k + 3 < kend; k += 4) {
+            a0 += Sr[(size_t)k * m] * sw[k];
+            a1 += Sr[(size_t)(k + 1) * m] * sw[k + 1];
+            a2 += Sr[(size_t)(k + 2) * m] * sw[k + 2];
+            a3 += Sr[(size_t)(k + 3) * m] * sw[k + 3];
+        }
+        for (; k < kend; ++k) a0 += Sr[(size_t)k * m] * sw[k];
+        const double acc = (a0 + a1) + (a2 + a3);
+        if (r < p) y[st + r] = acc;
+        else w[r] = sw[r] - acc;
+    }
+}
+
+__global__ void __launch_bounds__(128) k_bwd_small(int64_t first, FrontView fv, const double* __restrict__ y,
+                                                   const double* __restrict__ dinv, double* __restrict__ x,
+                                                   const double* __restrict__ Sb) {
+    const int64_t t = first + blockIdx.x;
+    const int p = fv.p[t], q = fv.q[t], m = p + q;
+    __shared__ double sg[SMALL_M];
+    const int64_t st = fv.start[t];
+    const int32_t* b = fv.bnd + fv.bndoff[t];
+    for (int i = threadIdx.x; i < m; i += 128) sg[i] = (i < p) ? y[st + i] * dinv[st + i] : -x[b[i - p]];
+    __syncthreads();
+    const double* S = Sb + fv.Loff[t];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int c = warp; c < p; c += 4) {
+        const double* Sc = S + (size_t)c * m;
+        double a0 = 0.0, a1 = 0.0;
+        int r = c + lane;
+        for (; r + 32 < m; r += 64) {
+            a0 += Sc[r] * sg[r];
+            a1 += Sc[r + 32] * sg[r + 32];
+        }
+        if (r < m) a0 += Sc[r] * sg[r];
+        double acc = a0 + a1;
+#pragma unroll
+        for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) x[st + c] = acc;
+    }
 }
 
 __global__ void k_permute_in(int64_t N, const int32_t* __restrict__ perm, const double* __restrict__ b, double* __restrict__ bp) {
@@ -488,6 +627,13 @@ static void build_plan(ws_solver* s, cudaStream_t st) {
         const int nkb = (maxp + NB - 1) / NB;
         LP.upd.assign(nkb, Range());
         LP.pan.assign(nkb, Range());
+        LP.trail.assign(nkb, Range());
+        int maxm = 0;
+        for (int64_t t = f0; t < f1; ++t) maxm = std::max(maxm, (int)(Y.p[t] + Y.q[t]));
+        LP.small = maxm <= SMALL_M;
+        // few large fronts: a left-looking block-column update has too few tiles to fill the GPU
+        // (and a long serial k loop); update the whole trailing panel after every block column.
+        LP.right_looking = (f1 - f0) <= 64 && maxp > 4 * NB;
         // extend-add of the children of this level's fronts (left children first, then right)
         if (l < depth) {
             for (int side = 0; side < 2; ++side) {
@@ -505,7 +651,7 @@ static void build_plan(ws_solver* s, cudaStream_t st) {
         for (int kb = 0; kb < nkb; ++kb) {
             const int k0 = kb * NB;
             LP.upd[kb].off = (int64_t)G.size();
-            if (kb > 0)
+            if (kb > 0 && !LP.right_looking)
                 for (int64_t t = f0; t < f1; ++t) {
                     const int p = Y.p[t], m = p + Y.q[t];
                     if (p <= k0) continue;
@@ -550,6 +696,30 @@ static void build_plan(ws_solver* s, cudaStream_t st) {
                 } while (r0 < m);
             }
             LP.pan[kb].cnt = (int64_t)P.size() - LP.pan[kb].off;
+            LP.trail[kb].off = (int64_t)G.size();
+            if (LP.right_looking)
+                for (int64_t t = f0; t < f1; ++t) {
+                    const int p = Y.p[t], m = p + Y.q[t];
+                    if (p <= k0) continue;
+                    const int nbk = std::min(NB, p - k0);
+                    const int c0 = k0 + nbk;           // first trailing row / column
+                    double* Lt = Lb + Y.Loff[t];
+                    for (int i0 = c0; i0 < m; i0 += GT)
+                        for (int j0 = c0; j0 <= i0 && j0 < p; j0 += GT) {
+                            GemmTask g{};
+                            g.A = Lt + i0 + (size_t)k0 * m;
+                            g.B = Lt + j0 + (size_t)k0 * m;
+                            g.C = Lt + i0 + (size_t)j0 * m;
+                            g.dscale = db + Y.start[t] + k0;
+                            g.lda = g.ldb = g.ldc = m;
+                            g.m = std::min(GT, m - i0);
+                            g.n = std::min(GT, p - j0);
+                            g.k = nbk;
+                            g.flags = GF_ACCUM | GF_NEG;
+                            G.push_back(g);
+                        }
+                }
+            LP.trail[kb].cnt = (int64_t)G.size() - LP.trail[kb].off;
         }
         // Schur complement U -= L21 D L21^T (lower tiles)
         LP.syrk.off = (int64_t)G.size();
@@ -578,7 +748,7 @@ static void build_plan(ws_solver* s, cudaStream_t st) {
         // solve sweeps
         LP.fwd.off = (int64_t)F.size();
         LP.bwd.off = (int64_t)Bk.size();
-        for (int64_t t = f0; t < f1; ++t) {
+        for (int64_t t = f0; t < f1 && !LP.small; ++t) {
             const int p = Y.p[t], q = Y.q[t], m = p + q;
             if (!p) continue;
             for (int r0 = 0; r0 < m; r0 += GEMV_ROWS) {
@@ -707,8 +877,14 @@ static void build_plan(ws_solver* s, cudaStream_t st) {
 
 static void launch_gemm(const ws_solver* s, const Range& r, bool narrow, cudaStream_t st) {
     if (!r.cnt) return;
-    if (narrow) k_gemm_tiles<32><<<(unsigned)r.cnt, 128, 0, st>>>(s->gemm_tasks.get() + r.off);
-    else k_gemm_tiles<64><<<(unsigned)r.cnt, 128, 0, st>>>(s->gemm_tasks.get() + r.off);
+    static bool configured = false;
+    if (!configured) {
+        WS_CUDA(cudaFuncSetAttribute(k_gemm_tiles<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem_bytes<32>()));
+        WS_CUDA(cudaFuncSetAttribute(k_gemm_tiles<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem_bytes<64>()));
+        configured = true;
+    }
+    if (narrow) k_gemm_tiles<32><<<(unsigned)r.cnt, 128, gemm_smem_bytes<32>(), st>>>(s->gemm_tasks.get() + r.off);
+    else k_gemm_tiles<64><<<(unsigned)r.cnt, 128, gemm_smem_bytes<64>(), st>>>(s->gemm_tasks.get() + r.off);
     count_launch(1);
 }
 
@@ -827,6 +1003,7 @@ int ws_solver_factor(ws_solver* s, const double* A_vals, const double* B_vals, d
                                                                          s->S.get(), s->stats.get());
                 count_launch(1);
             }
+            launch_gemm(s, LP.trail[kb], false, st);
         }
         launch_gemm(s, LP.syrk, false, st);
     }
@@ -871,18 +1048,38 @@ int ws_solver_solve(ws_solver* s, const double* b, double* x, int nrhs, int devi
         const double* bi = b + (size_t)rhs * s->N;
         double* xi = x + (size_t)rhs * s->N;
         k_permute_in<<<ceil_div(s->N, T), T, 0, st>>>(s->N, s->perm.get(), bi, s->bperm.get());
+        int nl = 2;
         for (int l = Y.depth; l >= 0; --l) {
             const LevelPlan& LP = s->levels[l];
-            k_fwd_gather<<<(unsigned)LP.nfronts, 256, 0, st>>>(LP.first_front, l < Y.depth ? 1 : 0, fv, s->bperm.get(), s->W.get());
-            if (LP.fwd.cnt) k_fwd_gemv<<<(unsigned)LP.fwd.cnt, 256, 0, st>>>(s->gemv_tasks.get() + LP.fwd.off);
+            const int hc = l < Y.depth ? 1 : 0;
+            if (LP.small) {
+                k_fwd_small<<<(unsigned)LP.nfronts, 128, 0, st>>>(LP.first_front, hc, fv, s->bperm.get(), s->W.get(), s->S.get(), s->y.get());
+                ++nl;
+            } else {
+                k_fwd_gather<<<(unsigned)LP.nfronts, 256, 0, st>>>(LP.first_front, hc, fv, s->bperm.get(), s->W.get());
+                if (LP.fwd.cnt) {
+                    if (LP.fwd.cnt >= 500) k_fwd_gemv<8><<<(unsigned)LP.fwd.cnt, GEMV_ROWS * 8, 0, st>>>(s->gemv_tasks.get() + LP.fwd.off);
+                    else k_fwd_gemv<32><<<(unsigned)LP.fwd.cnt, GEMV_ROWS * 32, 0, st>>>(s->gemv_tasks.get() + LP.fwd.off);
+                }
+                nl += 2;
+            }
         }
         for (int l = 0; l <= Y.depth; ++l) {
             const LevelPlan& LP = s->levels[l];
-            k_bwd_gather<<<(unsigned)LP.nfronts, 256, 0, st>>>(LP.first_front, fv, s->y.get(), s->dinv.get(), s->x.get(), s->W.get());
-            if (LP.bwd.cnt) k_bwd_gemvT<<<(unsigned)LP.bwd.cnt, 32 * GEMVT_COLS, 0, st>>>(s->gemvt_tasks.get() + LP.bwd.off);
+            if (LP.small) {
+                k_bwd_small<<<(unsigned)LP.nfronts, 128, 0, st>>>(LP.first_front, fv, s->y.get(), s->dinv.get(), s->x.get(), s->S.get());
+                ++nl;
+            } else {
+                k_bwd_gather<<<(unsigned)LP.nfronts, 256, 0, st>>>(LP.first_front, fv, s->y.get(), s->dinv.get(), s->x.get(), s->W.get());
+                if (LP.bwd.cnt) {
+                    if (LP.bwd.cnt >= 430) k_bwd_gemvT<1><<<(unsigned)LP.bwd.cnt, 32 * GEMVT_COLS, 0, st>>>(s->gemvt_tasks.get() + LP.bwd.off);
+                    else k_bwd_gemvT<4><<<(unsigned)LP.bwd.cnt, 32 * GEMVT_COLS * 4, 0, st>>>(s->gemvt_tasks.get() + LP.bwd.off);
+                }
+                nl += 2;
+            }
         }
         k_permute_out<<<ceil_div(s->N, T), T, 0, st>>>(s->N, s->perm.get(), s->x.get(), xi);
-        count_launch(2 + 4 * (Y.depth + 1));
+        count_launch(nl);
     }
     WS_CUDA(cudaGetLastError());
     WS_API_END

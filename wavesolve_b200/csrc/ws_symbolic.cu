@@ -80,8 +80,8 @@ void parallel_for(int64_t n, int nthreads, F f) {
 
 }  // namespace
 
-void analyse_host(Symbolic& S, const int32_t* dofs, int64_t Ne, int64_t N, const double* exy,
-                  int64_t cls_start, int leaf_elems) {
+void analyse_host(Symbolic& S, const int32_t* dofs, int64_t Ne, int64_t N, const double* xy, int64_t Np,
+                  int vert_col, int64_t vert_offset, int64_t cls_start, int leaf_elems) {
     WS_REQUIRE(Ne > 0 && N > 0, "analyse: empty problem");
     WS_REQUIRE(leaf_elems >= 1, "leaf_elems >= 1");
     int depth = 0;
@@ -100,7 +100,27 @@ void analyse_host(Symbolic& S, const int32_t* dofs, int64_t Ne, int64_t N, const
     // ---- 1. k-d bisection
     double t0 = now();
     std::vector<Pt> pts(Ne);
-    for (int64_t e = 0; e < Ne; ++e) pts[e] = Pt{exy[2 * e], exy[2 * e + 1], (int32_t)e};
+    {
+        // element centroids from the three vertex ids stored at dofs[e*6 + vert_col ..] - vert_offset
+        std::vector<int> bad(nthreads, 0);
+        std::vector<std::thread> th;
+        for (int t = 0; t < nthreads; ++t)
+            th.emplace_back([&, t]() {
+                const int64_t e0 = Ne * t / nthreads, e1 = Ne * (t + 1) / nthreads;
+                for (int64_t e = e0; e < e1; ++e) {
+                    double cx = 0.0, cy = 0.0;
+                    for (int a = 0; a < 3; ++a) {
+                        const int64_t v = (int64_t)dofs[e * 6 + vert_col + a] - vert_offset;
+                        if (v < 0 || v >= Np) { bad[t] = 1; continue; }
+                        cx += xy[2 * v];
+                        cy += xy[2 * v + 1];
+                    }
+                    pts[e] = Pt{cx / 3.0, cy / 3.0, (int32_t)e};
+                }
+            });
+        for (auto& x : th) x.join();
+        for (int b : bad) WS_REQUIRE(!b, "analyse: vertex id out of range");
+    }
     std::vector<int64_t> leaf_lo(nleaf + 1, 0);
     kd_rec(pts.data(), 0, Ne, 0, depth, 0, leaf_lo.data(), par_levels);
     leaf_lo[nleaf] = Ne;
@@ -312,16 +332,18 @@ using namespace ws;
 
 extern "C" {
 
-int ws_symbolic_create(const int32_t* h_dofs, int64_t Ne, int64_t N, const double* h_elem_xy,
-                       int64_t first_class_start, int leaf_elems, ws_symbolic** out) {
+int ws_symbolic_create(const int32_t* h_dofs, int64_t Ne, int64_t N, const double* h_xy, int64_t Np,
+                       int vert_col, int64_t vert_offset, int64_t first_class_start, int leaf_elems,
+                       ws_symbolic** out) {
     WS_API_BEGIN
     WS_REQUIRE(out, "out == NULL");
     *out = nullptr;
-    WS_REQUIRE(h_dofs && h_elem_xy, "null pointer");
+    WS_REQUIRE(h_dofs && h_xy, "null pointer");
+    WS_REQUIRE(vert_col == 0 || vert_col == 3, "vert_col must be 0 or 3");
     WS_REQUIRE(N < ((int64_t)1 << 31), "N must fit int32");
     auto* s = new ws_symbolic();
     try {
-        analyse_host(s->S, h_dofs, Ne, N, h_elem_xy, first_class_start, leaf_elems);
+        analyse_host(s->S, h_dofs, Ne, N, h_xy, Np, vert_col, vert_offset, first_class_start, leaf_elems);
     } catch (...) {
         delete s;
         throw;

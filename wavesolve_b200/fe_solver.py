@@ -98,7 +98,7 @@ class DevicePattern:
 class ScalarProblem:
     """Device-resident scalar P2 problem: mesh arrays, pattern, A and B values."""
 
-    def __init__(self, mesh, IOR_dict, k, device=None, all_cells_mass_only=False):
+    def __init__(self, mesh, IOR_dict, k, device=None, all_cells_mass_only=False, build_pattern=True):
         self.dev = dev = _dev.require_cuda(device)
         if all_cells_mass_only:
             conn = np.asarray(mesh.cells[1].data)
@@ -114,8 +114,14 @@ class ScalarProblem:
             self.xy = _dev.h2d(xy, dev)
             self.dofs = _dev.h2d(conn, dev)
             self.k2n2 = _dev.h2d(k2, dev)
-            self.pattern = DevicePattern(self.dofs, self.N)
+            self.pattern = DevicePattern(self.dofs, self.N) if build_pattern else None
         self.h2d_bytes = xy.nbytes + conn.nbytes + k2.nbytes
+
+    def build_pattern(self):
+        if self.pattern is None:
+            with torch.cuda.device(self.dev):
+                self.pattern = DevicePattern(self.dofs, self.N)
+        return self.pattern
 
     def assemble(self):
         p = self.pattern
@@ -149,11 +155,16 @@ class VectorProblem:
         connectivity, material data) but rebuilds the pattern -- bench.py's device-resident step."""
         o = object.__new__(VectorProblem)
         o.__dict__.update(self.__dict__)
-        with torch.cuda.device(self.dev):
-            o.pattern = DevicePattern(o.dofs, o.N)
+        o.pattern = None
         return o
 
-    def __init__(self, mesh, IOR_dict, k, device=None):
+    def build_pattern(self):
+        if self.pattern is None:
+            with torch.cuda.device(self.dev):
+                self.pattern = DevicePattern(self.dofs, self.N)
+        return self.pattern
+
+    def __init__(self, mesh, IOR_dict, k, device=None, build_pattern=True):
         self.dev = dev = _dev.require_cuda(device)
         tris, k2 = _material_major(mesh, IOR_dict, k)
         eidx, _ = _material_major(mesh, IOR_dict, k, data=np.asarray(mesh.edge_indices))
@@ -162,7 +173,9 @@ class VectorProblem:
         self.Ntt = len(mesh.cells[0].data)                        # fe_solver.py:159-162
         self.Nzz = len(mesh.points)
         self.N = self.Ntt + self.Nzz
-        dofs = np.hstack([eidx, tris + np.int32(self.Ntt)]).astype(np.int32)
+        dofs = np.empty((len(tris), 6), dtype=np.int32)
+        dofs[:, :3] = eidx
+        np.add(tris, np.int32(self.Ntt), out=dofs[:, 3:])
         xy = np.ascontiguousarray(np.asarray(mesh.points, dtype=np.float64)[:, :2])
         self.h_dofs, self.h_xy, self.first_class_start = dofs, xy, self.Ntt
         self.h_tris = tris
@@ -173,7 +186,7 @@ class VectorProblem:
             self.dofs = _dev.h2d(dofs, dev)
             self.k2n2 = _dev.h2d(k2, dev)
             self.edges = _dev.h2d(self.h_edges, dev)
-            self.pattern = DevicePattern(self.dofs, self.N)
+            self.pattern = DevicePattern(self.dofs, self.N) if build_pattern else None
         self.h2d_bytes = xy.nbytes + tris.nbytes + dofs.nbytes + k2.nbytes + self.h_edges.nbytes
 
     def assemble(self, transpose=False):
@@ -346,13 +359,15 @@ def solve_waveguide(mesh, wl, IOR_dict, plot=False, ignore_warning=False, sparse
         raise NotImplementedError("order=1 scalar solve is not on the accelerated path yet")
     else:
         raise NotImplementedError
-    prob = ScalarProblem(mesh, IOR_dict, k, device)
+    prob = ScalarProblem(mesh, IOR_dict, k, device, build_pattern=False)
     N = prob.N
     if N > 2000 and not ignore_warning and not sparse:
         raise Exception("A and B matrices are larger than 2000 x 2000 - this may make your system unstable. consider setting sparse=True")
     with torch.cuda.device(prob.dev):
+        fut = _sv.SymbolicFuture(prob.h_dofs, prob.h_xy, N, 0, leaf_elems or _sv.DEFAULT_LEAF_ELEMS)
+        prob.build_pattern()
         A, B = prob.assemble()
-        sym = _sv.Symbolic(prob.h_dofs, prob.centroids(), N, 0, leaf_elems or _sv.DEFAULT_LEAF_ELEMS)
+        sym = fut.result()
         S = _sv.Solver(prob.pattern, sym)
         st = S.factor(A, B, est_eigval)
         wd, Vd, info = _eig_device(prob.pattern, S, B, est_eigval, 0, Nmax, N, prob.dev)
@@ -373,10 +388,15 @@ def solve_vector_resident(prob, sigma, Nmax, leaf_elems=None, symbolic=None):
     quasi-definite M', symbolic analysis (host), factorisation, Krylov iteration.  Returns
     device tensors (w, V) and diagnostics."""
     from . import solver as _sv
+    fut = None
+    if symbolic is None:
+        # host analysis in a worker thread, overlapped with the pattern build and the assembly
+        fut = _sv.SymbolicFuture(prob.h_dofs, prob.h_xy, prob.N, prob.Ntt,
+                                 leaf_elems or _sv.DEFAULT_LEAF_ELEMS)
+    prob.build_pattern()
     A, B = prob.assemble()
     Mq = prob.assemble_qd(sigma)
-    sym = symbolic or _sv.Symbolic(prob.h_dofs, prob.centroids(), prob.N, prob.Ntt,
-                                   leaf_elems or _sv.DEFAULT_LEAF_ELEMS)
+    sym = symbolic if fut is None else fut.result()
     S = _sv.Solver(prob.pattern, sym)
     try:
         st = S.factor(Mq)
@@ -411,7 +431,7 @@ def solve_waveguide_vec(mesh, wl, IOR_dict, plot=False, ignore_warning=False, sp
         est_eigval = np.power(k * target_neff, 2)
     if verbose:
         print("building matrices ... ")
-    prob = VectorProblem(mesh, IOR_dict, k, device)
+    prob = VectorProblem(mesh, IOR_dict, k, device, build_pattern=False)
     N = prob.N
     if N > 2000 and not ignore_warning and not sparse:
         raise Exception("A and B matrices are larger than 2000 x 2000 - this may make your system unstable. consider setting sparse=True")

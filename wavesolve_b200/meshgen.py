@@ -80,6 +80,29 @@ def _add_midside_nodes(points, tris3):
     return pts, tris6
 
 
+def _spatial_sort(points, tris, bits=16):
+    """Order the triangles along a Morton (Z-order) curve of their centroids.  Mesh generators
+    emit elements in a spatially coherent order (advancing front / incremental Delaunay); qhull
+    does not, and an incoherent element order makes the first-appearance edge numbering -- and
+    every gather that follows -- needlessly cache-hostile."""
+    cen = points[tris[:, :3], :2].mean(axis=1)
+    lo = cen.min(axis=0)
+    span = np.maximum(cen.max(axis=0) - lo, 1e-300)
+    q = np.minimum(((cen - lo) / span * (1 << bits)).astype(np.uint64), (1 << bits) - 1)
+
+    def spread(v):
+        v = v & np.uint64(0xFFFFFFFF)
+        v = (v | (v << np.uint64(16))) & np.uint64(0x0000FFFF0000FFFF)
+        v = (v | (v << np.uint64(8))) & np.uint64(0x00FF00FF00FF00FF)
+        v = (v | (v << np.uint64(4))) & np.uint64(0x0F0F0F0F0F0F0F0F)
+        v = (v | (v << np.uint64(2))) & np.uint64(0x3333333333333333)
+        v = (v | (v << np.uint64(1))) & np.uint64(0x5555555555555555)
+        return v
+
+    key = spread(q[:, 0]) | (spread(q[:, 1]) << np.uint64(1))
+    return tris[np.argsort(key, kind="stable")]
+
+
 def _materials_by_radius(points, tris, radii_labels, centres=None):
     """Assign each triangle to the first (label, radius[, centre]) disc containing its centroid.
     Returns an ordered dict label -> [None, idx, None]."""
@@ -150,7 +173,7 @@ def _disc_points(h, R, rng, jitter, circles):
 
 
 def fiber_disc(target_elements, r_core=5.0, r_clad=10.0, order=2, seed=0, jitter=0.2,
-               dtype=np.int64):
+               dtype=np.int64, spatial_sort=False):
     """Step-index circular fibre (getting-started notebook cell 9: r_core=5, r_clad=10):
     Delaunay triangulation of jittered points in the cladding disc, conforming (up to
     Delaunay) to the core circle.  ``target_elements`` is approximate."""
@@ -169,6 +192,8 @@ def fiber_disc(target_elements, r_core=5.0, r_clad=10.0, order=2, seed=0, jitter
     a, b, c = p[tris[:, 0]], p[tris[:, 1]], p[tris[:, 2]]
     J = (b[:, 0] - a[:, 0]) * (c[:, 1] - a[:, 1]) - (c[:, 0] - a[:, 0]) * (b[:, 1] - a[:, 1])
     tris = tris[J > 1e-3 * h * h]
+    if spatial_sort:
+        tris = _spatial_sort(pts, tris)
     if order == 2:
         pts, tris = _add_midside_nodes(pts, tris)
     sets = _materials_by_radius(pts, tris, [("core", r_core), ("cladding", 1e300)])

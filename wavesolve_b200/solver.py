@@ -14,15 +14,20 @@ DEFAULT_LEAF_ELEMS = 48
 class Symbolic:
     """Host-side nested-dissection analysis (``ws_symbolic``)."""
 
-    def __init__(self, dofs: np.ndarray, elem_xy: np.ndarray, N: int, first_class_start: int = 0,
+    def __init__(self, dofs: np.ndarray, xy: np.ndarray, N: int, first_class_start: int = 0,
                  leaf_elems: int = DEFAULT_LEAF_ELEMS):
+        """dofs (Ne,6) int32 unknowns per element, xy (Np,2) node coordinates.  Scalar P2
+        (first_class_start == 0): vertex ids are dofs[:, :3]; vector (first_class_start == Ntt):
+        vertex ids are dofs[:, 3:] - Ntt."""
         dofs = np.ascontiguousarray(dofs, dtype=np.int32)
-        elem_xy = np.ascontiguousarray(elem_xy, dtype=np.float64)
-        assert dofs.ndim == 2 and dofs.shape[1] == 6 and elem_xy.shape == (dofs.shape[0], 2)
+        xy = np.ascontiguousarray(xy, dtype=np.float64)
+        assert dofs.ndim == 2 and dofs.shape[1] == 6 and xy.ndim == 2 and xy.shape[1] == 2
+        vector = first_class_start > 0
         h = C.c_void_p()
         _lib.check(_lib.lib().ws_symbolic_create(dofs.ctypes.data, dofs.shape[0], int(N),
-                                                 elem_xy.ctypes.data, int(first_class_start),
-                                                 int(leaf_elems), C.byref(h)))
+                                                 xy.ctypes.data, xy.shape[0], 3 if vector else 0,
+                                                 int(first_class_start) if vector else 0,
+                                                 int(first_class_start), int(leaf_elems), C.byref(h)))
         self.handle = h
         info = np.zeros(8, dtype=np.int64)
         dinfo = np.zeros(4, dtype=np.float64)
@@ -54,6 +59,31 @@ class Symbolic:
             self.close()
         except Exception:
             pass
+
+
+class SymbolicFuture:
+    """Runs the host symbolic analysis in a worker thread (the C call releases the GIL) so that it
+    overlaps the device-side pattern build and assembly."""
+
+    def __init__(self, *args, **kw):
+        import threading
+        self._out = None
+        self._err = None
+
+        def work():
+            try:
+                self._out = Symbolic(*args, **kw)
+            except BaseException as e:      # re-raised in result()
+                self._err = e
+
+        self._th = threading.Thread(target=work, daemon=True)
+        self._th.start()
+
+    def result(self) -> Symbolic:
+        self._th.join()
+        if self._err is not None:
+            raise self._err
+        return self._out
 
 
 class Solver:

@@ -40,10 +40,9 @@ def get_unique_edges(mesh, mutate=True, device=None):
         edges = _dev.d2h(edges_d).astype(tris.dtype if tris.size else np.int64)
         edge_indices = _dev.d2h(eidx_d).astype(np.uint)             # waveguide.py:16
     if mutate:
-        loc = tris[:, [0, 1, 1, 2, 2, 0]].reshape(-1, 3, 2)
         mesh.cells[0].data = edges                                  # waveguide.py:38-42
         mesh.edge_indices = edge_indices
-        mesh.edge_flips = np.where(loc[..., 0] <= loc[..., 1], 1.0, -1.0)
+        mesh.edge_flips = np.where(t32 <= t32[:, [1, 2, 0]], 1.0, -1.0)   # waveguide.py:33-34
         mesh.num_edges = len(edges)
         mesh.num_points = mesh.points.shape[0]
     return edges, edge_indices
