@@ -48,6 +48,11 @@ extern "C" {
 #define WS_ERR_NUMERIC 2
 #define WS_ERR_NOCONV 3
 
+/* flags of the assembly entry points */
+#define WS_ASM_TRANSPOSE 1 /* slot (i,j) receives element entry (j,i): CSC values of the symmetric pattern */
+#define WS_ASM_FAST 2      /* one reciprocal per element row instead of IEEE divisions (<= 2 ulp off the
+                              reference arithmetic); for the eigen-solve pipeline, not for exported matrices */
+
 typedef struct ws_pattern ws_pattern; /* CSR pattern + row-incidence lists of one mesh   */
 typedef struct ws_symbolic ws_symbolic; /* host: nested-dissection ordering + front tree     */
 typedef struct ws_solver ws_solver;   /* multifrontal LDL^T of A - sigma B               */
@@ -84,10 +89,9 @@ int ws_pattern_destroy(ws_pattern* p);
 /* ---- K3: scalar P2 assembly (fe_solver.py:47-55, shape_funcs.py:192-246) -----------------
  * xy [Np*2] node coordinates, dofs as given to ws_pattern_create, elem_k2n2 [Ne] = k^2 n_e^2
  * (fe_solver.py:51).  A_vals/B_vals [nnz] in the pattern's slot order.
- * transpose != 0 writes slot (i,j) with the element entry (j,i) (CSC values of the same
- * symmetric pattern).                                                                  */
+ * flags: WS_ASM_TRANSPOSE | WS_ASM_FAST.                                                 */
 int ws_assemble_scalar_p2(const ws_pattern* p, const double* xy, const int32_t* dofs,
-                          const double* elem_k2n2, double* A_vals, double* B_vals, int transpose,
+                          const double* elem_k2n2, double* A_vals, double* B_vals, int flags,
                           int device, void* stream);
 /* mass matrix only, all elements (fe_solver.py:71-99) */
 int ws_assemble_mass_p2(const ws_pattern* p, const double* xy, const int32_t* dofs, double* B_vals,
@@ -98,7 +102,7 @@ int ws_assemble_mass_p2(const ws_pattern* p, const double* xy, const int32_t* do
  * A_vals/B_vals [nnz] on the pattern of B; A is non-zero only in the edge-edge block.  */
 int ws_assemble_vector_p1(const ws_pattern* p, const double* xy, const int32_t* tris,
                           const double* elem_k2n2, int64_t Ntt, double* A_vals, double* B_vals,
-                          int transpose, int device, void* stream);
+                          int flags, int device, void* stream);
 
 /* ---- zero pruning (lil_matrix semantics behind fe_solver.py:196-199, 212-213) -------------
  * Compacts (pattern, vals) to the entries with vals != 0.0.  out_* sized for nnz.        */
@@ -161,11 +165,12 @@ int ws_solver_destroy(ws_solver* s);
  * G[i,lo] = -1/len_i) and T = [[I,-G],[0,I]], M' = T^T M T is symmetric quasi-definite:
  *     M' = [[ (k2n2-sigma) NeNe - curlcurl , -k2n2 NedN ], [ . , k2n2 (dNdN + sigma NN) ]]
  * so LDL^T needs no pivoting, and M^-1 = T M'^-1 T^T.
- * ws_assemble_vector_qd writes M' on the pattern; ws_vector_T applies T (mode 0) or T^T (mode 1).
+ * ws_assemble_vector_qd writes M' on the pattern (and, when B_vals != NULL, B in the same pass);
+ * ws_vector_T applies T (mode 0) or T^T (mode 1).
  * edges [Ntt*2] as produced by ws_edges_first_appearance.                                    */
 int ws_assemble_vector_qd(const ws_pattern* p, const double* xy, const int32_t* tris,
                           const double* elem_k2n2, int64_t Ntt, double sigma, double* M_vals,
-                          int device, void* stream);
+                          double* B_vals, int flags, int device, void* stream);
 int ws_vector_T(const ws_pattern* p, const int32_t* edges, const double* xy, int64_t Ntt, int mode,
                 const double* in, double* out, int device, void* stream);
 

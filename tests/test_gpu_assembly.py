@@ -221,3 +221,28 @@ def test_empty_and_tiny_meshes(ws):
     m1.cells[1].data = m1.cells[1].data[:0]
     edges, eidx = ws.get_unique_edges(m1, mutate=False)
     assert edges.shape[0] == 0 and eidx.shape == (0, 3)
+
+
+def test_fast_mode_and_fused_qd_assembly(ws):
+    """WS_ASM_FAST (reciprocal arithmetic inside the solve pipeline) stays within a few ulp of the
+    exact mode; the fused pass returns the same M' and B as the separate ones."""
+    from wavesolve_b200 import fe_solver as fs
+    mg = ws.meshgen
+    k = 2 * np.pi / 1.55
+    sp_ = fs.ScalarProblem(mg.fiber_disc(30000, seed=8), mg.FIBER_IOR, k)
+    A, B = sp_.assemble()
+    Af, Bf = sp_.assemble(fast=True)
+    for X, Y in ((A, Af), (B, Bf)):
+        X, Y = X.cpu().numpy(), Y.cpu().numpy()
+        assert np.abs(X - Y).max() <= 1e-14 * np.abs(X).max()
+    mesh = mg.fiber_disc(30000, order=1, seed=9)
+    ws.get_unique_edges(mesh)
+    vp = fs.VectorProblem(mesh, mg.FIBER_IOR, k)
+    sigma = (k * 1.4528) ** 2
+    A, B = vp.assemble()
+    M1 = vp.assemble_qd(sigma)
+    M2, B2 = vp.assemble_qd(sigma, with_B=True)
+    assert torch.equal(M1, M2) and torch.equal(B, B2)
+    M3, B3 = vp.assemble_qd(sigma, with_B=True, fast=True)
+    assert (M3 - M1).abs().max().item() <= 1e-13 * M1.abs().max().item()
+    assert (B3 - B).abs().max().item() <= 1e-14 * B.abs().max().item()

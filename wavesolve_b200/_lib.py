@@ -11,6 +11,9 @@ LIB_PATH = os.path.join(PKG, "libwavesolve_b200.so")
 
 _lib = None
 
+ASM_TRANSPOSE = 1
+ASM_FAST = 2
+
 c_i32p = C.c_void_p   # device pointers travel as integers
 c_f64p = C.c_void_p
 c_i64 = C.c_int64
@@ -42,7 +45,7 @@ _SIGNATURES = {
     "ws_solver_solve": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_vp]),
     "ws_solver_stats": (c_int, [c_vp, c_vp, c_vp]),
     "ws_solver_destroy": (c_int, [c_vp]),
-    "ws_assemble_vector_qd": (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, C.c_double, c_vp, c_int, c_vp]),
+    "ws_assemble_vector_qd": (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, C.c_double, c_vp, c_vp, c_int, c_int, c_vp]),
     "ws_eig_solve": (c_int, [c_vp, c_vp, c_vp, C.c_double, c_int, c_int, c_int, C.c_double, c_int, C.c_uint64,
                              c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_int, c_vp]),
     "ws_host_eig_general": (c_int, [c_int, c_vp, c_vp, c_vp, c_vp, c_int]),

@@ -17,13 +17,15 @@
 //
 //   scalar P2 : shape_funcs.py:192-246 (compute_NN_dNdN_vec), fe_solver.py:51-54
 //   vector    : shape_funcs.py:310-428 (precompute, computeL_*), fe_solver.py:196-199
+#include <algorithm>
+#include <cstdlib>
+
 #include "ws_common.cuh"
 
 namespace ws {
 
 constexpr int ROWS_PER_CTA = 128;
-constexpr int TILE_CAP = 3072;  // slots per CTA tile in shared memory (A and B: 48 KB -> 4 CTAs / SM);
-                                // denser row blocks fall back to accumulating in global memory
+constexpr int MAX_TILE_BYTES = 96 * 1024;   // larger row blocks accumulate in global memory instead
 
 struct RowCtx {
     const int32_t* rowptr;
@@ -31,6 +33,15 @@ struct RowCtx {
     const uint32_t* inc;
     const uint16_t* pos;
     int64_t N;
+    int64_t first_block;  // first 128-row block of this launch
+    int cap;              // slots of the shared-memory tile (>= the largest block of the launch, if it fits)
+};
+
+// raw inputs of one element: vertex ids, vertex coordinates, k^2 n^2
+struct RawTri {
+    int32_t t0, t1, t2;
+    double2 P0, P1, P2;
+    double c;
 };
 
 // ---- scalar P2 ---------------------------------------------------------------------------
@@ -39,14 +50,26 @@ struct RowCtx {
 // or renames the coordinate differences, and round-to-nearest is sign-symmetric, so each
 // entry has the same bits as the reference's un-rotated formula.  J is taken from the
 // un-rotated vertices (shape_funcs.py:202).
+// fast != 0: one reciprocal instead of the 5-8 IEEE divisions per row (entries within 2 ulp of
+// the exact mode); used inside the eigen-solve pipeline, never for the matrices handed back to
+// the caller.
 struct ScalarP2 {
     const double2* xy;
     const int32_t* dofs;
     const double* k2n2;   // nullptr -> mass only
+    int fast;
 
-    __device__ __forceinline__ void row(uint32_t e, int a, double (&Av)[6], double (&Bv)[6], int (&cb)[6]) const {
+    __device__ __forceinline__ RawTri load(uint32_t e) const {
         const int32_t* d = dofs + (int64_t)e * 6;
-        double2 P0 = xy[d[0]], P1 = xy[d[1]], P2 = xy[d[2]];
+        RawTri r;
+        r.t0 = d[0]; r.t1 = d[1]; r.t2 = d[2];
+        r.P0 = xy[r.t0]; r.P1 = xy[r.t1]; r.P2 = xy[r.t2];
+        r.c = k2n2 ? k2n2[e] : 0.0;
+        return r;
+    }
+
+    __device__ __forceinline__ void row(const RawTri& in, int a, double (&Av)[6], double (&Bv)[6], int (&cb)[6]) const {
+        double2 P0 = in.P0, P1 = in.P1, P2 = in.P2;
         const double J = (P1.x - P0.x) * (P2.y - P0.y) - (P2.x - P0.x) * (P1.y - P0.y);
         const int rot = a < 3 ? a : a - 3;
         if (rot == 1) { double2 t = P0; P0 = P1; P1 = P2; P2 = t; }
@@ -58,36 +81,62 @@ struct ScalarP2 {
         const int r1 = rot == 2 ? 0 : rot + 1, r2 = rot == 0 ? 2 : rot - 1;
         cb[0] = rot; cb[1] = r1; cb[2] = r2; cb[3] = 3 + rot; cb[4] = 3 + r1; cb[5] = 3 + r2;
         double K[6], M[6];
-        if (a < 3) {
-            const double s01 = y32 * y31 + x32 * x31;
-            const double s02 = y21 * y32 + x21 * x32;
-            K[0] = (y32 * y32 + x32 * x32) / (2 * J);
-            K[1] = s01 / (6 * J);
-            K[2] = (-y21 * y32 - x21 * x32) / (6 * J);
-            K[3] = -2 * s01 / (3 * J);
-            K[4] = 0.0;
-            K[5] = 2 * s02 / (3 * J);
-            M[0] = J / 60;
-            M[1] = M[2] = -J / 360;
-            M[3] = M[5] = 0.0;
-            M[4] = -J / 90;
+        const double s01 = y32 * y31 + x32 * x31;
+        if (!fast) {
+            if (a < 3) {
+                const double s02 = y21 * y32 + x21 * x32;
+                K[0] = (y32 * y32 + x32 * x32) / (2 * J);          // shape_funcs.py:222-224
+                K[1] = s01 / (6 * J);                              // :230-232
+                K[2] = (-y21 * y32 - x21 * x32) / (6 * J);
+                K[3] = -2 * s01 / (3 * J);                         // :235-237
+                K[4] = 0.0;
+                K[5] = 2 * s02 / (3 * J);
+                M[0] = J / 60;                                     // :205
+                M[1] = M[2] = -J / 360;                            // :209
+                M[3] = M[5] = 0.0;
+                M[4] = -J / 90;                                    // :212
+            } else {
+                const double f = 4 / (3 * J);
+                K[0] = K[1] = -2 * s01 / (3 * J);                  // :235-237
+                K[2] = 0.0;
+                K[3] = f * (y32 * y32 + y31 * y21 + x32 * x32 + x31 * x21);   // :225-227
+                K[4] = f * (y21 * y32 + x21 * x32);                // :242-244
+                K[5] = -f * (y31 * y21 + x31 * x21);
+                M[0] = M[1] = 0.0;
+                M[2] = -J / 90;                                    // :212
+                M[3] = 4 * J / 45;                                 // :206
+                M[4] = M[5] = 2 * J / 45;                          // :214
+            }
         } else {
-            const double f = 4 / (3 * J);
-            const double s01 = y32 * y31 + x32 * x31;
-            K[0] = K[1] = -2 * s01 / (3 * J);
-            K[2] = 0.0;
-            K[3] = f * (y32 * y32 + y31 * y21 + x32 * x32 + x31 * x21);
-            K[4] = f * (y21 * y32 + x21 * x32);
-            K[5] = -f * (y31 * y21 + x31 * x21);
-            M[0] = M[1] = 0.0;
-            M[2] = -J / 90;
-            M[3] = 4 * J / 45;
-            M[4] = M[5] = 2 * J / 45;
+            const double rJ = 1.0 / J;
+            if (a < 3) {
+                const double s02 = y21 * y32 + x21 * x32;
+                K[0] = (y32 * y32 + x32 * x32) * (0.5 * rJ);
+                K[1] = s01 * (rJ * (1.0 / 6.0));
+                K[2] = -s02 * (rJ * (1.0 / 6.0));
+                K[3] = -2 * s01 * (rJ * (1.0 / 3.0));
+                K[4] = 0.0;
+                K[5] = 2 * s02 * (rJ * (1.0 / 3.0));
+                M[0] = J * (1.0 / 60.0);
+                M[1] = M[2] = -J * (1.0 / 360.0);
+                M[3] = M[5] = 0.0;
+                M[4] = -J * (1.0 / 90.0);
+            } else {
+                const double f = 4 * (rJ * (1.0 / 3.0));
+                K[0] = K[1] = -2 * s01 * (rJ * (1.0 / 3.0));
+                K[2] = 0.0;
+                K[3] = f * (y32 * y32 + y31 * y21 + x32 * x32 + x31 * x21);
+                K[4] = f * (y21 * y32 + x21 * x32);
+                K[5] = -f * (y31 * y21 + x31 * x21);
+                M[0] = M[1] = 0.0;
+                M[2] = -J * (1.0 / 90.0);
+                M[3] = 4 * J * (1.0 / 45.0);
+                M[4] = M[5] = 2 * J * (1.0 / 45.0);
+            }
         }
         if (k2n2) {
-            const double c = k2n2[e];
 #pragma unroll
-            for (int j = 0; j < 6; ++j) Av[j] = __dsub_rn(__dmul_rn(c, M[j]), K[j]);   // fe_solver.py:51
+            for (int j = 0; j < 6; ++j) Av[j] = __dsub_rn(__dmul_rn(in.c, M[j]), K[j]);   // fe_solver.py:51
         }
 #pragma unroll
         for (int j = 0; j < 6; ++j) Bv[j] = M[j];                                        // fe_solver.py:54
@@ -95,22 +144,34 @@ struct ScalarP2 {
 };
 
 // ---- vector: Whitney edge elements + P1 nodes ---------------------------------------------
+// mode 0: Av = row of A, Bv = row of B (reference semantics, fe_solver.py:196-199)
+// mode 1: Bv = row of the quasi-definite M' = T^T (A - sigma B) T
+// mode 2: Av = row of M', Bv = row of B (what the eigen-solve pipeline needs, one pass)
 struct VectorP1 {
     const double2* xy;
     const int32_t* tris;
     const double* k2n2;
     int transpose;
-    int qd;          // 1: write the quasi-definite shift-invert matrix M' = T^T (A - sigma B) T into Bv
+    int mode;
     double sigma;
+    int fast;
+
+    __device__ __forceinline__ RawTri load(uint32_t e) const {
+        const int32_t* t = tris + (int64_t)e * 3;
+        RawTri r;
+        r.t0 = t[0]; r.t1 = t[1]; r.t2 = t[2];
+        r.P0 = xy[r.t0]; r.P1 = xy[r.t1]; r.P2 = xy[r.t2];
+        r.c = k2n2[e];
+        return r;
+    }
 
     // Branch-free in the local index: the (cheap) numerators of all rows are formed and the ones
     // of row `a` are picked with selects, so a warp whose lanes hold different local rows does not
     // serialise three copies of the expensive part (3 sqrt + 7-8 IEEE divisions per incidence).
     // Every expression keeps the reference's association (shape_funcs.py line cited per entry).
-    __device__ __forceinline__ void row(uint32_t e, int a, double (&Av)[6], double (&Bv)[6], int (&cb)[6]) const {
-        const int32_t* t = tris + (int64_t)e * 3;
-        const int32_t t0 = t[0], t1 = t[1], t2 = t[2];
-        const double2 P0 = xy[t0], P1 = xy[t1], P2 = xy[t2];
+    __device__ __forceinline__ void row(const RawTri& in, int a, double (&Av)[6], double (&Bv)[6], int (&cb)[6]) const {
+        const int32_t t0 = in.t0, t1 = in.t1, t2 = in.t2;
+        const double2 P0 = in.P0, P1 = in.P1, P2 = in.P2;
         const double x21 = P1.x - P0.x, y21 = P1.y - P0.y;          // shape_funcs.py:311-316
         const double x31 = P2.x - P0.x, y31 = P2.y - P0.y;
         const double x32 = P2.x - P1.x, y32 = P2.y - P1.y;
@@ -118,14 +179,13 @@ struct VectorP1 {
         const double s2 = t1 < t2 ? 1.0 : -1.0;
         const double s3 = t2 < t0 ? 1.0 : -1.0;
         const double J = x21 * y31 - x31 * y21;                      // shape_funcs.py:323
-        const double c = k2n2[e];
+        const double c = in.c;
         const double xx = x21 * x31, yy = y21 * y31;
         const double l12 = sqrt(x21 * x21 + y21 * y21) * s1;         // shape_funcs.py:320-322
         const double l23 = sqrt(x32 * x32 + y32 * y32) * s2;
         const double l31 = sqrt(x31 * x31 + y31 * y31) * s3;
         const double sq12 = l12 * l12, sq23 = l23 * l23, sq31 = l31 * l31;
         const double x3 = (3 * x21) * x31, y3 = (3 * y21) * y31;
-        const double J6 = 6 * J;
 #pragma unroll
         for (int j = 0; j < 6; ++j) { cb[j] = j; Av[j] = 0.0; }
         // numerators of NedN (D_ij, i = edge, j = node), shape_funcs.py:393-401
@@ -138,8 +198,8 @@ struct VectorP1 {
         const double nD20 = l31 * (2 * sq12 - x3 + sq31 - y3);        // :400
         const double nD21 = l31 * (2 * xx + 2 * yy - sq31);           // :399
         const double nD22 = l31 * (-2 * sq12 + xx + yy);              // :395
+        const double rJ = fast ? 1.0 / J : 0.0;
         if (a < 3) {
-            const double J12 = 12 * J, tJ = 2 / J;
             // numerators of NeNe (symmetric), shape_funcs.py:369-374
             const double nE00 = sq12 * (sq12 - x3 + 3 * sq31 - y3);          // :369
             const double nE11 = sq23 * (sq12 + xx + sq31 + yy);              // :370
@@ -148,32 +208,44 @@ struct VectorP1 {
             const double nE12 = l23 * l31 * (-sq12 - xx + sq31 - yy);        // :373
             const double nE02 = l31 * l12 * (-sq12 + x3 - sq31 + y3);        // :374
             const bool a0 = a == 0, a1 = a == 1;
-            const double E0 = (a0 ? nE00 : (a1 ? nE01 : nE02)) / J12;
-            const double E1 = (a0 ? nE01 : (a1 ? nE11 : nE12)) / J12;
-            const double E2 = (a0 ? nE02 : (a1 ? nE12 : nE22)) / J12;
-            const double D0 = (a0 ? nD00 : (a1 ? nD10 : nD20)) / J6;
-            const double D1 = (a0 ? nD01 : (a1 ? nD11 : nD21)) / J6;
-            const double D2 = (a0 ? nD02 : (a1 ? nD12 : nD22)) / J6;
+            const double e0 = a0 ? nE00 : (a1 ? nE01 : nE02);
+            const double e1 = a0 ? nE01 : (a1 ? nE11 : nE12);
+            const double e2 = a0 ? nE02 : (a1 ? nE12 : nE22);
+            const double d0 = a0 ? nD00 : (a1 ? nD10 : nD20);
+            const double d1 = a0 ? nD01 : (a1 ? nD11 : nD21);
+            const double d2 = a0 ? nD02 : (a1 ? nD12 : nD22);
+            double E0, E1, E2, D0, D1, D2, tJ;
+            if (!fast) {
+                const double J12 = 12 * J, J6 = 6 * J;
+                E0 = e0 / J12; E1 = e1 / J12; E2 = e2 / J12;
+                D0 = d0 / J6; D1 = d1 / J6; D2 = d2 / J6;
+                tJ = 2 / J;
+            } else {
+                const double i12 = rJ * (1.0 / 12.0), i6 = rJ * (1.0 / 6.0);
+                E0 = e0 * i12; E1 = e1 * i12; E2 = e2 * i12;
+                D0 = d0 * i6; D1 = d1 * i6; D2 = d2 * i6;
+                tJ = 2 * rJ;
+            }
             const double la = a0 ? l12 : (a1 ? l23 : l31);
             // curl-curl ((2/J) l_i) l_j, shape_funcs.py:382-383 (row i = a; transposed: column i = a)
             const double C0 = transpose ? (tJ * l12) * la : (tJ * la) * l12;
             const double C1 = transpose ? (tJ * l23) * la : (tJ * la) * l23;
             const double C2 = transpose ? (tJ * l31) * la : (tJ * la) * l31;
-            if (qd) {
-                Bv[0] = (c - sigma) * E0 - C0; Bv[1] = (c - sigma) * E1 - C1; Bv[2] = (c - sigma) * E2 - C2;
-                Bv[3] = -c * D0; Bv[4] = -c * D1; Bv[5] = -c * D2;
-                return;
+            if (mode != 0) {
+                double (&Mv)[6] = mode == 1 ? Bv : Av;
+                Mv[0] = (c - sigma) * E0 - C0; Mv[1] = (c - sigma) * E1 - C1; Mv[2] = (c - sigma) * E2 - C2;
+                Mv[3] = -c * D0; Mv[4] = -c * D1; Mv[5] = -c * D2;
+                if (mode == 1) return;
+            } else {
+                Av[0] = __dsub_rn(__dmul_rn(c, E0), C0);                          // fe_solver.py:196
+                Av[1] = __dsub_rn(__dmul_rn(c, E1), C1);
+                Av[2] = __dsub_rn(__dmul_rn(c, E2), C2);
             }
-            Av[0] = __dsub_rn(__dmul_rn(c, E0), C0);                              // fe_solver.py:196
-            Av[1] = __dsub_rn(__dmul_rn(c, E1), C1);
-            Av[2] = __dsub_rn(__dmul_rn(c, E2), C2);
             Bv[0] = E0; Bv[1] = E1; Bv[2] = E2;                                    // fe_solver.py:197
             Bv[3] = D0; Bv[4] = D1; Bv[5] = D2;                                    // fe_solver.py:198
         } else {
             const int i = a - 3;
             const bool i0 = i == 0, i1 = i == 1;
-            const double J2 = 2 * J;
-            const double Nd = J / 12, No = J / 24;                                // shape_funcs.py:410-411
             // numerators of dNdN (symmetric), shape_funcs.py:421-426
             const double nG00 = sq12 + sq31 - 2 * xx - 2 * yy;                    // :421
             const double nG11 = sq31;                                             // :422
@@ -181,17 +253,30 @@ struct VectorP1 {
             const double nG01 = -sq31 + xx + yy;                                  // :424
             const double nG12 = -xx - yy;                                         // :425
             const double nG02 = -sq12 + xx + yy;                                  // :426
-            const double Dt0 = (i0 ? nD00 : (i1 ? nD01 : nD02)) / J6;             // column i of NedN
-            const double Dt1 = (i0 ? nD10 : (i1 ? nD11 : nD12)) / J6;
-            const double Dt2 = (i0 ? nD20 : (i1 ? nD21 : nD22)) / J6;
-            const double G0 = (i0 ? nG00 : (i1 ? nG01 : nG02)) / J2;
-            const double G1 = (i0 ? nG01 : (i1 ? nG11 : nG12)) / J2;
-            const double G2 = (i0 ? nG02 : (i1 ? nG12 : nG22)) / J2;
+            const double d0 = i0 ? nD00 : (i1 ? nD01 : nD02);                     // column i of NedN
+            const double d1 = i0 ? nD10 : (i1 ? nD11 : nD12);
+            const double d2 = i0 ? nD20 : (i1 ? nD21 : nD22);
+            const double g0 = i0 ? nG00 : (i1 ? nG01 : nG02);
+            const double g1 = i0 ? nG01 : (i1 ? nG11 : nG12);
+            const double g2 = i0 ? nG02 : (i1 ? nG12 : nG22);
+            double Dt0, Dt1, Dt2, G0, G1, G2, Nd, No;
+            if (!fast) {
+                const double J6 = 6 * J, J2 = 2 * J;
+                Dt0 = d0 / J6; Dt1 = d1 / J6; Dt2 = d2 / J6;
+                G0 = g0 / J2; G1 = g1 / J2; G2 = g2 / J2;
+                Nd = J / 12; No = J / 24;                                         // shape_funcs.py:410-411
+            } else {
+                const double i6 = rJ * (1.0 / 6.0), i2 = 0.5 * rJ;
+                Dt0 = d0 * i6; Dt1 = d1 * i6; Dt2 = d2 * i6;
+                G0 = g0 * i2; G1 = g1 * i2; G2 = g2 * i2;
+                Nd = J * (1.0 / 12.0); No = J * (1.0 / 24.0);
+            }
             const double N0 = i0 ? Nd : No, N1 = i1 ? Nd : No, N2 = (i == 2) ? Nd : No;
-            if (qd) {
-                Bv[0] = -c * Dt0; Bv[1] = -c * Dt1; Bv[2] = -c * Dt2;
-                Bv[3] = c * (G0 + sigma * N0); Bv[4] = c * (G1 + sigma * N1); Bv[5] = c * (G2 + sigma * N2);
-                return;
+            if (mode != 0) {
+                double (&Mv)[6] = mode == 1 ? Bv : Av;
+                Mv[0] = -c * Dt0; Mv[1] = -c * Dt1; Mv[2] = -c * Dt2;
+                Mv[3] = c * (G0 + sigma * N0); Mv[4] = c * (G1 + sigma * N1); Mv[5] = c * (G2 + sigma * N2);
+                if (mode == 1) return;
             }
             Bv[0] = Dt0; Bv[1] = Dt1; Bv[2] = Dt2;                                // fe_solver.py:209
             Bv[3] = __dsub_rn(G0, __dmul_rn(c, N0));                              // fe_solver.py:199
@@ -201,17 +286,21 @@ struct VectorP1 {
     }
 };
 
-template <class Op, bool WRITE_A>
+// One thread per matrix row.  The raw inputs of the NEXT incident element are requested before
+// the arithmetic of the current one starts (software prefetch: the incidence -> connectivity ->
+// coordinates chain is three dependent loads deep), and the row's slots live in a shared-memory
+// tile that is written back with coalesced stores.
+template <class Op, bool WRITE_A, bool PREFETCH>
 __global__ void __launch_bounds__(ROWS_PER_CTA)
 k_assemble_rows(RowCtx cx, Op op, double* __restrict__ A, double* __restrict__ B) {
     extern __shared__ double tile[];
-    const int64_t r0 = (int64_t)blockIdx.x * ROWS_PER_CTA;
+    const int64_t r0 = (cx.first_block + blockIdx.x) * ROWS_PER_CTA;
     const int64_t r1 = min(r0 + ROWS_PER_CTA, cx.N);
     const int s0 = cx.rowptr[r0], s1 = cx.rowptr[r1];
     const int S = s1 - s0;
-    const bool in_smem = S <= TILE_CAP;
+    const bool in_smem = S <= cx.cap;
     double* tB = in_smem ? tile : B + s0;
-    double* tA = in_smem ? tile + TILE_CAP : (WRITE_A ? A + s0 : nullptr);
+    double* tA = in_smem ? tile + cx.cap : (WRITE_A ? A + s0 : nullptr);
     for (int t = threadIdx.x; t < S; t += ROWS_PER_CTA) {
         tB[t] = 0.0;
         if (WRITE_A) tA[t] = 0.0;
@@ -221,17 +310,36 @@ k_assemble_rows(RowCtx cx, Op op, double* __restrict__ A, double* __restrict__ B
     if (r < r1) {
         const int base = cx.rowptr[r] - s0;
         const int i0 = cx.incptr[r], i1 = cx.incptr[r + 1];
-        for (int i = i0; i < i1; ++i) {
-            const uint32_t u = cx.inc[i];
-            double Av[6], Bv[6];
-            int cb[6];
-            op.row(u >> 3, (int)(u & 7u), Av, Bv, cb);
-            const uint16_t* p = cx.pos + (int64_t)i * 6;
+        if (i0 < i1) {
+            uint32_t u = cx.inc[i0];
+            RawTri cur = op.load(u >> 3);
+            for (int i = i0; i < i1; ++i) {
+                uint32_t un = u;
+                RawTri nxt = cur;
+                if (PREFETCH) {
+                    un = (i + 1 < i1) ? cx.inc[i + 1] : u;
+                    nxt = op.load(un >> 3);
+                }
+                const uint32_t* pp = reinterpret_cast<const uint32_t*>(cx.pos + (int64_t)i * 6);
+                const uint32_t pk0 = pp[0], pk1 = pp[1], pk2 = pp[2];
+                double Av[6], Bv[6];
+                int cb[6];
+                op.row(cur, (int)(u & 7u), Av, Bv, cb);
 #pragma unroll
-            for (int j = 0; j < 6; ++j) {
-                const int q = base + p[cb[j]];
-                tB[q] += Bv[j];
-                if (WRITE_A) tA[q] += Av[j];
+                for (int j = 0; j < 6; ++j) {
+                    const int h = cb[j] >> 1;
+                    const uint32_t w = h == 0 ? pk0 : (h == 1 ? pk1 : pk2);
+                    const int q = base + (int)((cb[j] & 1) ? (w >> 16) : (w & 0xffffu));
+                    tB[q] += Bv[j];
+                    if (WRITE_A) tA[q] += Av[j];
+                }
+                if (PREFETCH) {
+                    cur = nxt;
+                    u = un;
+                } else if (i + 1 < i1) {
+                    u = cx.inc[i + 1];
+                    cur = op.load(u >> 3);
+                }
             }
         }
     }
@@ -244,20 +352,41 @@ k_assemble_rows(RowCtx cx, Op op, double* __restrict__ A, double* __restrict__ B
     }
 }
 
+// The row blocks are launched in up to 16 contiguous groups, each with a shared-memory tile
+// sized for its own densest block: sparse stretches of the matrix (edge rows, mid-side rows)
+// then run at a much higher occupancy than the dense ones (vertex / node rows).
 template <class Op, bool WRITE_A>
 static void launch_rows(const ws_pattern* p, const Op& op, double* A, double* B, cudaStream_t st) {
     if (p->N == 0 || p->nnz == 0) return;
-    RowCtx cx{p->rowptr.get(), p->incptr.get(), p->inc.get(), p->pos.get(), p->N};
-    size_t smem = (size_t)TILE_CAP * 8 * (WRITE_A ? 2 : 1);
-    auto kern = k_assemble_rows<Op, WRITE_A>;
+    const int per_slot = 8 * (WRITE_A ? 2 : 1);
+    static int n_ranges = -1, prefetch = -1;
+    if (n_ranges < 0) {
+        const char* e = getenv("WS_ASM_RANGES");
+        n_ranges = e ? std::max(1, std::min(atoi(e), (int)ws_pattern::NRANGE)) : 1;
+        const char* f = getenv("WS_ASM_PREFETCH");
+        prefetch = f ? atoi(f) : 0;
+    }
+    auto kern = prefetch ? k_assemble_rows<Op, WRITE_A, true> : k_assemble_rows<Op, WRITE_A, false>;
     static bool configured = false;
     if (!configured) {
-        WS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        WS_CUDA(cudaFuncSetAttribute(k_assemble_rows<Op, WRITE_A, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_TILE_BYTES));
+        WS_CUDA(cudaFuncSetAttribute(k_assemble_rows<Op, WRITE_A, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_TILE_BYTES));
         configured = true;
     }
-    kern<<<ceil_div(p->N, ROWS_PER_CTA), ROWS_PER_CTA, smem, st>>>(cx, op, A, B);
+    const int nblocks = ceil_div(p->N, ROWS_PER_CTA);
+    const int per_group = std::max(1, ceil_div(nblocks, ws_pattern::NRANGE));
+    const int groups_per_launch = ws_pattern::NRANGE / n_ranges;
+    for (int g = 0; g * per_group < nblocks; g += groups_per_launch) {
+        const int b0 = g * per_group, b1 = std::min(nblocks, (g + groups_per_launch) * per_group);
+        int cap = 32;
+        for (int gg = g; gg < g + groups_per_launch && gg < ws_pattern::NRANGE; ++gg) cap = std::max(cap, p->range_block_slots[gg]);
+        cap = (cap + 31) & ~31;
+        if ((size_t)cap * per_slot > MAX_TILE_BYTES) cap = MAX_TILE_BYTES / per_slot;
+        RowCtx cx{p->rowptr.get(), p->incptr.get(), p->inc.get(), p->pos.get(), p->N, b0, cap};
+        kern<<<b1 - b0, ROWS_PER_CTA, (size_t)cap * per_slot, st>>>(cx, op, A, B);
+        count_launch(1);
+    }
     WS_CUDA(cudaGetLastError());
-    count_launch(1);
 }
 
 __global__ void k_axpby(int64_t n, double alpha, const double* __restrict__ x, double beta, double* __restrict__ y) {
@@ -273,15 +402,15 @@ using namespace ws;
 extern "C" {
 
 int ws_assemble_scalar_p2(const ws_pattern* p, const double* xy, const int32_t* dofs,
-                          const double* elem_k2n2, double* A_vals, double* B_vals, int transpose,
+                          const double* elem_k2n2, double* A_vals, double* B_vals, int flags,
                           int device, void* stream) {
     WS_API_BEGIN
-    (void)transpose;   // P2 scalar element matrices are bit-symmetric
+    // WS_ASM_TRANSPOSE is a no-op here: P2 scalar element matrices are bit-symmetric
     WS_REQUIRE(p, "pattern == NULL");
     if (p->nnz == 0) return WS_OK;
     WS_REQUIRE(xy && dofs && elem_k2n2 && A_vals && B_vals, "null pointer");
     DeviceGuard g(device);
-    ScalarP2 op{(const double2*)xy, dofs, elem_k2n2};
+    ScalarP2 op{(const double2*)xy, dofs, elem_k2n2, (flags & WS_ASM_FAST) ? 1 : 0};
     launch_rows<ScalarP2, true>(p, op, A_vals, B_vals, (cudaStream_t)stream);
     WS_API_END
 }
@@ -293,36 +422,42 @@ int ws_assemble_mass_p2(const ws_pattern* p, const double* xy, const int32_t* do
     if (p->nnz == 0) return WS_OK;
     WS_REQUIRE(xy && dofs && B_vals, "null pointer");
     DeviceGuard g(device);
-    ScalarP2 op{(const double2*)xy, dofs, nullptr};
+    ScalarP2 op{(const double2*)xy, dofs, nullptr, 0};
     launch_rows<ScalarP2, false>(p, op, nullptr, B_vals, (cudaStream_t)stream);
     WS_API_END
 }
 
 int ws_assemble_vector_p1(const ws_pattern* p, const double* xy, const int32_t* tris,
                           const double* elem_k2n2, int64_t Ntt, double* A_vals, double* B_vals,
-                          int transpose, int device, void* stream) {
+                          int flags, int device, void* stream) {
     WS_API_BEGIN
     WS_REQUIRE(p, "pattern == NULL");
     WS_REQUIRE(Ntt >= 0 && Ntt <= p->N, "0 <= Ntt <= N");
     if (p->nnz == 0) return WS_OK;
     WS_REQUIRE(xy && tris && elem_k2n2 && A_vals && B_vals, "null pointer");
     DeviceGuard g(device);
-    VectorP1 op{(const double2*)xy, tris, elem_k2n2, transpose, 0, 0.0};
+    VectorP1 op{(const double2*)xy, tris, elem_k2n2, (flags & WS_ASM_TRANSPOSE) ? 1 : 0, 0, 0.0, (flags & WS_ASM_FAST) ? 1 : 0};
     launch_rows<VectorP1, true>(p, op, A_vals, B_vals, (cudaStream_t)stream);
     WS_API_END
 }
 
 int ws_assemble_vector_qd(const ws_pattern* p, const double* xy, const int32_t* tris,
                           const double* elem_k2n2, int64_t Ntt, double sigma, double* M_vals,
-                          int device, void* stream) {
+                          double* B_vals, int flags, int device, void* stream) {
     WS_API_BEGIN
     WS_REQUIRE(p, "pattern == NULL");
     WS_REQUIRE(Ntt >= 0 && Ntt <= p->N, "0 <= Ntt <= N");
     if (p->nnz == 0) return WS_OK;
     WS_REQUIRE(xy && tris && elem_k2n2 && M_vals, "null pointer");
     DeviceGuard g(device);
-    VectorP1 op{(const double2*)xy, tris, elem_k2n2, 0, 1, sigma};
-    launch_rows<VectorP1, false>(p, op, nullptr, M_vals, (cudaStream_t)stream);
+    const int fast = (flags & WS_ASM_FAST) ? 1 : 0;
+    if (B_vals) {
+        VectorP1 op{(const double2*)xy, tris, elem_k2n2, 0, 2, sigma, fast};
+        launch_rows<VectorP1, true>(p, op, M_vals, B_vals, (cudaStream_t)stream);
+    } else {
+        VectorP1 op{(const double2*)xy, tris, elem_k2n2, 0, 1, sigma, fast};
+        launch_rows<VectorP1, false>(p, op, nullptr, M_vals, (cudaStream_t)stream);
+    }
     WS_API_END
 }
 

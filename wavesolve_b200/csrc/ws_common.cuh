@@ -123,6 +123,9 @@ struct ws_pattern {
     int64_t Ne = 0;    // elements (as assembled, material-major, duplicates allowed)
     int64_t nnz = 0;
     int max_row_len = 0;
+    int max_block_slots = 0;   // largest number of entries in a block of 128 consecutive rows
+    static constexpr int NRANGE = 16;
+    int range_block_slots[NRANGE] = {0};   // the same maximum per sixteenth of the 128-row blocks
     ws::DevBuf<int32_t> rowptr;   // [N+1]
     ws::DevBuf<int32_t> colidx;   // [nnz]
     // row-incidence lists: for row r, entries incptr[r]..incptr[r+1] of inc[] hold

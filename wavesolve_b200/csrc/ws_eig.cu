@@ -537,9 +537,9 @@ struct EigWork {
     int nchunks;
 };
 
-static void dots(EigWork& W, const double* Zb, int nvec, const double* u, double* h, double* hacc) {
-    k_dots_partial<<<W.nchunks, 256, 0, W.st>>>(Zb, W.N, nvec, u, W.N, W.partial.get());
-    k_dots_reduce<<<nvec, 32, 0, W.st>>>(W.partial.get(), W.nchunks, nvec, h, hacc);
+static void dots(EigWork& W, cudaStream_t q, const double* Zb, int nvec, const double* u, double* h, double* hacc) {
+    k_dots_partial<<<W.nchunks, 256, 0, q>>>(Zb, W.N, nvec, u, W.N, W.partial.get());
+    k_dots_reduce<<<nvec, 32, 0, q>>>(W.partial.get(), W.nchunks, nvec, h, hacc);
     count_launch(2);
 }
 
@@ -598,40 +598,102 @@ int ws_eig_solve(const ws_pattern* p, ws_solver* s, const double* B_vals, double
     double* Z = kind == 0 ? W.Z.get() : V;
     const int T = 256;
     const int nb = ceil_div(N, T);
-    auto solve = [&](const double* b, double* x) {
-        int rc = ws_solver_solve(s, b, x, 1, device, stream);
+    // every enqueue helper takes the stream explicitly: the Arnoldi steps are recorded once into
+    // CUDA graphs (stream capture on a private stream) and replayed on the caller's stream, so an
+    // eigensolve costs ~10^2 host launches instead of ~7000 and does not depend on host latency.
+    auto solve = [&](cudaStream_t q, const double* b, double* x) {
+        int rc = ws_solver_solve(s, b, x, 1, device, (void*)q);
         if (rc) throw Error(rc, ws_last_error());
     };
-    auto vecT = [&](int mode, const double* in, double* out) {
-        int rc = ws_vector_T(p, edges, xy, Ntt, mode, in, out, device, stream);
+    auto vecT = [&](cudaStream_t q, int mode, const double* in, double* out) {
+        int rc = ws_vector_T(p, edges, xy, Ntt, mode, in, out, device, (void*)q);
         if (rc) throw Error(rc, ws_last_error());
     };
     // OP applied to basis vector j -> W.w
-    auto apply_op = [&](int j) {
+    auto apply_op = [&](cudaStream_t q, int j) {
         if (kind == 0) {
-            solve(Z + (size_t)j * N, W.w.get());                       // Z_j = B v_j is carried along
+            solve(q, Z + (size_t)j * N, W.w.get());                    // Z_j = B v_j is carried along
         } else {
-            spmv_launch(p, B_vals, V + (size_t)j * N, W.t1.get(), st);
-            vecT(1, W.t1.get(), W.t2.get());
-            solve(W.t2.get(), W.t3.get());
-            vecT(0, W.t3.get(), W.w.get());
+            spmv_launch(p, B_vals, V + (size_t)j * N, W.t1.get(), q);
+            vecT(q, 1, W.t1.get(), W.t2.get());
+            solve(q, W.t2.get(), W.t3.get());
+            vecT(q, 0, W.t3.get(), W.w.get());
         }
     };
     // normalise W.w in the inner product into basis slot j (H entry written to hslot)
-    auto normalize_into = [&](int j, double* hslot) {
+    auto normalize_into = [&](cudaStream_t q, int j, double* hslot) {
         const double* dual = W.w.get();
         if (kind == 0) {
-            spmv_launch(p, B_vals, W.w.get(), W.t1.get(), st);
+            spmv_launch(p, B_vals, W.w.get(), W.t1.get(), q);
             dual = W.t1.get();
         }
-        dots(W, dual, 1, W.w.get(), W.nrm.get(), nullptr);
-        k_normalize<<<nb, T, 0, st>>>(W.w.get(), kind == 0 ? W.t1.get() : nullptr, W.nrm.get(), hslot,
-                                     V + (size_t)j * N, kind == 0 ? Z + (size_t)j * N : nullptr, N);
+        dots(W, q, dual, 1, W.w.get(), W.nrm.get(), nullptr);
+        k_normalize<<<nb, T, 0, q>>>(W.w.get(), kind == 0 ? W.t1.get() : nullptr, W.nrm.get(), hslot,
+                                    V + (size_t)j * N, kind == 0 ? Z + (size_t)j * N : nullptr, N);
+        count_launch(1);
+    };
+    // one Arnoldi step: w = OP v_j, CGS2 against rows 0..j (coefficients with the dual basis,
+    // update with the primal one), normalise into slot j+1
+    auto arnoldi_step = [&](cudaStream_t q, int j) {
+        apply_op(q, j);
+        double* Hcol = W.Hd.get() + (size_t)j * (m + 1);
+        for (int pass = 0; pass < 2; ++pass) {
+            dots(W, q, Z, j + 1, W.w.get(), W.h.get(), Hcol);
+            k_update<<<nb, T, 0, q>>>(W.w.get(), V, N, j + 1, W.h.get(), N);
+            count_launch(1);
+        }
+        normalize_into(q, j + 1, Hcol + (j + 1));
+    };
+    struct GraphSet {
+        std::vector<cudaGraphExec_t> exec;
+        cudaStream_t cap = nullptr;
+        ~GraphSet() {
+            for (auto e : exec)
+                if (e) cudaGraphExecDestroy(e);
+            if (cap) cudaStreamDestroy(cap);
+        }
+    } graphs;
+    graphs.exec.assign(m, nullptr);
+    const char* nog = getenv("WS_NO_GRAPH");
+    const bool use_graphs = !(nog && atoi(nog));
+    if (use_graphs) WS_CUDA(cudaStreamCreateWithFlags(&graphs.cap, cudaStreamNonBlocking));
+    auto run_step = [&](int j) {
+        if (!use_graphs) {
+            arnoldi_step(st, j);
+            return;
+        }
+        if (!graphs.exec[j]) {
+            cudaGraph_t g = nullptr;
+            WS_CUDA(cudaStreamBeginCapture(graphs.cap, cudaStreamCaptureModeThreadLocal));
+            try {
+                arnoldi_step(graphs.cap, j);
+            } catch (...) {
+                cudaStreamEndCapture(graphs.cap, &g);
+                if (g) cudaGraphDestroy(g);
+                throw;
+            }
+            WS_CUDA(cudaStreamEndCapture(graphs.cap, &g));
+            cudaError_t e = cudaGraphInstantiate(&graphs.exec[j], g, 0);
+            cudaGraphDestroy(g);
+            if (e != cudaSuccess) throw Error(WS_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e));
+        }
+        WS_CUDA(cudaGraphLaunch(graphs.exec[j], st));
         count_launch(1);
     };
 
     // optional phase timing (WS_TRACE=1): synchronises after every phase, diagnostic only
-    const bool trace = getenv("WS_TRACE") != nullptr;
+    const char* trace_env = getenv("WS_TRACE");
+    const bool trace = trace_env != nullptr && atoi(trace_env) == 1;
+    const bool etrace = trace_env != nullptr && atoi(trace_env) == 2;
+    std::vector<cudaEvent_t> evs;
+    auto mark = [&]() {
+        if (!etrace) return;
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, st);
+        evs.push_back(e);
+    };
+    const double wall0 = std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
     double tr_op = 0, tr_orth = 0, tr_norm = 0, tr_host = 0, tr_rot = 0, tr_t0 = 0;
     auto tick = [&]() {
         if (!trace) return 0.0;
@@ -642,9 +704,11 @@ int ws_eig_solve(const ws_pattern* p, ws_solver* s, const double* B_vals, double
     // ---- start vector: random, pushed once through OP (stays in range(OP), as ARPACK does)
     k_random<<<nb, T, 0, st>>>(W.w.get(), N, seed ? seed : 0x5DEECE66Dull);
     count_launch(1);
-    normalize_into(0, nullptr);
-    apply_op(0);
-    normalize_into(0, nullptr);
+    normalize_into(st, 0, nullptr);
+    apply_op(st, 0);
+    normalize_into(st, 0, nullptr);
+    // every kernel of a step has now run once outside stream capture, except the update:
+    k_update<<<nb, T, 0, st>>>(W.w.get(), V, N, 0, W.h.get(), N);   // nvec = 0: no-op, loads the kernel
     WS_CUDA(cudaMemsetAsync(W.Hd.get(), 0, W.Hd.bytes(), st));
 
     std::vector<double> Hh((size_t)(m + 1) * m, 0.0);    // column-major (m+1) x m, as on the device
@@ -659,21 +723,11 @@ int ws_eig_solve(const ws_pattern* p, ws_solver* s, const double* B_vals, double
     while (!done) {
         for (int j = j0; j < m; ++j) {
             double ta = tick();
-            apply_op(j);
+            mark();
+            run_step(j);
+            mark();
             ++nops;
-            double tb = tick();
-            tr_op += tb - ta;
-            double* Hcol = W.Hd.get() + (size_t)j * (m + 1);
-            // CGS2 against rows 0..j : coefficients with the dual basis, update with the primal one
-            for (int pass = 0; pass < 2; ++pass) {
-                dots(W, Z, j + 1, W.w.get(), W.h.get(), Hcol);
-                k_update<<<nb, T, 0, st>>>(W.w.get(), V, N, j + 1, W.h.get(), N);
-                count_launch(1);
-            }
-            double tc = tick();
-            tr_orth += tc - tb;
-            normalize_into(j + 1, Hcol + (j + 1));
-            tr_norm += tick() - tc;
+            tr_op += tick() - ta;
         }
         double th0 = tick();
         WS_CUDA(cudaMemcpyAsync(Hh.data(), W.Hd.get(), Hh.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -841,7 +895,7 @@ int ws_eig_solve(const ws_pattern* p, ws_solver* s, const double* B_vals, double
     if (kind == 1) {
         // unit 2-norm rows (what ARPACK's dneupd returns)
         for (int i = 0; i < nev; ++i) {
-            dots(W, V_out + (size_t)i * N, 1, V_out + (size_t)i * N, W.nrm.get() + i, nullptr);
+            dots(W, st, V_out + (size_t)i * N, 1, V_out + (size_t)i * N, W.nrm.get() + i, nullptr);
         }
         k_scale_rows<<<nb, T, 0, st>>>(V_out, N, nev, W.nrm.get(), N);
         count_launch(1);
@@ -849,6 +903,20 @@ int ws_eig_solve(const ws_pattern* p, ws_solver* s, const double* B_vals, double
     WS_CUDA(cudaMemcpyAsync(w_out, wh.data(), nev * sizeof(double), cudaMemcpyHostToDevice, st));
     WS_CUDA(cudaStreamSynchronize(st));
     WS_CUDA(cudaGetLastError());
+    if (etrace) {
+        cudaStreamSynchronize(st);
+        const double wall1 = std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+        double op_ms = 0, mx = 0, mn = 1e30, span = 0;
+        for (size_t i = 0; i + 1 < evs.size(); i += 2) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, evs[i], evs[i + 1]);
+            op_ms += ms; mx = std::max<double>(mx, ms); mn = std::min<double>(mn, ms);
+        }
+        if (evs.size() >= 2) { float ms = 0; cudaEventElapsedTime(&ms, evs.front(), evs.back()); span = ms; }
+        fprintf(stderr, "[ws_eig etrace] wall %.1f ms, first-op-start..last-op-end %.1f ms, sum(op) %.1f ms over %zu ops (min %.3f max %.3f)\n",
+                (wall1 - wall0) * 1e3, span, op_ms, evs.size() / 2, mn, mx);
+        for (auto e : evs) cudaEventDestroy(e);
+    }
     if (trace)
         fprintf(stderr, "[ws_eig] kind=%d N=%lld ops=%lld restarts=%d total=%.1f ms: op=%.1f orth=%.1f norm=%.1f host=%.1f rotate=%.1f\n",
                 kind, (long long)N, (long long)nops, restarts, (tick() - tr_t0) * 1e3, tr_op * 1e3, tr_orth * 1e3, tr_norm * 1e3,

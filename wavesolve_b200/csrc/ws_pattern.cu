@@ -6,6 +6,7 @@
 //   waveguide.py:10-43     get_unique_edges  (O(E^2) python list scan)
 //   fe_solver.py:38-40,67-68   COO triplets -> scipy coo_tocsr + sum_duplicates
 //   fe_solver.py:170-176,212-213   lil_matrix accumulation -> tocsc (exact zeros dropped)
+#include <algorithm>
 #include <cub/cub.cuh>
 
 #include "ws_common.cuh"
@@ -78,6 +79,19 @@ __global__ void k_max_rowlen(const int32_t* __restrict__ rowptr, int64_t N, int*
     int len = (r < N) ? rowptr[r + 1] - rowptr[r] : 0;
     for (int o = 16; o; o >>= 1) len = max(len, __shfl_xor_sync(0xffffffffu, len, o));
     if ((threadIdx.x & 31) == 0 && len) atomicMax(out, len);
+}
+
+// out[0] = max entries of a `rows`-row block; out[1 + g] = the same over the blocks of group g
+// (blocks are split into `ngroups` contiguous groups of `per_group` blocks)
+__global__ void k_max_blockslots(const int32_t* __restrict__ rowptr, int64_t N, int rows, int per_group,
+                                 int* __restrict__ out) {
+    int64_t b = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    int64_t r0 = b * rows;
+    if (r0 >= N) return;
+    int64_t r1 = min(r0 + rows, N);
+    const int c = rowptr[r1] - rowptr[r0];
+    atomicMax(out, c);
+    atomicMax(out + 1 + (int)(b / per_group), c);
 }
 
 // pos[6*i+b] = position of column dofs[e*6+b] inside row r (r = row of incidence i)
@@ -296,8 +310,9 @@ int ws_pattern_create(const int32_t* dofs, int64_t Ne, int64_t N, ws_pattern** o
         k_row_bounds<<<ceil_div(N + 1, T), T, 0, st>>>(ik1.get(), n_inc, N, P->incptr.get());
         ik0.release();
         // --- unique (row, col) pairs
-        DevBuf<int32_t> d_counts(2, st);
-        WS_CUDA(cudaMemsetAsync(d_counts.get(), 0, 2 * sizeof(int32_t), st));
+        constexpr int NR = ws_pattern::NRANGE;
+        DevBuf<int32_t> d_counts(3 + NR, st);
+        WS_CUDA(cudaMemsetAsync(d_counts.get(), 0, (3 + NR) * sizeof(int32_t), st));
         int64_t nnz = 0;
         {
             DevBuf<uint64_t> pk0(n_pair, st), pk1(n_pair, st);
@@ -317,13 +332,19 @@ int ws_pattern_create(const int32_t* dofs, int64_t Ne, int64_t N, ws_pattern** o
             k_row_bounds<<<ceil_div(N + 1, T), T, 0, st>>>(pk0.get(), nnz, N, P->rowptr.get());
         }
         k_max_rowlen<<<ceil_div(N, T), T, 0, st>>>(P->rowptr.get(), N, d_counts.get() + 1);
+        const int nblocks128 = ceil_div(N, 128);
+        const int per_group = std::max(1, ceil_div(nblocks128, NR));
+        k_max_blockslots<<<ceil_div(nblocks128, T), T, 0, st>>>(P->rowptr.get(), N, 128, per_group, d_counts.get() + 2);
         P->pos.alloc(n_pair, st);
         k_positions<<<ceil_div(n_pair, T), T, 0, st>>>(ik1.get(), n_inc, dofs, P->rowptr.get(), P->colidx.get(), P->pos.get());
-        int32_t h_max = 0;
-        WS_CUDA(cudaMemcpyAsync(&h_max, d_counts.get() + 1, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        int32_t h_mx[2 + NR] = {0};
+        WS_CUDA(cudaMemcpyAsync(h_mx, d_counts.get() + 1, (2 + NR) * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
         WS_CUDA(cudaStreamSynchronize(st));
         WS_CUDA(cudaGetLastError());
+        const int32_t h_max = h_mx[0];
         P->max_row_len = h_max;
+        P->max_block_slots = h_mx[1];
+        for (int g2 = 0; g2 < NR; ++g2) P->range_block_slots[g2] = h_mx[2 + g2];
         count_launch(9 + 3);
         if (h_max > 65535) throw Error(WS_ERR_ARG, "a matrix row has more than 65535 entries");
     } catch (...) {

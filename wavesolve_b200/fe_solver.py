@@ -123,12 +123,15 @@ class ScalarProblem:
                 self.pattern = DevicePattern(self.dofs, self.N)
         return self.pattern
 
-    def assemble(self):
-        p = self.pattern
+    def assemble(self, fast=False):
+        """A, B values on the pattern.  fast=True: reciprocal arithmetic (<= 2 ulp off the
+        reference's), used inside the solve pipeline only."""
+        p = self.build_pattern()
         A = torch.empty(p.nnz, dtype=torch.float64, device=self.dev)
         B = torch.empty(p.nnz, dtype=torch.float64, device=self.dev)
         _lib.check(_lib.lib().ws_assemble_scalar_p2(p.handle, _dev.ptr(self.xy), _dev.ptr(self.dofs),
-                                                    _dev.ptr(self.k2n2), _dev.ptr(A), _dev.ptr(B), 0,
+                                                    _dev.ptr(self.k2n2), _dev.ptr(A), _dev.ptr(B),
+                                                    _lib.ASM_FAST if fast else 0,
                                                     self.dev.index, _dev.stream_ptr(self.dev)))
         return A, B
 
@@ -189,24 +192,28 @@ class VectorProblem:
             self.pattern = DevicePattern(self.dofs, self.N) if build_pattern else None
         self.h2d_bytes = xy.nbytes + tris.nbytes + dofs.nbytes + k2.nbytes + self.h_edges.nbytes
 
-    def assemble(self, transpose=False):
-        p = self.pattern
+    def assemble(self, transpose=False, fast=False):
+        p = self.build_pattern()
         A = torch.empty(p.nnz, dtype=torch.float64, device=self.dev)
         B = torch.empty(p.nnz, dtype=torch.float64, device=self.dev)
         _lib.check(_lib.lib().ws_assemble_vector_p1(p.handle, _dev.ptr(self.xy), _dev.ptr(self.tris),
                                                     _dev.ptr(self.k2n2), self.Ntt, _dev.ptr(A),
-                                                    _dev.ptr(B), 1 if transpose else 0,
+                                                    _dev.ptr(B),
+                                                    (_lib.ASM_TRANSPOSE if transpose else 0) | (_lib.ASM_FAST if fast else 0),
                                                     self.dev.index, _dev.stream_ptr(self.dev)))
         return A, B
 
-    def assemble_qd(self, sigma):
-        """Quasi-definite shift-invert matrix M' = T^T (A - sigma B) T on the pattern."""
-        p = self.pattern
+    def assemble_qd(self, sigma, with_B=False, fast=False):
+        """Quasi-definite shift-invert matrix M' = T^T (A - sigma B) T on the pattern (and B in the
+        same pass when with_B)."""
+        p = self.build_pattern()
         M = torch.empty(p.nnz, dtype=torch.float64, device=self.dev)
+        B = torch.empty(p.nnz, dtype=torch.float64, device=self.dev) if with_B else None
         _lib.check(_lib.lib().ws_assemble_vector_qd(p.handle, _dev.ptr(self.xy), _dev.ptr(self.tris),
                                                     _dev.ptr(self.k2n2), self.Ntt, float(sigma), _dev.ptr(M),
+                                                    _dev.ptr(B), _lib.ASM_FAST if fast else 0,
                                                     self.dev.index, _dev.stream_ptr(self.dev)))
-        return M
+        return (M, B) if with_B else M
 
     def apply_T(self, v, transpose=False):
         out = torch.empty_like(v)
@@ -366,7 +373,7 @@ def solve_waveguide(mesh, wl, IOR_dict, plot=False, ignore_warning=False, sparse
     with torch.cuda.device(prob.dev):
         fut = _sv.SymbolicFuture(prob.h_dofs, prob.h_xy, N, 0, leaf_elems or _sv.DEFAULT_LEAF_ELEMS)
         prob.build_pattern()
-        A, B = prob.assemble()
+        A, B = prob.assemble(fast=True)
         sym = fut.result()
         S = _sv.Solver(prob.pattern, sym)
         st = S.factor(A, B, est_eigval)
@@ -394,8 +401,7 @@ def solve_vector_resident(prob, sigma, Nmax, leaf_elems=None, symbolic=None):
         fut = _sv.SymbolicFuture(prob.h_dofs, prob.h_xy, prob.N, prob.Ntt,
                                  leaf_elems or _sv.DEFAULT_LEAF_ELEMS)
     prob.build_pattern()
-    A, B = prob.assemble()
-    Mq = prob.assemble_qd(sigma)
+    Mq, B = prob.assemble_qd(sigma, with_B=True, fast=True)
     sym = symbolic if fut is None else fut.result()
     S = _sv.Solver(prob.pattern, sym)
     try:
