@@ -10,6 +10,7 @@
  *                                   sum_duplicates) and fe_solver.py:170-176,212-213 (lil -> csc)
  *   ws_assemble_scalar_p2        <- fe_solver.py:47-55 + shape_funcs.py:192-246
  *   ws_assemble_mass_p2          <- fe_solver.py:71-99   construct_B_order2
+ *   ws_assemble_scalar_p1        <- fe_solver.py:103-129 construct_AB_order1 + shape_funcs.py:403-428
  *   ws_assemble_vector_p1        <- fe_solver.py:178-210 + shape_funcs.py:310-428
  *   ws_prune_zeros               <- the "exact zeros are not stored" behaviour of lil_matrix
  *                                   behind fe_solver.py:196-199, 212-213
@@ -96,6 +97,13 @@ int ws_assemble_scalar_p2(const ws_pattern* p, const double* xy, const int32_t* 
 /* mass matrix only, all elements (fe_solver.py:71-99) */
 int ws_assemble_mass_p2(const ws_pattern* p, const double* xy, const int32_t* dofs, double* B_vals,
                         int device, void* stream);
+
+/* scalar P1 (fe_solver.py:103-129, shape_funcs.py:403-428).  The pattern is built from six
+ * unknowns per element: pass dofs = (v0 v1 v2 v0 v1 v2) per linear triangle, to
+ * ws_pattern_create and here.  A_e = k2n2 * LNN - LdNdN, B_e = LNN.                          */
+int ws_assemble_scalar_p1(const ws_pattern* p, const double* xy, const int32_t* dofs,
+                          const double* elem_k2n2, double* A_vals, double* B_vals, int device,
+                          void* stream);
 
 /* ---- K4: vector assembly, Whitney edges + P1 nodes (fe_solver.py:178-210) -----------------
  * tris [Ne*3] vertex ids (element order = dofs order), Ntt = number of edge unknowns.

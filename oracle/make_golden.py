@@ -71,6 +71,26 @@ def scalar_case(fe, name, mesh, ior, Nmax=10, target_neff=None, store_v=True, wi
           "neff", (np.sqrt(out["w"]) / k)[:4] if Nmax else None, "count", out.get("count"))
 
 
+def scalar_p1_case(fe, name, mesh, ior, Nmax=6):
+    """order=1 scalar path: construct_AB_order1 (fe_solver.py:103-129, lil matrices) and
+    solve_waveguide(order=1) (fe_solver.py:292-348)."""
+    k = 2 * np.pi / WL
+    out = mesh_arrays(mesh)
+    out["ior"] = np.array([ior[l] for l in mesh.cell_sets.keys()])
+    out["wl"] = np.array(WL)
+    A, B = fe.construct_AB(mesh, ior, k, sparse=True, order=1)
+    assert A.format == "lil"
+    out.update(csx("A", A.tocsr()))
+    out.update(csx("B", B.tocsr()))
+    w, v, cnt = fe.solve_waveguide(mesh, WL, ior, sparse=True, Nmax=Nmax, order=1)
+    out["w"] = np.array(w)
+    out["v"] = np.ascontiguousarray(v)
+    out["count"] = np.array(cnt)
+    out["Nmax"] = np.array(Nmax)
+    np.savez_compressed(os.path.join(GOLD, name + ".npz"), **out)
+    print(name, "Ne", mesh.num_elements, "N", A.shape[0], "nnz", A.nnz, "neff", np.sqrt(out["w"]) / k, "count", cnt)
+
+
 def vector_case(fe, wg, name, mesh, ior, Nmax=6, target_neff=None, solve=True):
     k = 2 * np.pi / WL
     out = mesh_arrays(mesh)
@@ -102,6 +122,10 @@ def main():
     fe, sf, wg = refshim.load()
     os.makedirs(GOLD, exist_ok=True)
     ior = mg.FIBER_IOR
+    if "--p1-only" in sys.argv:          # added later; leaves the earlier fixtures untouched
+        scalar_p1_case(fe, "scalar_p1_sq8", mg.structured_square(8, order=1), ior, Nmax=4)
+        scalar_p1_case(fe, "scalar_p1_disc800", mg.fiber_disc(800, order=1, seed=6), ior, Nmax=6)
+        return
     # ---- scalar P2 ----
     scalar_case(fe, "scalar_sq8", mg.structured_square(8), ior, with_B=True)
     scalar_case(fe, "scalar_disc600", mg.fiber_disc(600, seed=1), ior)
@@ -132,6 +156,9 @@ def main():
                 target_neff=1.448)
     m = mg.structured_square(5, order=1, dtype=np.uint64)
     vector_case(fe, wg, "vec_sq5_uint64", m, ior, solve=False)
+    # ---- scalar P1 ----
+    scalar_p1_case(fe, "scalar_p1_sq8", mg.structured_square(8, order=1), ior, Nmax=4)
+    scalar_p1_case(fe, "scalar_p1_disc800", mg.fiber_disc(800, order=1, seed=6), ior, Nmax=6)
 
 
 if __name__ == "__main__":

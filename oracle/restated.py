@@ -279,6 +279,24 @@ def construct_AB_vec(mesh, IOR_dict, k):
     return A, B
 
 
+def construct_AB_order1(mesh, IOR_dict, k):
+    """Scalar P1 assembly, sparse=True (fe_solver.py:103-129): per element
+    A[ix] += (k^2 n^2) LNN - LdNdN, B[ix] += LNN into N x N lil matrices, N = len(points)
+    (fe_solver.py:107); element matrices from shape_funcs.py:403-428.  Returned as canonical
+    CSC without stored zeros (what lil -> tocsr/tocsc holds)."""
+    conn, mat, labels = material_major(mesh)
+    conn = conn.astype(np.int64)
+    N = len(mesh.points)
+    _, _, _, NNl, G = vec_element_blocks(mesh.points[conn], conn)
+    k2 = np.empty(len(conn))
+    for mi, label in enumerate(labels):
+        k2[mat == mi] = k ** 2 * IOR_dict[label] ** 2
+    Ae = k2[:, None, None] * NNl - G
+    r = np.repeat(conn, 3, 1).ravel()
+    c = np.tile(conn, (1, 3)).ravel()
+    return _sum_in_order(N, N, r, c, Ae.ravel()), _sum_in_order(N, N, r, c, NNl.ravel())
+
+
 # --------------------------------------------------------------------------------------
 # solves
 # --------------------------------------------------------------------------------------
@@ -314,13 +332,15 @@ def count_modes_vec(w, k, IOR_dict, target_neff):
     return cnt
 
 
-def solve_waveguide(mesh, wl, IOR_dict, Nmax=10, target_neff=None, AB=None):
-    """Scalar solve, sparse=True, order=2 (fe_solver.py:292-348): sigma = (k n_max)^2 or
+def solve_waveguide(mesh, wl, IOR_dict, Nmax=10, target_neff=None, AB=None, order=2):
+    """Scalar solve, sparse=True (fe_solver.py:292-348): sigma = (k n_max)^2 or
     (k target)^2, eigsh(A, M=B, k=Nmax, which='SA', sigma=sigma), results reversed to
     descending order."""
     k = 2 * np.pi / wl
     sigma = np.power(k * (max(IOR_dict.values()) if target_neff is None else target_neff), 2)
-    A, B = construct_AB_order2(mesh, IOR_dict, k) if AB is None else AB
+    if AB is None:
+        AB = construct_AB_order2(mesh, IOR_dict, k) if order == 2 else construct_AB_order1(mesh, IOR_dict, k)
+    A, B = AB
     w, v = spla.eigsh(A.tocsr(), M=B.tocsr(), k=Nmax, which="SA", sigma=sigma)
     return w[::-1], v.T[::-1], count_modes_scalar(w[::-1], k, IOR_dict)
 

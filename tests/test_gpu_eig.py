@@ -161,3 +161,25 @@ def test_full_size_vector_1M_properties(ws):
     assert ne[0] < 1.4528 and ne[5] > 1.444
     ntt = len(mesh.cells[0].data)
     assert info["factor"]["neg_pivots"] == ntt and info["factor"]["pos_pivots"] == len(mesh.points)
+
+
+@pytest.mark.parametrize("name", ["scalar_p1_sq8", "scalar_p1_disc800"])
+def test_scalar_p1_assembly_and_solve_vs_reference_golden(ws, name):
+    """order=1 scalar path (fe_solver.py:103-129, solve_waveguide(order=1))."""
+    import scipy.sparse as sp
+    mesh, ior, z = util.load_golden(name)
+    k = 2 * np.pi / float(z["wl"])
+    A, B = ws.construct_AB(mesh, ior, k, sparse=True, order=1)
+    assert sp.issparse(A) and A.format == "lil" and B.format == "lil"
+    for M, pre in ((A, "A"), (B, "B")):
+        G = util.golden_matrix(z, pre)
+        util.assert_same_pattern(M.tocsr(), G)     # exact zeros pruned like lil does
+        util.assert_values_close(M.tocsr(), G)
+    Ad, Bd = ws.construct_AB(mesh, ior, k, sparse=False, order=1)
+    assert Ad.shape == (len(mesh.points),) * 2 and np.allclose(Bd, util.golden_matrix(z, "B").toarray(), rtol=1e-12, atol=1e-18)
+    w, v, cnt = ws.solve_waveguide(mesh, float(z["wl"]), ior, Nmax=int(z["Nmax"]), order=1)
+    assert cnt == int(z["count"]) and v.shape == z["v"].shape
+    assert np.allclose(util.neff(w), util.neff(z["w"]), rtol=NEFF_TOL, atol=0)
+    check_fields(w, v, z["w"], z["v"], util.golden_matrix(z, "B"))
+    with pytest.raises(AssertionError):
+        ws.solve_waveguide(mesh, float(z["wl"]), ior, order=2)

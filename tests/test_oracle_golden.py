@@ -77,3 +77,20 @@ def test_vector_solve_matrix_free_equals_transform(name):
     assert np.allclose(a, b, rtol=1e-10, atol=0)
     assert v.shape == z["v"].shape
     assert np.allclose(np.linalg.norm(v, axis=1), 1.0, atol=1e-12)   # unit 2-norm rows
+
+
+@pytest.mark.parametrize("name", ["scalar_p1_sq8", "scalar_p1_disc800"])
+def test_scalar_p1_assembly_and_solve(name):
+    """order=1 scalar path (fe_solver.py:103-129 + solve_waveguide(order=1))."""
+    mesh, ior, z = util.load_golden(name)
+    k = 2 * np.pi / float(z["wl"])
+    A, B = R.construct_AB_order1(mesh, ior, k)
+    for M, pre in ((A, "A"), (B, "B")):
+        G = util.golden_matrix(z, pre)              # stored as lil.tocsr()
+        M = M.tocsr()
+        util.assert_same_pattern(M, G)
+        util.assert_values_close(M, G, tol=1e-14)      # l**2 (libm pow) vs l*l, last bit
+        assert (M.data != G.data).mean() < 0.02
+    w, v, cnt = R.solve_waveguide(mesh, float(z["wl"]), ior, Nmax=int(z["Nmax"]), order=1)
+    assert cnt == int(z["count"])
+    assert np.allclose(util.neff(w), util.neff(z["w"]), rtol=1e-10, atol=0)

@@ -31,6 +31,7 @@ _SIGNATURES = {
     "ws_pattern_arrays": (c_int, [c_vp, C.POINTER(c_vp), C.POINTER(c_vp)]),
     "ws_pattern_destroy": (c_int, [c_vp]),
     "ws_assemble_scalar_p2": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_vp]),
+    "ws_assemble_scalar_p1": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_vp]),
     "ws_assemble_mass_p2": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_vp]),
     "ws_assemble_vector_p1": (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_int, c_int, c_vp]),
     "ws_prune_zeros": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, C.POINTER(c_i64), c_int, c_vp]),

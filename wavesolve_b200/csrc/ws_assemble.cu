@@ -143,6 +143,55 @@ struct ScalarP2 {
     }
 };
 
+// ---- scalar P1 (fe_solver.py:103-129, shape_funcs.py:403-428) ------------------------------
+// The pattern machinery works on six unknowns per element; a linear triangle is presented as
+// (v0 v1 v2 v0 v1 v2): local rows 3..5 are aliases that contribute exact zeros, local rows 0..2
+// carry LNN / LdNdN.  (order=1 scalar is not in any benchmark configuration.)
+struct ScalarP1 {
+    const double2* xy;
+    const int32_t* dofs;
+    const double* k2n2;
+
+    __device__ __forceinline__ RawTri load(uint32_t e) const {
+        const int32_t* d = dofs + (int64_t)e * 6;
+        RawTri r;
+        r.t0 = d[0]; r.t1 = d[1]; r.t2 = d[2];
+        r.P0 = xy[r.t0]; r.P1 = xy[r.t1]; r.P2 = xy[r.t2];
+        r.c = k2n2[e];
+        return r;
+    }
+
+    __device__ __forceinline__ void row(const RawTri& in, int a, double (&Av)[6], double (&Bv)[6], int (&cb)[6]) const {
+#pragma unroll
+        for (int j = 0; j < 6; ++j) { cb[j] = j; Av[j] = 0.0; Bv[j] = 0.0; }
+        if (a >= 3) return;
+        const double2 P0 = in.P0, P1 = in.P1, P2 = in.P2;
+        const double x21 = P1.x - P0.x, y21 = P1.y - P0.y;          // shape_funcs.py:311-314
+        const double x31 = P2.x - P0.x, y31 = P2.y - P0.y;
+        const double J = x21 * y31 - x31 * y21;                      // :323
+        const double l12 = sqrt(x21 * x21 + y21 * y21), l31 = sqrt(x31 * x31 + y31 * y31);   // :320-322 (sign squares away)
+        const double sq12 = l12 * l12, sq31 = l31 * l31;
+        const double xx = x21 * x31, yy = y21 * y31;
+        const double nG00 = sq12 + sq31 - 2 * xx - 2 * yy;          // :421
+        const double nG11 = sq31, nG22 = sq12;                      // :422-423
+        const double nG01 = -sq31 + xx + yy;                        // :424
+        const double nG12 = -xx - yy;                               // :425
+        const double nG02 = -sq12 + xx + yy;                        // :426
+        const bool i0 = a == 0, i1 = a == 1;
+        const double g0 = i0 ? nG00 : (i1 ? nG01 : nG02);
+        const double g1 = i0 ? nG01 : (i1 ? nG11 : nG12);
+        const double g2 = i0 ? nG02 : (i1 ? nG12 : nG22);
+        const double J2 = 2 * J;
+        const double G0 = g0 / J2, G1 = g1 / J2, G2 = g2 / J2;
+        const double Nd = J / 12, No = J / 24;                      // :410-411
+        const double N0 = i0 ? Nd : No, N1 = i1 ? Nd : No, N2 = (a == 2) ? Nd : No;
+        Av[0] = __dsub_rn(__dmul_rn(in.c, N0), G0);                 // fe_solver.py:127
+        Av[1] = __dsub_rn(__dmul_rn(in.c, N1), G1);
+        Av[2] = __dsub_rn(__dmul_rn(in.c, N2), G2);
+        Bv[0] = N0; Bv[1] = N1; Bv[2] = N2;                         // fe_solver.py:128
+    }
+};
+
 // ---- vector: Whitney edge elements + P1 nodes ---------------------------------------------
 // mode 0: Av = row of A, Bv = row of B (reference semantics, fe_solver.py:196-199)
 // mode 1: Bv = row of the quasi-definite M' = T^T (A - sigma B) T
@@ -412,6 +461,19 @@ int ws_assemble_scalar_p2(const ws_pattern* p, const double* xy, const int32_t* 
     DeviceGuard g(device);
     ScalarP2 op{(const double2*)xy, dofs, elem_k2n2, (flags & WS_ASM_FAST) ? 1 : 0};
     launch_rows<ScalarP2, true>(p, op, A_vals, B_vals, (cudaStream_t)stream);
+    WS_API_END
+}
+
+int ws_assemble_scalar_p1(const ws_pattern* p, const double* xy, const int32_t* dofs,
+                          const double* elem_k2n2, double* A_vals, double* B_vals, int device,
+                          void* stream) {
+    WS_API_BEGIN
+    WS_REQUIRE(p, "pattern == NULL");
+    if (p->nnz == 0) return WS_OK;
+    WS_REQUIRE(xy && dofs && elem_k2n2 && A_vals && B_vals, "null pointer");
+    DeviceGuard g(device);
+    ScalarP1 op{(const double2*)xy, dofs, elem_k2n2};
+    launch_rows<ScalarP1, true>(p, op, A_vals, B_vals, (cudaStream_t)stream);
     WS_API_END
 }
 

@@ -36,6 +36,17 @@ def _material_major(mesh, IOR_dict, k, data=None):
     return data[:0], np.zeros(0)
 
 
+def _k2n2_host(mesh, IOR_dict, k):
+    """k^2 n^2 per element in material-major order (fe_solver.py:51 / :181) -- the only input
+    that changes between the wavelengths / index sets of a sweep on one mesh."""
+    out = []
+    for material in mesh.cell_sets.keys():
+        idx = mesh.cell_sets[material][1]
+        n = len(idx) if idx is not None else len(mesh.cells[1].data)
+        out.append(np.full(n, k ** 2 * IOR_dict[material] ** 2, dtype=np.float64))
+    return np.concatenate(out) if out else np.zeros(0)
+
+
 def _as_i32(a, what):
     a = np.asarray(a)
     if a.size and (int(a.max()) >= 2 ** 31 or int(a.min()) < 0):
@@ -98,16 +109,22 @@ class DevicePattern:
 class ScalarProblem:
     """Device-resident scalar P2 problem: mesh arrays, pattern, A and B values."""
 
-    def __init__(self, mesh, IOR_dict, k, device=None, all_cells_mass_only=False, build_pattern=True):
+    def __init__(self, mesh, IOR_dict, k, device=None, all_cells_mass_only=False, build_pattern=True, order=2):
         self.dev = dev = _dev.require_cuda(device)
+        self.order = order
         if all_cells_mass_only:
             conn = np.asarray(mesh.cells[1].data)
             k2 = np.zeros(len(conn))
         else:
             conn, k2 = _material_major(mesh, IOR_dict, k)
         conn = _as_i32(conn, "node ids")
-        # csr_matrix((data,(row,col))) infers the shape from the largest index (fe_solver.py:67)
-        self.N = int(conn.max()) + 1 if conn.size else 0
+        if order == 1:
+            # linear triangles ride the six-unknown pattern machinery as (v0 v1 v2 v0 v1 v2)
+            conn = np.ascontiguousarray(np.hstack([conn[:, :3], conn[:, :3]]))
+            self.N = len(mesh.points)                             # fe_solver.py:107
+        else:
+            # csr_matrix((data,(row,col))) infers the shape from the largest index (fe_solver.py:67)
+            self.N = int(conn.max()) + 1 if conn.size else 0
         xy = np.ascontiguousarray(np.asarray(mesh.points, dtype=np.float64)[:, :2])
         self.h_dofs, self.h_xy, self.first_class_start = conn, xy, 0
         with torch.cuda.device(dev):
@@ -123,12 +140,25 @@ class ScalarProblem:
                 self.pattern = DevicePattern(self.dofs, self.N)
         return self.pattern
 
+    def set_materials(self, mesh, IOR_dict, k):
+        """New wavelength / index set on the same mesh (K11): only k^2 n^2 per element changes;
+        pattern, incidence lists and symbolic analysis are kept."""
+        k2 = _k2n2_host(mesh, IOR_dict, k)
+        assert k2.shape[0] == self.k2n2.shape[0], "mesh does not match this problem"
+        with torch.cuda.device(self.dev):
+            self.k2n2.copy_(torch.from_numpy(k2), non_blocking=False)
+
     def assemble(self, fast=False):
         """A, B values on the pattern.  fast=True: reciprocal arithmetic (<= 2 ulp off the
         reference's), used inside the solve pipeline only."""
         p = self.build_pattern()
         A = torch.empty(p.nnz, dtype=torch.float64, device=self.dev)
         B = torch.empty(p.nnz, dtype=torch.float64, device=self.dev)
+        if self.order == 1:
+            _lib.check(_lib.lib().ws_assemble_scalar_p1(p.handle, _dev.ptr(self.xy), _dev.ptr(self.dofs),
+                                                        _dev.ptr(self.k2n2), _dev.ptr(A), _dev.ptr(B),
+                                                        self.dev.index, _dev.stream_ptr(self.dev)))
+            return A, B
         _lib.check(_lib.lib().ws_assemble_scalar_p2(p.handle, _dev.ptr(self.xy), _dev.ptr(self.dofs),
                                                     _dev.ptr(self.k2n2), _dev.ptr(A), _dev.ptr(B),
                                                     _lib.ASM_FAST if fast else 0,
@@ -166,6 +196,8 @@ class VectorProblem:
             with torch.cuda.device(self.dev):
                 self.pattern = DevicePattern(self.dofs, self.N)
         return self.pattern
+
+    set_materials = ScalarProblem.set_materials
 
     def __init__(self, mesh, IOR_dict, k, device=None, build_pattern=True):
         self.dev = dev = _dev.require_cuda(device)
@@ -269,6 +301,19 @@ def construct_B_order2(mesh, sparse=False, device=None):
 construct_B = construct_B_order2                                   # fe_solver.py:101
 
 
+def construct_AB_order1(mesh, IOR_dict, k, sparse=False, device=None):
+    """fe_solver.py:103-129: linear-triangle scalar assembly.  ``sparse=True`` returns two
+    lil matrices of shape (len(points),)*2 (exact zeros not stored), ``sparse=False`` dense arrays."""
+    prob = ScalarProblem(mesh, IOR_dict, k, device, order=1)
+    with torch.cuda.device(prob.dev):
+        A, B = prob.assemble()
+        Am = _to_scipy(sp.csr_matrix, prob.N, *prob.pattern.prune(A))
+        Bm = _to_scipy(sp.csr_matrix, prob.N, *prob.pattern.prune(B))
+    if not sparse:
+        return Am.toarray(), Bm.toarray()
+    return Am.tolil(), Bm.tolil()
+
+
 def construct_AB(mesh, IOR_dict, k, sparse=False, order=2, device=None):
     """fe_solver.py:131-146."""
     if order == 2:
@@ -276,7 +321,7 @@ def construct_AB(mesh, IOR_dict, k, sparse=False, order=2, device=None):
         return construct_AB_order2(mesh, IOR_dict, k, sparse, device=device)
     elif order == 1:
         assert mesh.cells[1].data.shape[1] == 3, "must use order 1 mesh for order 1 solver"
-        raise NotImplementedError("order=1 scalar assembly (fe_solver.py:103-129) is not on the accelerated path yet")
+        return construct_AB_order1(mesh, IOR_dict, k, sparse, device=device)
     else:
         raise NotImplementedError
 
@@ -313,9 +358,16 @@ last_info = {}      # diagnostics of the most recent solve_waveguide / solve_wav
 
 
 def _eig_device(pattern, solver, B_vals, sigma, kind, nev, N, dev, ncv=0, tol=0.0, maxit=0, seed=0,
-                edges=None, xy=None, Ntt=0):
-    w = torch.empty(nev, dtype=torch.float64, device=dev)
-    V = torch.empty((nev, N), dtype=torch.float64, device=dev)
+                edges=None, xy=None, Ntt=0, out=None):
+    """``out=(w, V)``: caller-provided device tensors (nev,) / (nev, N) -- in a sweep these are
+    views of the rank's NCCL send buffer, so the Ritz-vector kernel (K10) writes the gather
+    payload directly (K12)."""
+    if out is None:
+        w = torch.empty(nev, dtype=torch.float64, device=dev)
+        V = torch.empty((nev, N), dtype=torch.float64, device=dev)
+    else:
+        w, V = out
+        assert w.is_contiguous() and V.is_contiguous() and w.numel() == nev and V.numel() == nev * N
     info = np.zeros(5, dtype=np.int64)
     resid = np.zeros(nev, dtype=np.float64)
     rc = _lib.lib().ws_eig_solve(pattern.handle, solver.handle, _dev.ptr(B_vals), float(sigma), int(kind),
@@ -353,7 +405,6 @@ def solve_waveguide(mesh, wl, IOR_dict, plot=False, ignore_warning=False, sparse
     runs on the host at fe_solver.py:328) with scipy's defaults ncv = max(2 Nmax + 1, 20), tol = eps.
     ``sparse=False`` (LAPACK eigh on dense matrices in the reference, which cannot even assemble
     them for order 2) is served by the same path with the shift at the top of the spectrum."""
-    from . import solver as _sv
     k = 2 * np.pi / wl
     if target_neff is None or not sparse:
         est_eigval = np.power(k * max(IOR_dict.values()), 2)
@@ -363,25 +414,16 @@ def solve_waveguide(mesh, wl, IOR_dict, plot=False, ignore_warning=False, sparse
         assert mesh.cells[1].data.shape[1] == 6, "must use order 2 mesh for order 2 solver."
     elif order == 1:
         assert mesh.cells[1].data.shape[1] == 3, "must use order 1 mesh for order 1 solver"
-        raise NotImplementedError("order=1 scalar solve is not on the accelerated path yet")
     else:
         raise NotImplementedError
-    prob = ScalarProblem(mesh, IOR_dict, k, device, build_pattern=False)
+    prob = ScalarProblem(mesh, IOR_dict, k, device, build_pattern=False, order=order)
     N = prob.N
     if N > 2000 and not ignore_warning and not sparse:
         raise Exception("A and B matrices are larger than 2000 x 2000 - this may make your system unstable. consider setting sparse=True")
     with torch.cuda.device(prob.dev):
-        fut = _sv.SymbolicFuture(prob.h_dofs, prob.h_xy, N, 0, leaf_elems or _sv.DEFAULT_LEAF_ELEMS)
-        prob.build_pattern()
-        A, B = prob.assemble(fast=True)
-        sym = fut.result()
-        S = _sv.Solver(prob.pattern, sym)
-        st = S.factor(A, B, est_eigval)
-        wd, Vd, info = _eig_device(prob.pattern, S, B, est_eigval, 0, Nmax, N, prob.dev)
+        wd, Vd, info = solve_scalar_resident(prob, est_eigval, Nmax, leaf_elems)
         w = _dev.d2h(wd)
         v = _dev.d2h(Vd)
-        S.close()
-    info.update(factor=st, N=N, nnz=prob.pattern.nnz, sigma=float(est_eigval))
     last_info.clear()
     last_info.update(info)
     mode_count = _count_modes(w, k, IOR_dict)
@@ -390,26 +432,52 @@ def solve_waveguide(mesh, wl, IOR_dict, plot=False, ignore_warning=False, sparse
     return w, v, mode_count
 
 
-def solve_vector_resident(prob, sigma, Nmax, leaf_elems=None, symbolic=None):
+def solve_vector_resident(prob, sigma, Nmax, leaf_elems=None, symbolic=None, solver=None, out=None):
     """Device part of the vector solve on a resident VectorProblem: assembly of B and of the
     quasi-definite M', symbolic analysis (host), factorisation, Krylov iteration.  Returns
-    device tensors (w, V) and diagnostics."""
+    device tensors (w, V) and diagnostics.  ``solver``: a Solver already bound to this pattern
+    (sweeps reuse the task plan and the front storage across wavelengths)."""
     from . import solver as _sv
     fut = None
-    if symbolic is None:
+    if symbolic is None and solver is None:
         # host analysis in a worker thread, overlapped with the pattern build and the assembly
         fut = _sv.SymbolicFuture(prob.h_dofs, prob.h_xy, prob.N, prob.Ntt,
                                  leaf_elems or _sv.DEFAULT_LEAF_ELEMS)
     prob.build_pattern()
     Mq, B = prob.assemble_qd(sigma, with_B=True, fast=True)
-    sym = symbolic if fut is None else fut.result()
-    S = _sv.Solver(prob.pattern, sym)
+    if solver is not None:
+        S = solver
+    else:
+        S = _sv.Solver(prob.pattern, symbolic if fut is None else fut.result())
     try:
         st = S.factor(Mq)
         wd, Vd, info = _eig_device(prob.pattern, S, B, sigma, 1, Nmax, prob.N, prob.dev,
-                                   edges=prob.edges, xy=prob.xy, Ntt=prob.Ntt)
+                                   edges=prob.edges, xy=prob.xy, Ntt=prob.Ntt, out=out)
     finally:
-        S.close()
+        if solver is None:
+            S.close()
+    info.update(factor=st, N=prob.N, nnz=prob.pattern.nnz, sigma=float(sigma))
+    return wd, Vd, info
+
+
+def solve_scalar_resident(prob, sigma, Nmax, leaf_elems=None, symbolic=None, solver=None, out=None):
+    """Device part of the scalar solve on a resident ScalarProblem (see solve_vector_resident)."""
+    from . import solver as _sv
+    fut = None
+    if symbolic is None and solver is None:
+        fut = _sv.SymbolicFuture(prob.h_dofs, prob.h_xy, prob.N, 0, leaf_elems or _sv.DEFAULT_LEAF_ELEMS)
+    prob.build_pattern()
+    A, B = prob.assemble(fast=True)
+    if solver is not None:
+        S = solver
+    else:
+        S = _sv.Solver(prob.pattern, symbolic if fut is None else fut.result())
+    try:
+        st = S.factor(A, B, sigma)
+        wd, Vd, info = _eig_device(prob.pattern, S, B, sigma, 0, Nmax, prob.N, prob.dev, out=out)
+    finally:
+        if solver is None:
+            S.close()
     info.update(factor=st, N=prob.N, nnz=prob.pattern.nnz, sigma=float(sigma))
     return wd, Vd, info
 

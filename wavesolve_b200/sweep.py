@@ -1,0 +1,261 @@
+"""Parameter sweeps (wavelengths x z-slices x index sets): one eigenproblem per GPU at a time,
+NCCL only to gather the eigenpairs at the end.
+
+The reference runs sweeps as a serial notebook loop that re-meshes per z-slice, re-assembles
+per wavelength and pickles per radius (lantern-demo.ipynb cell 4).  Here a sweep is a list of
+independent ``SweepProblem``s:
+
+* ``partition``      cost-sorted, mesh-grouped longest-first assignment of problems to ranks
+                     (pure host logic; identical on every rank, no communication);
+* ``solve_sweep``    each rank keeps one resident context per mesh (pattern, incidence lists,
+                     symbolic analysis, solver task plan and front storage) and for every
+                     wavelength only refreshes k^2 n^2, re-assembles the values, refactors and
+                     iterates (K11); the Ritz vectors are written by the last kernel of the
+                     eigensolver directly into the rank's send buffer;
+* ``gather_eigenpairs``  one collective over ``torch.distributed`` (NCCL on GPUs; the same code
+                     runs on gloo/CPU tensors in the tests): metadata by all_gather_object,
+                     payload by one padded all_gather.
+
+A single mesh is never sharded across GPUs.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+
+@dataclass
+class SweepProblem:
+    mesh_id: int                 # index into the list of meshes handed to solve_sweep
+    wl: float
+    IOR_dict: Dict[str, float]
+    target_neff: Optional[float] = None
+    tag: object = None           # free-form label carried to the result (e.g. (radius, wl))
+
+
+@dataclass
+class SweepResult:
+    index: int                   # position in the problem list
+    w: np.ndarray                # (Nmax,) eigenvalues, descending
+    v: Optional[np.ndarray]      # (Nmax, N) eigenvectors as rows (None when gathered without vectors)
+    mode_count: int
+    rank: int
+    info: dict = field(default_factory=dict)
+
+
+def estimate_cost(n_unknowns: int) -> float:
+    """Relative cost of one eigensolve: 2-D nested dissection factorisation ~ N^1.5."""
+    return float(n_unknowns) ** 1.5
+
+
+def partition(mesh_ids: Sequence[int], costs: Sequence[float], world: int) -> List[List[int]]:
+    """Assign problem indices to ``world`` ranks.
+
+    Problems of one mesh form a group (they share pattern / symbolic analysis / plan).  Groups
+    are placed longest-first on the least-loaded rank; a group larger than the ideal share is
+    split into contiguous chunks first so that a sweep over few meshes still uses every GPU.
+    Deterministic (ties broken by index), so every rank computes the same table."""
+    assert world >= 1 and len(mesh_ids) == len(costs)
+    n = len(mesh_ids)
+    total = float(sum(costs))
+    ideal = total / world if world else total
+    groups: Dict[int, List[int]] = {}
+    for i, m in enumerate(mesh_ids):
+        groups.setdefault(int(m), []).append(i)
+    chunks: List[List[int]] = []
+    for m in sorted(groups):
+        idx = groups[m]
+        gcost = sum(costs[i] for i in idx)
+        nsplit = 1
+        if ideal > 0 and gcost > ideal and len(idx) > 1:
+            nsplit = min(len(idx), int(np.ceil(gcost / ideal)))
+        # contiguous, near-equal chunks
+        bounds = [round(j * len(idx) / nsplit) for j in range(nsplit + 1)]
+        for a, b in zip(bounds[:-1], bounds[1:]):
+            if b > a:
+                chunks.append(idx[a:b])
+    chunks.sort(key=lambda c: (-sum(costs[i] for i in c), c[0]))
+    load = [0.0] * world
+    out: List[List[int]] = [[] for _ in range(world)]
+    for c in chunks:
+        r = min(range(world), key=lambda j: (load[j], j))
+        out[r].extend(c)
+        load[r] += sum(costs[i] for i in c)
+    for r in range(world):
+        out[r].sort(key=lambda i: (mesh_ids[i], i))      # keep a mesh's wavelengths adjacent
+    assert sorted(i for r in out for i in r) == list(range(n))
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# gather (K12)
+# ---------------------------------------------------------------------------------------------
+def _dist():
+    import torch.distributed as dist
+    return dist
+
+
+def gather_eigenpairs(local: Dict[int, tuple], n_problems: int, group=None, with_vectors=True,
+                      dst: Optional[int] = None, packed: Optional[torch.Tensor] = None):
+    """Collect per-problem results from all ranks.
+
+    ``local``: {problem index: (w tensor (k,), V tensor (k, N), mode_count int)} -- tensors on the
+    rank's device (CUDA for NCCL, CPU for gloo).  Returns a list of ``n_problems`` entries
+    ``(w ndarray, v ndarray | None, mode_count, owner_rank)`` on every rank (``dst=None``) or on
+    rank ``dst`` only (other ranks get None).  Without an initialised process group this is the
+    single-rank identity.  ``packed``: the flat buffer [w_i | V_i ...] (in ``local``'s insertion order) the tensors
+    of ``local`` are views of; when it is at least as long as the largest rank payload it is sent
+    as is (no staging copy)."""
+    dist = _dist()
+    multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+    rank = dist.get_rank(group) if multi else 0
+    world = dist.get_world_size(group) if multi else 1
+    keys = list(local)            # insertion order = packing order
+    meta = [(i, int(local[i][0].numel()), int(local[i][1].shape[-1]) if with_vectors else 0, int(local[i][2]))
+            for i in keys]
+    if multi:
+        metas = [None] * world
+        dist.all_gather_object(metas, meta, group=group)
+    else:
+        metas = [meta]
+    sizes = [sum(k * (1 + n) for (_, k, n, _) in m) for m in metas]
+    pad = max(sizes) if sizes else 0
+    ref = local[keys[0]][0] if keys else torch.zeros(0, dtype=torch.float64)
+    dev = ref.device
+    if packed is not None and with_vectors and packed.numel() >= max(pad, 1) and packed.is_contiguous():
+        send = packed[:max(pad, 1)]
+    else:
+        send = torch.zeros(max(pad, 1), dtype=torch.float64, device=dev)
+        off = 0
+        for i in keys:
+            w, V, _ = local[i]
+            k = w.numel()
+            send[off:off + k].copy_(w.reshape(-1))
+            off += k
+            if with_vectors:
+                send[off:off + V.numel()].copy_(V.reshape(-1))
+                off += V.numel()
+    if multi:
+        recv = [torch.empty_like(send) for _ in range(world)]
+        dist.all_gather(recv, send, group=group)
+    else:
+        recv = [send]
+    if dst is not None and rank != dst:
+        return None
+    out: List[Optional[tuple]] = [None] * n_problems
+    for r, m in enumerate(metas):
+        buf = recv[r].cpu().numpy()
+        off = 0
+        for (i, k, n, cnt) in m:
+            w = buf[off:off + k].copy()
+            off += k
+            v = None
+            if with_vectors:
+                v = buf[off:off + k * n].reshape(k, n).copy()
+                off += k * n
+            out[i] = (w, v, cnt, r)
+    missing = [i for i, o in enumerate(out) if o is None]
+    if missing:
+        raise RuntimeError("sweep gather: no rank reported problems %s" % missing[:8])
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# driver
+# ---------------------------------------------------------------------------------------------
+class _MeshContext:
+    """Everything that depends on the mesh only, resident on this rank's GPU."""
+
+    def __init__(self, mesh, kind, IOR_dict, k, device, leaf_elems):
+        from . import fe_solver as fs, solver as sv
+        self.kind = kind
+        self.mesh = mesh
+        if kind == "vector":
+            self.prob = fs.VectorProblem(mesh, IOR_dict, k, device, build_pattern=False)
+            fcs = self.prob.Ntt
+        else:
+            self.prob = fs.ScalarProblem(mesh, IOR_dict, k, device, build_pattern=False)
+            fcs = 0
+        fut = sv.SymbolicFuture(self.prob.h_dofs, self.prob.h_xy, self.prob.N, fcs,
+                                leaf_elems or sv.DEFAULT_LEAF_ELEMS)
+        self.prob.build_pattern()
+        self.symbolic = fut.result()
+        self.solver = sv.Solver(self.prob.pattern, self.symbolic)
+
+    def close(self):
+        self.solver.close()
+        self.prob.pattern.close()
+        self.symbolic.close()
+
+
+def solve_sweep(meshes: Sequence, problems: Sequence[SweepProblem], Nmax: int = 10, kind: str = "vector",
+                group=None, device=None, leaf_elems=None, with_vectors: bool = True, gather: bool = True,
+                dst: Optional[int] = None):
+    """Solve every problem of the sweep, this rank taking its share (``partition``), and gather.
+
+    ``meshes``: mesh objects (vector sweeps: already passed through ``get_unique_edges``), the same
+    list on every rank.  Returns a list of ``SweepResult`` in problem order (on every rank, or on
+    ``dst`` only), or this rank's own results when ``gather=False``."""
+    from . import device as _dev, fe_solver as fs
+    assert kind in ("vector", "scalar")
+    dist = _dist()
+    multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+    rank = dist.get_rank(group) if multi else 0
+    world = dist.get_world_size(group) if multi else 1
+    dev = _dev.require_cuda(device)
+
+    def n_unknowns(mesh):
+        if kind == "vector":
+            return len(mesh.cells[0].data) + len(mesh.points)
+        return int(np.asarray(mesh.cells[1].data).max()) + 1
+
+    sizes = [n_unknowns(m) for m in meshes]
+    table = partition([p.mesh_id for p in problems], [estimate_cost(sizes[p.mesh_id]) for p in problems], world)
+    mine = table[rank]
+    local, infos = {}, {}
+    # one flat send buffer per rank: [w_0 | V_0 | w_1 | V_1 ...]; the eigensolver writes into its views
+    # (sized for the largest rank payload so that it can be handed to all_gather unpadded)
+    total = max(sum(Nmax * (1 + sizes[problems[i].mesh_id]) for i in r) for r in table)
+    with torch.cuda.device(dev):
+        sendbuf = torch.zeros(max(total, 1), dtype=torch.float64, device=dev)
+        off = 0
+        ctx, ctx_mesh = None, None
+        for i in mine:
+            pr = problems[i]
+            k = 2 * np.pi / pr.wl
+            if ctx_mesh != pr.mesh_id:
+                if ctx is not None:
+                    ctx.close()
+                ctx = _MeshContext(meshes[pr.mesh_id], kind, pr.IOR_dict, k, dev, leaf_elems)
+                ctx_mesh = pr.mesh_id
+            else:
+                ctx.prob.set_materials(ctx.mesh, pr.IOR_dict, k)
+            N = ctx.prob.N
+            wv = sendbuf[off:off + Nmax]
+            Vv = sendbuf[off + Nmax:off + Nmax + Nmax * N].view(Nmax, N)
+            off += Nmax * (1 + N)
+            nmax_ior = max(pr.IOR_dict.values())
+            sigma = float(np.power(k * (nmax_ior if pr.target_neff is None else pr.target_neff), 2))
+            if kind == "vector":
+                _, _, info = fs.solve_vector_resident(ctx.prob, sigma, Nmax, solver=ctx.solver, out=(wv, Vv))
+            else:
+                _, _, info = fs.solve_scalar_resident(ctx.prob, sigma, Nmax, solver=ctx.solver, out=(wv, Vv))
+            w_host = wv.cpu().numpy()
+            cnt = fs._count_modes(w_host, k, pr.IOR_dict,
+                                  always=(kind == "vector" and pr.target_neff is not None))
+            local[i] = (wv, Vv, cnt)
+            infos[i] = info
+        if ctx is not None:
+            ctx.close()
+        torch.cuda.synchronize(dev)
+        if not gather:
+            return [SweepResult(i, local[i][0].cpu().numpy(), local[i][1].cpu().numpy() if with_vectors else None,
+                                local[i][2], rank, infos[i]) for i in mine]
+        got = gather_eigenpairs(local, len(problems), group=group, with_vectors=with_vectors, dst=dst,
+                                packed=sendbuf)
+    if got is None:
+        return None
+    return [SweepResult(i, w, v, cnt, r, infos.get(i, {})) for i, (w, v, cnt, r) in enumerate(got)]
