@@ -6,7 +6,7 @@
 //     k_panel        NBxNB diagonal block LDL^T + row-block TRSM
 //     k_diag_inverse unit-lower NBxNB inverse
 //     k_extend_add   child update matrix -> parent front
-//     k_fwd_gemv / k_bwd_gemvT   the two solve sweeps as dense mat-vecs
+//     k_fwd_front / k_fwd_tile / k_bwd_front / k_bwd_tile   the two solve sweeps as dense mat-vecs
 // -- and the numeric phase is a fixed sequence of launches over slices of those task arrays,
 // level by level from the leaves to the root (left-looking inside a front: every block column
 // is updated once with a rank-k0 GEMM, the Schur complement with one rank-p SYRK, so each
@@ -37,11 +37,17 @@ struct InvTask {
     int32_t ld, nb;
 };
 
+struct FrontRec;
+struct FwdTile;
+struct BwdTile;
+
 struct LevelPlan {
     std::vector<Range> upd, pan, trail;   // per block column (upd: left-looking, trail: right-looking)
     Range syrk, ext_left, ext_right, fwd, bwd;
     int64_t first_front = 0, nfronts = 0;
-    bool small = false;                   // every front fits the single-CTA solve kernels
+    bool small = false;                   // every front fits the one-CTA-per-front solve kernels
+    int nt = 32;                          // threads of those kernels: largest front rounded up to a warp
+    int maxp = 0, maxm = 0;
     bool right_looking = false;
 };
 
@@ -56,15 +62,17 @@ struct ws_solver {
     ws::DevBuf<int32_t> perm, iperm, node_of_new, fr_p, fr_q, bnd, rel;
     ws::DevBuf<int64_t> fr_start, fr_Loff, fr_Uoff, fr_woff, fr_bndoff, dest;
     // numeric storage
-    ws::DevBuf<double> L, S, T, U, W, d, dinv, y, x, bperm;
+    ws::DevBuf<double> L, S, T, U, W, d, dinv, yd, x;
+    ws::DevBuf<ws::FrontRec> recs;
+    ws::DevBuf<int32_t> wsrc0, wsrc1;       // gather maps of the forward sweep
     ws::DevBuf<unsigned long long> stats;   // [0] negative pivots [1] zero/NaN pivots [2] min |pivot| bits [3] max |pivot| bits
     // tasks
     ws::DevBuf<ws::GemmTask> gemm_tasks;
     ws::DevBuf<ws::PanelTask> panel_tasks;
     ws::DevBuf<ws::ExtTask> ext_tasks;
     ws::DevBuf<ws::InvTask> inv_tasks;
-    ws::DevBuf<ws::GemvTask> gemv_tasks;
-    ws::DevBuf<ws::GemvTTask> gemvt_tasks;
+    ws::DevBuf<ws::FwdTile> fwd_tiles;
+    ws::DevBuf<ws::BwdTile> bwd_tiles;
     std::vector<ws::LevelPlan> levels;      // index = tree level
     ws::Range inv0;
     std::vector<std::pair<ws::Range, ws::Range>> inv_stages;   // (step1, step2) per doubling stage
@@ -400,184 +408,303 @@ __global__ void __launch_bounds__(256) k_extend_add(const ExtTask* __restrict__ 
 }
 
 // ---- solve sweeps -----------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_fwd_gather(int64_t first, int has_children, FrontView fv,
-                                                    const double* __restrict__ bperm, double* __restrict__ Wb) {
-    const int64_t t = first + blockIdx.x;
-    const int p = fv.p[t], q = fv.q[t], m = p + q;
-    double* w = Wb + fv.woff[t];
-    const int64_t st = fv.start[t];
-    for (int i = threadIdx.x; i < m; i += blockDim.x) w[i] = (i < p) ? bperm[st + i] : 0.0;
-    if (!has_children) return;
-    for (int cc = 0; cc < 2; ++cc) {
-        __syncthreads();
-        const int64_t c = 2 * t + cc;
-        const int pc = fv.p[c], qc = fv.q[c];
-        const double* wc = Wb + fv.woff[c] + pc;
-        const int32_t* rel = fv.rel + fv.bndoff[c];
-        for (int j = threadIdx.x; j < qc; j += blockDim.x) w[rel[j]] += wc[j];
+// x = M^-1 b with the selectively inverted panels S:  forward  y_own = S11 w_own, w_bnd -= S21 w_own
+// (w = b restricted to the front + the children's boundary remainders), backward
+// x_own = S11^T (D^-1 y_own) - S21^T x_bnd.  One launch per tree level and direction; nothing else:
+//   * every front has ONE 48-byte record (no chain of per-field lookups);
+//   * the children's contributions are fetched through gather maps built once per mesh
+//     (wsrc0/wsrc1[row of the parent] = position of the child's remainder in W, or -1), so a
+//     front needs no child metadata and no separate gather kernel, and the sum order is fixed;
+//   * the matrix loads do not depend on the vectors, so every thread first puts a batch of S
+//     loads in flight and only then resolves the vector dependency (the kernels are bound by
+//     the latency of that chain, not by arithmetic);
+//   * the row / column permutation and the D^-1 scaling are folded into the first and last touch.
+struct FrontRec {
+    int64_t Loff, start, woff, bndoff;
+    int32_t p, q, pad0, pad1;
+};
+
+constexpr int FRONT_MAX_M = 1024;   // fronts up to this size are handled by one CTA
+
+struct SolveCtx {
+    const FrontRec* recs;
+    const double* S;
+    const int32_t* perm;
+    const int32_t* wsrc0;
+    const int32_t* wsrc1;
+    const int32_t* bnd;
+    const double* dinv;
+    double* W;      // boundary remainders of every front (forward)
+    double* yd;     // D^-1 y, permuted order
+    double* x;      // solution, permuted order
+};
+
+__device__ __forceinline__ double fwd_gather(const SolveCtx& cx, const FrontRec& R, int i, int has_children,
+                                             const double* __restrict__ b) {
+    double v = (i < R.p) ? b[cx.perm[R.start + i]] : 0.0;
+    if (has_children) {
+        const int s0 = cx.wsrc0[R.woff + i], s1 = cx.wsrc1[R.woff + i];
+        if (s0 >= 0) v += cx.W[s0];
+        if (s1 >= 0) v += cx.W[s1];
+    }
+    return v;
+}
+
+// one CTA per front, one thread per front row (blockDim.x >= m, multiple of 32, <= MAXT).
+// The k loop is double-buffered: KB loads of the next batch are in flight while the current
+// batch is multiplied.  (MAXT only sets the register budget: with a 1024-thread bound ptxas has
+// 64 registers and serialises the batch, so small fronts get their own instantiation.)
+template <int MAXT, int KB>
+__global__ void __launch_bounds__(MAXT) k_fwd_front(int64_t first, int has_children, SolveCtx cx,
+                                                    const double* __restrict__ b) {
+    extern __shared__ double sw[];
+    const FrontRec R = cx.recs[first + blockIdx.x];
+    const int p = R.p, m = p + R.q, r = threadIdx.x;
+    const bool act = r < m;
+    const int kend = act ? (r < p ? r + 1 : p) : 0;
+    const double* Sr = cx.S + R.Loff + r;
+    const size_t ld = (size_t)m;
+    double a[KB], c[KB];
+#pragma unroll
+    for (int j = 0; j < KB; ++j) a[j] = (j < kend) ? __ldg(Sr + (size_t)j * ld) : 0.0;
+#pragma unroll
+    for (int j = 0; j < KB; ++j) c[j] = (KB + j < kend) ? __ldg(Sr + (size_t)(KB + j) * ld) : 0.0;
+    double wv = 0.0;
+    if (act) {
+        wv = fwd_gather(cx, R, r, has_children, b);
+        if (r < p) sw[r] = wv;
+    }
+    __syncthreads();
+    double acc0 = 0.0, acc1 = 0.0;
+    for (int k0 = 0; k0 < kend; k0 += 2 * KB) {
+#pragma unroll
+        for (int j = 0; j < KB; j += 2) {
+            if (k0 + j < kend) acc0 += a[j] * sw[k0 + j];
+            if (k0 + j + 1 < kend) acc1 += a[j + 1] * sw[k0 + j + 1];
+        }
+#pragma unroll
+        for (int j = 0; j < KB; ++j) a[j] = (k0 + 2 * KB + j < kend) ? __ldg(Sr + (size_t)(k0 + 2 * KB + j) * ld) : 0.0;
+#pragma unroll
+        for (int j = 0; j < KB; j += 2) {
+            if (k0 + KB + j < kend) acc0 += c[j] * sw[k0 + KB + j];
+            if (k0 + KB + j + 1 < kend) acc1 += c[j + 1] * sw[k0 + KB + j + 1];
+        }
+#pragma unroll
+        for (int j = 0; j < KB; ++j) c[j] = (k0 + 3 * KB + j < kend) ? __ldg(Sr + (size_t)(k0 + 3 * KB + j) * ld) : 0.0;
+    }
+    if (act) {
+        const double acc = acc0 + acc1;
+        if (r < p) cx.yd[R.start + r] = acc * cx.dinv[R.start + r];
+        else cx.W[R.woff + r] = wv - acc;
     }
 }
 
-// rows [r0, r0+nr) of  out = S * w_own ;  own rows -> y, boundary rows: w_bnd -= out.
-// 32 rows x 32 k-lanes per CTA: every thread keeps 4 independent loads in flight.
-// FWD_KL = 8 (256 threads) when a level has thousands of tiles, 32 (1024 threads) for the few
-// large fronts near the root, where a tile's k loop would otherwise be long and serial.
-template <int FWD_KL>
-__global__ void __launch_bounds__(GEMV_ROWS * FWD_KL) k_fwd_gemv(const GemvTask* __restrict__ tasks) {
-    const GemvTask t = tasks[blockIdx.x];
-    __shared__ double red[FWD_KL][GEMV_ROWS + 1];
+// large fronts: 32 rows x KL k-lanes per CTA (task = row tile of one front)
+struct FwdTile {
+    int32_t front, r0, nr, pad;
+};
+template <int KL>
+__global__ void __launch_bounds__(32 * KL) k_fwd_tile(const FwdTile* __restrict__ tasks, int has_children, SolveCtx cx,
+                                                      const double* __restrict__ b) {
+    extern __shared__ double sm[];
+    const FwdTile t = tasks[blockIdx.x];
+    const FrontRec R = cx.recs[t.front];
+    const int p = R.p, m = p + R.q;
+    double* sw = sm;                       // [kend_tile]
     const int lr = threadIdx.x & 31, kl = threadIdx.x >> 5;
     const int r = t.r0 + lr;
     const bool valid = lr < t.nr;
-    const int kend_tile = min(t.p, (t.r0 < t.p) ? t.r0 + t.nr : t.p);
-    double acc = 0.0;
-    if (valid) {
-        const int kend = (r < t.p) ? min(kend_tile, r + 1) : t.p;
-        const double* Sr = t.S + r;
-        const size_t ld = (size_t)t.ld;
-        int k = kl;
-        for (; k + 3 * FWD_KL < kend; k += 4 * FWD_KL) {
-            const double s0 = Sr[(size_t)k * ld], s1 = Sr[(size_t)(k + FWD_KL) * ld];
-            const double s2 = Sr[(size_t)(k + 2 * FWD_KL) * ld], s3 = Sr[(size_t)(k + 3 * FWD_KL) * ld];
-            acc += s0 * t.w[k] + s1 * t.w[k + FWD_KL] + s2 * t.w[k + 2 * FWD_KL] + s3 * t.w[k + 3 * FWD_KL];
+    const int kend_tile = min(p, (t.r0 < p) ? t.r0 + t.nr : p);
+    double* red = sm + ((kend_tile + 1) & ~1);     // [KL][33]
+    const int kend = valid ? ((r < p) ? min(kend_tile, r + 1) : p) : 0;
+    const double* Sr = cx.S + R.Loff + r;
+    const size_t ld = (size_t)m;
+    constexpr int NL = 8;                  // loads in flight per thread
+    double a[NL];
+#pragma unroll
+    for (int j = 0; j < NL; ++j) a[j] = (kl + j * KL < kend) ? __ldg(Sr + (size_t)(kl + j * KL) * ld) : 0.0;
+    for (int k = threadIdx.x; k < kend_tile; k += 32 * KL) sw[k] = fwd_gather(cx, R, k, has_children, b);
+    double wv = 0.0;
+    if (kl == 0 && valid && r >= p) wv = fwd_gather(cx, R, r, has_children, b);
+    __syncthreads();
+    double acc = 0.0, acc1 = 0.0;
+    for (int k = kl; k < kend; k += NL * KL) {
+        double c[NL];
+#pragma unroll
+        for (int j = 0; j < NL; ++j) c[j] = a[j];
+#pragma unroll
+        for (int j = 0; j < NL; ++j)
+            a[j] = (k + (NL + j) * KL < kend) ? __ldg(Sr + (size_t)(k + (NL + j) * KL) * ld) : 0.0;
+#pragma unroll
+        for (int j = 0; j < NL; j += 2) {
+            if (k + j * KL < kend) acc += c[j] * sw[k + j * KL];
+            if (k + (j + 1) * KL < kend) acc1 += c[j + 1] * sw[k + (j + 1) * KL];
         }
-        for (; k < kend; k += FWD_KL) acc += Sr[(size_t)k * ld] * t.w[k];
     }
-    red[kl][lr] = acc;
+    acc += acc1;
+    red[kl * 33 + lr] = acc;
     __syncthreads();
     if (kl == 0 && valid) {
-        double s = 0.0;
+        double sacc = 0.0;
 #pragma unroll
-        for (int j = 0; j < FWD_KL; ++j) s += red[j][lr];
-        if (r < t.p) t.y[r] = s;
-        else t.w[r] -= s;
+        for (int j = 0; j < KL; ++j) sacc += red[j * 33 + lr];
+        if (r < p) cx.yd[R.start + r] = sacc * cx.dinv[R.start + r];
+        else cx.W[R.woff + r] = wv - sacc;
     }
 }
 
-__global__ void __launch_bounds__(256) k_bwd_gather(int64_t first, FrontView fv, const double* __restrict__ y,
-                                                    const double* __restrict__ dinv, const double* __restrict__ x,
-                                                    double* __restrict__ Wb) {
-    const int64_t t = first + blockIdx.x;
-    const int p = fv.p[t], q = fv.q[t], m = p + q;
-    double* g = Wb + fv.woff[t];
-    const int64_t st = fv.start[t];
-    const int32_t* b = fv.bnd + fv.bndoff[t];
-    for (int i = threadIdx.x; i < m; i += blockDim.x) g[i] = (i < p) ? y[st + i] * dinv[st + i] : -x[b[i - p]];
+// backward, one CTA per front: warp w owns columns w, w+NW, ...; BWD_CB columns x BWD_RJ row groups
+// of loads in flight per lane; g = [D^-1 y_own ; -x_bnd] is staged in shared memory.
+template <int MAXT, int BWD_CB, int BWD_RJ>
+__global__ void __launch_bounds__(MAXT) k_bwd_front(int64_t first, SolveCtx cx, double* __restrict__ xout) {
+    extern __shared__ double sg[];
+    const FrontRec R = cx.recs[first + blockIdx.x];
+    const int p = R.p, m = p + R.q;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, NW = blockDim.x >> 5;
+    const double* Sf = cx.S + R.Loff;
+    double a[BWD_CB][BWD_RJ];
+#pragma unroll
+    for (int i = 0; i < BWD_CB; ++i) {
+        const int c = warp + NW * i;
+#pragma unroll
+        for (int j = 0; j < BWD_RJ; ++j) {
+            const int r = c + lane + 32 * j;
+            a[i][j] = (c < p && r < m) ? __ldg(Sf + r + (size_t)c * m) : 0.0;
+        }
+    }
+    for (int i = threadIdx.x; i < m; i += blockDim.x)
+        sg[i] = (i < p) ? cx.yd[R.start + i] : -cx.x[cx.bnd[R.bndoff + i - p]];
+    __syncthreads();
+    for (int cb = warp; cb < p; cb += NW * BWD_CB) {
+        double acc[BWD_CB];
+#pragma unroll
+        for (int i = 0; i < BWD_CB; ++i) {
+            const int c = cb + NW * i;
+            double s = 0.0;
+#pragma unroll
+            for (int j = 0; j < BWD_RJ; ++j) {
+                const int r = c + lane + 32 * j;
+                if (c < p && r < m) s += a[i][j] * sg[r];
+            }
+            acc[i] = s;
+        }
+        // remaining row groups of this batch
+        const int rmax = m - cb;                    // rows below the first column of the batch
+        for (int j0 = BWD_RJ; j0 * 32 < rmax; j0 += BWD_RJ) {
+#pragma unroll
+            for (int i = 0; i < BWD_CB; ++i) {
+                const int c = cb + NW * i;
+#pragma unroll
+                for (int j = 0; j < BWD_RJ; ++j) {
+                    const int r = c + lane + 32 * (j0 + j);
+                    a[i][j] = (c < p && r < m) ? __ldg(Sf + r + (size_t)c * m) : 0.0;
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < BWD_CB; ++i) {
+                const int c = cb + NW * i;
+#pragma unroll
+                for (int j = 0; j < BWD_RJ; ++j) {
+                    const int r = c + lane + 32 * (j0 + j);
+                    if (c < p && r < m) acc[i] += a[i][j] * sg[r];
+                }
+            }
+        }
+        // prefetch the next batch while this one is reduced
+        const int nb = cb + NW * BWD_CB;
+#pragma unroll
+        for (int i = 0; i < BWD_CB; ++i) {
+            const int c = nb + NW * i;
+#pragma unroll
+            for (int j = 0; j < BWD_RJ; ++j) {
+                const int r = c + lane + 32 * j;
+                a[i][j] = (c < p && r < m) ? __ldg(Sf + r + (size_t)c * m) : 0.0;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < BWD_CB; ++i) {
+            double s = acc[i];
+#pragma unroll
+            for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            const int c = cb + NW * i;
+            if (lane == 0 && c < p) {
+                cx.x[R.start + c] = s;
+                xout[cx.perm[R.start + c]] = s;
+            }
+        }
+    }
 }
 
-// columns [c0, c0+nc): x_own[c] = sum_{r>=c} S[r,c] * g[r].  4 warps share one column (each a
-// quarter of the rows, 4 independent accumulators per lane), 8 columns per CTA.
-template <int BWD_WPC>
-__global__ void __launch_bounds__(32 * GEMVT_COLS * BWD_WPC) k_bwd_gemvT(const GemvTTask* __restrict__ tasks) {
-    const GemvTTask t = tasks[blockIdx.x];
-    __shared__ double red[GEMVT_COLS][BWD_WPC];
+// large fronts: GEMVT_COLS columns per CTA, WPC warps share a column (task = column tile)
+struct BwdTile {
+    int32_t front, c0, nc, pad;
+};
+template <int WPC>
+__global__ void __launch_bounds__(32 * GEMVT_COLS * WPC) k_bwd_tile(const BwdTile* __restrict__ tasks, SolveCtx cx,
+                                                                    double* __restrict__ xout) {
+    extern __shared__ double sm[];
+    const BwdTile t = tasks[blockIdx.x];
+    const FrontRec R = cx.recs[t.front];
+    const int p = R.p, m = p + R.q;
+    double* sg = sm;                                   // g[c0 .. m)
+    double* red = sm + ((m - t.c0 + 1) & ~1);          // [GEMVT_COLS][WPC]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int wc = warp / BWD_WPC, part = warp % BWD_WPC;
+    const int wc = warp / WPC, part = warp % WPC;
+    const int c = t.c0 + wc;
+    const bool on = wc < t.nc;
+    const double* Sc = cx.S + R.Loff + (size_t)c * m;
+    constexpr int step = 32 * WPC;
+    constexpr int NL = 8;                              // loads in flight per lane
+    const int rb = c + part * 32 + lane;               // first row of this lane
+    double a[NL];
+#pragma unroll
+    for (int j = 0; j < NL; ++j) a[j] = (on && rb + j * step < m) ? __ldg(Sc + rb + j * step) : 0.0;
+    for (int i = t.c0 + threadIdx.x; i < m; i += blockDim.x)
+        sg[i - t.c0] = (i < p) ? cx.yd[R.start + i] : -cx.x[cx.bnd[R.bndoff + i - p]];
+    __syncthreads();
     double acc = 0.0;
-    if (wc < t.nc) {
-        const int c = t.c0 + wc;
-        const double* Sc = t.S + (size_t)c * t.ld;
-        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-        const int step = 32 * BWD_WPC;
-        int r = c + part * 32 + lane;
-        for (; r + 3 * step < t.m; r += 4 * step) {
-            a0 += Sc[r] * t.g[r];
-            a1 += Sc[r + step] * t.g[r + step];
-            a2 += Sc[r + 2 * step] * t.g[r + 2 * step];
-            a3 += Sc[r + 3 * step] * t.g[r + 3 * step];
+    if (on) {
+        double a0 = 0.0, a1 = 0.0;
+        for (int r = rb; r < m; r += NL * step) {
+            double cbuf[NL];
+#pragma unroll
+            for (int j = 0; j < NL; ++j) cbuf[j] = a[j];
+#pragma unroll
+            for (int j = 0; j < NL; ++j) a[j] = (r + (NL + j) * step < m) ? __ldg(Sc + r + (NL + j) * step) : 0.0;
+#pragma unroll
+            for (int j = 0; j < NL; j += 2) {
+                if (r + j * step < m) a0 += cbuf[j] * sg[r + j * step - t.c0];
+                if (r + (j + 1) * step < m) a1 += cbuf[j + 1] * sg[r + (j + 1) * step - t.c0];
+            }
         }
-        for (; r < t.m; r += step) a0 += Sc[r] * t.g[r];
-        acc = (a0 + a1) + (a2 + a3);
+        acc = a0 + a1;
 #pragma unroll
         for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
     }
-    if (lane == 0 && wc < GEMVT_COLS) red[wc][part] = acc;
+    if (lane == 0) red[wc * WPC + part] = acc;
     __syncthreads();
     if (threadIdx.x < t.nc) {
         double sacc = 0.0;
 #pragma unroll
-        for (int j = 0; j < BWD_WPC; ++j) sacc += red[threadIdx.x][j];
-        t.x[t.c0 + threadIdx.x] = sacc;
+        for (int j = 0; j < WPC; ++j) sacc += red[threadIdx.x * WPC + j];
+        const int cc = t.c0 + threadIdx.x;
+        cx.x[R.start + cc] = sacc;
+        xout[cx.perm[R.start + cc]] = sacc;
     }
 }
 
-// ---- small fronts (m <= SMALL_M): one CTA does a whole front, work vector in shared memory ----
-constexpr int SMALL_M = 256;
-__global__ void __launch_bounds__(128) k_fwd_small(int64_t first, int has_children, FrontView fv,
-                                                   const double* __restrict__ bperm, double* __restrict__ Wb,
-                                                   const double* __restrict__ Sb, double* __restrict__ y) {
-    const int64_t t = first + blockIdx.x;
-    const int p = fv.p[t], q = fv.q[t], m = p + q;
-    __shared__ double sw[SMALL_M];
-    double* w = Wb + fv.woff[t];
-    const int64_t st = fv.start[t];
-    for (int i = threadIdx.x; i < m; i += 128) sw[i] = (i < p) ? bperm[st + i] : 0.0;
-    if (has_children) {
-        for (int cc = 0; cc < 2; ++cc) {
-            __syncthreads();
-            const int64_t c = 2 * t + cc;
-            const int pc = fv.p[c], qc = fv.q[c];
-            const double* wc = Wb + fv.woff[c] + pc;
-            const int32_t* rel = fv.rel + fv.bndoff[c];
-            for (int j = threadIdx.x; j < qc; j += 128) sw[rel[j]] += wc[j];
-        }
-    }
-    __syncthreads();
-    const double* S = Sb + fv.Loff[t];
-    for (int r = threadIdx.x; r < m; r += 128) {
-        const int kend = (r < p) ? r + 1 : p;
-        const double* Sr = S + r;
-        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-        int k = 0;
-        for (; k + 3 < kend; k += 4) {
-            a0 += Sr[(size_t)k * m] * sw[k];
-            a1 += Sr[(size_t)(k + 1) * m] * sw[k + 1];
-            a2 += Sr[(size_t)(k + 2) * m] * sw[k + 2];
-            a3 += Sr[(size_t)(k + 3) * m] * sw[k + 3];
-        }
-        for (; k < kend; ++k) a0 += Sr[(size_t)k * m] * sw[k];
-        const double acc = (a0 + a1) + (a2 + a3);
-        if (r < p) y[st + r] = acc;
-        else w[r] = sw[r] - acc;
-    }
+// gather maps: for child c of front t = c/2 and boundary entry j of c:
+//   wsrc{c&1}[woff[t] + rel_c[j]] = woff[c] + p_c + j
+__global__ void k_build_wsrc(int64_t nfronts, const FrontRec* __restrict__ recs, const int32_t* __restrict__ rel,
+                             int32_t* __restrict__ wsrc0, int32_t* __restrict__ wsrc1) {
+    const int64_t c = 2 + blockIdx.x;
+    if (c >= nfronts) return;
+    const FrontRec Rc = recs[c], Rp = recs[c >> 1];
+    int32_t* dst = (c & 1) ? wsrc1 : wsrc0;
+    for (int j = threadIdx.x; j < Rc.q; j += blockDim.x)
+        dst[Rp.woff + rel[Rc.bndoff + j]] = (int32_t)(Rc.woff + Rc.p + j);
 }
 
-__global__ void __launch_bounds__(128) k_bwd_small(int64_t first, FrontView fv, const double* __restrict__ y,
-                                                   const double* __restrict__ dinv, double* __restrict__ x,
-                                                   const double* __restrict__ Sb) {
-    const int64_t t = first + blockIdx.x;
-    const int p = fv.p[t], q = fv.q[t], m = p + q;
-    __shared__ double sg[SMALL_M];
-    const int64_t st = fv.start[t];
-    const int32_t* b = fv.bnd + fv.bndoff[t];
-    for (int i = threadIdx.x; i < m; i += 128) sg[i] = (i < p) ? y[st + i] * dinv[st + i] : -x[b[i - p]];
-    __syncthreads();
-    const double* S = Sb + fv.Loff[t];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int c = warp; c < p; c += 4) {
-        const double* Sc = S + (size_t)c * m;
-        double a0 = 0.0, a1 = 0.0;
-        int r = c + lane;
-        for (; r + 32 < m; r += 64) {
-            a0 += Sc[r] * sg[r];
-            a1 += Sc[r + 32] * sg[r + 32];
-        }
-        if (r < m) a0 += Sc[r] * sg[r];
-        double acc = a0 + a1;
-#pragma unroll
-        for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-        if (lane == 0) x[st + c] = acc;
-    }
-}
-
-__global__ void k_permute_in(int64_t N, const int32_t* __restrict__ perm, const double* __restrict__ b, double* __restrict__ bp) {
-    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (i < N) bp[i] = b[perm[i]];
-}
-__global__ void k_permute_out(int64_t N, const int32_t* __restrict__ perm, const double* __restrict__ x, double* __restrict__ out) {
-    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (i < N) out[perm[i]] = x[i];
-}
 __global__ void k_recip(int64_t N, const double* __restrict__ d, double* __restrict__ dinv) {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i < N) dinv[i] = 1.0 / d[i];
@@ -608,8 +735,8 @@ static void build_plan(ws_solver* s, cudaStream_t st) {
     std::vector<PanelTask> P;
     std::vector<ExtTask> E;
     std::vector<InvTask> I;
-    std::vector<GemvTask> F;
-    std::vector<GemvTTask> Bk;
+    std::vector<FwdTile> F;
+    std::vector<BwdTile> Bk;
     double* Lb = s->L.get();
     double* Sb = s->S.get();
     double* Tb = s->T.get();
@@ -630,7 +757,10 @@ static void build_plan(ws_solver* s, cudaStream_t st) {
         LP.trail.assign(nkb, Range());
         int maxm = 0;
         for (int64_t t = f0; t < f1; ++t) maxm = std::max(maxm, (int)(Y.p[t] + Y.q[t]));
-        LP.small = maxm <= SMALL_M;
+        LP.small = maxm <= FRONT_MAX_M;
+        LP.nt = std::max(32, (maxm + 31) & ~31);
+        LP.maxp = maxp;
+        LP.maxm = maxm;
         // few large fronts: a left-looking block-column update has too few tiles to fill the GPU
         // (and a long serial k loop); update the whole trailing panel after every block column.
         LP.right_looking = (f1 - f0) <= 64 && maxp > 4 * NB;
@@ -750,32 +880,17 @@ static void build_plan(ws_solver* s, cudaStream_t st) {
         LP.bwd.off = (int64_t)Bk.size();
         for (int64_t t = f0; t < f1 && !LP.small; ++t) {
             const int p = Y.p[t], q = Y.q[t], m = p + q;
-            if (!p) continue;
+            // (a front without own unknowns still forwards its children's remainders)
             for (int r0 = 0; r0 < m; r0 += GEMV_ROWS) {
                 // a tile must not straddle the own / boundary split (different k extents)
                 int nr = std::min(GEMV_ROWS, m - r0);
                 if (r0 < p && r0 + nr > p) nr = p - r0;
-                GemvTask f{};
-                f.S = Sb + Y.Loff[t];
-                f.w = Wb + Y.woff[t];
-                f.y = s->y.get() + Y.start[t];
-                f.ld = m; f.p = p; f.r0 = r0; f.nr = nr;
-                F.push_back(f);
-                if (nr < GEMV_ROWS && r0 + nr < m) {     // remainder of a straddling tile
-                    GemvTask f2 = f;
-                    f2.r0 = r0 + nr;
-                    f2.nr = std::min(GEMV_ROWS - nr, m - f2.r0);
-                    F.push_back(f2);
-                }
+                F.push_back(FwdTile{(int32_t)t, r0, nr, 0});
+                if (nr < GEMV_ROWS && r0 + nr < m)       // remainder of a straddling tile
+                    F.push_back(FwdTile{(int32_t)t, r0 + nr, std::min(GEMV_ROWS - nr, m - (r0 + nr)), 0});
             }
-            for (int c0 = 0; c0 < p; c0 += GEMVT_COLS) {
-                GemvTTask b{};
-                b.S = Sb + Y.Loff[t];
-                b.g = Wb + Y.woff[t];
-                b.x = s->x.get() + Y.start[t];
-                b.ld = m; b.m = m; b.c0 = c0; b.nc = std::min(GEMVT_COLS, p - c0);
-                Bk.push_back(b);
-            }
+            for (int c0 = 0; c0 < p; c0 += GEMVT_COLS)
+                Bk.push_back(BwdTile{(int32_t)t, c0, std::min(GEMVT_COLS, p - c0), 0});
         }
         LP.fwd.cnt = (int64_t)F.size() - LP.fwd.off;
         LP.bwd.cnt = (int64_t)Bk.size() - LP.bwd.off;
@@ -868,11 +983,11 @@ static void build_plan(ws_solver* s, cudaStream_t st) {
     upload(s->panel_tasks, P, st);
     upload(s->ext_tasks, E, st);
     upload(s->inv_tasks, I, st);
-    upload(s->gemv_tasks, F, st);
-    upload(s->gemvt_tasks, Bk, st);
+    upload(s->fwd_tiles, F, st);
+    upload(s->bwd_tiles, Bk, st);
     WS_CUDA(cudaStreamSynchronize(st));   // the host vectors die here
     s->bytes += (int64_t)(G.size() * sizeof(GemmTask) + P.size() * sizeof(PanelTask) + E.size() * sizeof(ExtTask) +
-                          I.size() * sizeof(InvTask) + F.size() * sizeof(GemvTask) + Bk.size() * sizeof(GemvTTask));
+                          I.size() * sizeof(InvTask) + F.size() * sizeof(FwdTile) + Bk.size() * sizeof(BwdTile));
 }
 
 static void launch_gemm(const ws_solver* s, const Range& r, bool narrow, cudaStream_t st) {
@@ -937,12 +1052,28 @@ int ws_solver_create(const ws_pattern* p, const ws_symbolic* sym, ws_solver** ou
         s->W.alloc(Y.Wtotal, st);
         s->d.alloc(Y.N, st);
         s->dinv.alloc(Y.N, st);
-        s->y.alloc(Y.N, st);
+        s->yd.alloc(Y.N, st);
         s->x.alloc(Y.N, st);
-        s->bperm.alloc(Y.N, st);
+        {
+            std::vector<FrontRec> recs((size_t)Y.nfronts);
+            for (int64_t t = 1; t < Y.nfronts; ++t)
+                recs[t] = FrontRec{Y.Loff[t], Y.start[t], Y.woff[t], Y.bndoff[t], Y.p[t], Y.q[t], 0, 0};
+            upload(s->recs, recs, st);
+            WS_CUDA(cudaStreamSynchronize(st));   // recs dies here
+            WS_REQUIRE(Y.Wtotal < ((int64_t)1 << 31), "work-vector storage exceeds 32-bit indexing");
+            s->wsrc0.alloc(std::max<int64_t>(Y.Wtotal, 1), st);
+            s->wsrc1.alloc(std::max<int64_t>(Y.Wtotal, 1), st);
+            WS_CUDA(cudaMemsetAsync(s->wsrc0.get(), 0xFF, s->wsrc0.bytes(), st));
+            WS_CUDA(cudaMemsetAsync(s->wsrc1.get(), 0xFF, s->wsrc1.bytes(), st));
+            if (Y.nfronts > 2) {
+                k_build_wsrc<<<(unsigned)(Y.nfronts - 2), 128, 0, st>>>(Y.nfronts, s->recs.get(), s->rel.get(),
+                                                                         s->wsrc0.get(), s->wsrc1.get());
+                count_launch(1);
+            }
+        }
         s->stats.alloc(4, st);
         s->dest.alloc(p->nnz, st);
-        s->bytes = (3 * Y.Ltotal + Y.Utotal + Y.Wtotal + 5 * Y.N) * 8 + p->nnz * 8;
+        s->bytes = (3 * Y.Ltotal + Y.Utotal + 2 * Y.Wtotal + 4 * Y.N) * 8 + p->nnz * 8;
         const double tc1 = tnow();
         const int T = 128;
         k_dest_map<<<ceil_div(Y.N, T), T, 0, st>>>(Y.N, p->rowptr.get(), p->colidx.get(), s->iperm.get(),
@@ -1042,43 +1173,60 @@ int ws_solver_solve(ws_solver* s, const double* b, double* x, int nrhs, int devi
     DeviceGuard g(device);
     cudaStream_t st = (cudaStream_t)stream;
     const Symbolic& Y = s->sym;
-    FrontView fv = view(s);
-    const int T = 256;
+    // (b may alias x: b is read by the forward sweep only, x is written by the backward sweep only)
+    static bool configured = false;
+    if (!configured) {
+        const int big = 160 * 1024;
+        WS_CUDA(cudaFuncSetAttribute(k_fwd_tile<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+        WS_CUDA(cudaFuncSetAttribute(k_fwd_tile<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+        WS_CUDA(cudaFuncSetAttribute(k_bwd_tile<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+        WS_CUDA(cudaFuncSetAttribute(k_bwd_tile<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+        configured = true;
+    }
+    SolveCtx cx{s->recs.get(), s->S.get(), s->perm.get(), s->wsrc0.get(), s->wsrc1.get(), s->bnd.get(),
+                s->dinv.get(), s->W.get(), s->yd.get(), s->x.get()};
     for (int rhs = 0; rhs < nrhs; ++rhs) {
         const double* bi = b + (size_t)rhs * s->N;
         double* xi = x + (size_t)rhs * s->N;
-        k_permute_in<<<ceil_div(s->N, T), T, 0, st>>>(s->N, s->perm.get(), bi, s->bperm.get());
-        int nl = 2;
+        int nl = 0;
         for (int l = Y.depth; l >= 0; --l) {
             const LevelPlan& LP = s->levels[l];
             const int hc = l < Y.depth ? 1 : 0;
             if (LP.small) {
-                k_fwd_small<<<(unsigned)LP.nfronts, 128, 0, st>>>(LP.first_front, hc, fv, s->bperm.get(), s->W.get(), s->S.get(), s->y.get());
+                const size_t sh = (size_t)std::max(LP.maxp, 2) * sizeof(double);
+                const unsigned nf = (unsigned)LP.nfronts;
+                if (LP.nt <= 128) k_fwd_front<128, 16><<<nf, LP.nt, sh, st>>>(LP.first_front, hc, cx, bi);
+                else if (LP.nt <= 256) k_fwd_front<256, 16><<<nf, LP.nt, sh, st>>>(LP.first_front, hc, cx, bi);
+                else if (LP.nt <= 512) k_fwd_front<512, 16><<<nf, LP.nt, sh, st>>>(LP.first_front, hc, cx, bi);
+                else k_fwd_front<1024, 8><<<nf, LP.nt, sh, st>>>(LP.first_front, hc, cx, bi);
                 ++nl;
-            } else {
-                k_fwd_gather<<<(unsigned)LP.nfronts, 256, 0, st>>>(LP.first_front, hc, fv, s->bperm.get(), s->W.get());
-                if (LP.fwd.cnt) {
-                    if (LP.fwd.cnt >= 500) k_fwd_gemv<8><<<(unsigned)LP.fwd.cnt, GEMV_ROWS * 8, 0, st>>>(s->gemv_tasks.get() + LP.fwd.off);
-                    else k_fwd_gemv<32><<<(unsigned)LP.fwd.cnt, GEMV_ROWS * 32, 0, st>>>(s->gemv_tasks.get() + LP.fwd.off);
-                }
-                nl += 2;
+            } else if (LP.fwd.cnt) {
+                const size_t base = (size_t)((LP.maxp + 1) & ~1);
+                if (LP.fwd.cnt >= 500)
+                    k_fwd_tile<8><<<(unsigned)LP.fwd.cnt, 32 * 8, (base + 8 * 33) * sizeof(double), st>>>(s->fwd_tiles.get() + LP.fwd.off, hc, cx, bi);
+                else
+                    k_fwd_tile<32><<<(unsigned)LP.fwd.cnt, 32 * 32, (base + 32 * 33) * sizeof(double), st>>>(s->fwd_tiles.get() + LP.fwd.off, hc, cx, bi);
+                ++nl;
             }
         }
         for (int l = 0; l <= Y.depth; ++l) {
             const LevelPlan& LP = s->levels[l];
             if (LP.small) {
-                k_bwd_small<<<(unsigned)LP.nfronts, 128, 0, st>>>(LP.first_front, fv, s->y.get(), s->dinv.get(), s->x.get(), s->S.get());
+                const size_t sh = (size_t)std::max(LP.maxm, 2) * sizeof(double);
+                const unsigned nf = (unsigned)LP.nfronts;
+                if (LP.nt <= 128) k_bwd_front<128, 8, 4><<<nf, LP.nt, sh, st>>>(LP.first_front, cx, xi);
+                else if (LP.nt <= 512) k_bwd_front<512, 4, 4><<<nf, LP.nt, sh, st>>>(LP.first_front, cx, xi);
+                else k_bwd_front<1024, 2, 4><<<nf, LP.nt, sh, st>>>(LP.first_front, cx, xi);
                 ++nl;
-            } else {
-                k_bwd_gather<<<(unsigned)LP.nfronts, 256, 0, st>>>(LP.first_front, fv, s->y.get(), s->dinv.get(), s->x.get(), s->W.get());
-                if (LP.bwd.cnt) {
-                    if (LP.bwd.cnt >= 430) k_bwd_gemvT<1><<<(unsigned)LP.bwd.cnt, 32 * GEMVT_COLS, 0, st>>>(s->gemvt_tasks.get() + LP.bwd.off);
-                    else k_bwd_gemvT<4><<<(unsigned)LP.bwd.cnt, 32 * GEMVT_COLS * 4, 0, st>>>(s->gemvt_tasks.get() + LP.bwd.off);
-                }
-                nl += 2;
+            } else if (LP.bwd.cnt) {
+                const size_t base = (size_t)((LP.maxm + 1) & ~1);
+                if (LP.bwd.cnt >= 430)
+                    k_bwd_tile<1><<<(unsigned)LP.bwd.cnt, 32 * GEMVT_COLS, (base + GEMVT_COLS) * sizeof(double), st>>>(s->bwd_tiles.get() + LP.bwd.off, cx, xi);
+                else
+                    k_bwd_tile<4><<<(unsigned)LP.bwd.cnt, 32 * GEMVT_COLS * 4, (base + GEMVT_COLS * 4) * sizeof(double), st>>>(s->bwd_tiles.get() + LP.bwd.off, cx, xi);
+                ++nl;
             }
         }
-        k_permute_out<<<ceil_div(s->N, T), T, 0, st>>>(s->N, s->perm.get(), s->x.get(), xi);
         count_launch(nl);
     }
     WS_CUDA(cudaGetLastError());

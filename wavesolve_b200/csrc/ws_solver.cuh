@@ -74,20 +74,6 @@ struct PanelTask {
     int32_t ld, k0, nb, r0, nr, write_diag;
 };
 
-// y / work-vector mat-vec tasks of the solve sweeps
-struct GemvTask {
-    const double* S;     // solve panel base (m x p, ld = m)
-    double* w;           // front work vector (length m)
-    double* y;           // global vector at start
-    int32_t ld, p, r0, nr;
-};
-struct GemvTTask {
-    const double* S;
-    const double* g;     // front work vector (length m): [dinv*y_own ; -x_bnd]
-    double* x;           // global x at start
-    int32_t ld, m, c0, nc;
-};
-
 struct LevelRange {
     int64_t begin = 0, count = 0;
 };

@@ -9,17 +9,26 @@
 // shared memory, and one thread per row then adds its products in column order (deterministic).
 // x is N*8 B and stays L2-resident for every mesh in scope.
 // Bound: HBM, 12 B per non-zero + 20 B per row.
+#include <algorithm>
+
 #include "ws_common.cuh"
 
 namespace ws {
 
 constexpr int SPMV_ROWS = 128;          // rows (and threads) per CTA
-constexpr int SPMV_CAP = 4096;          // products held in shared memory (32 KB)
+constexpr int SPMV_CHUNKS = 3;          // 4-entry chunks a thread keeps in flight per round (12 entries)
+constexpr int SPMV_MAX_SMEM = 64 * 1024;
 
+// One round = every thread issues SPMV_CHUNKS 16-byte column loads and 2*SPMV_CHUNKS 16-byte value
+// loads back to back (the slice is walked from its 4-entry-aligned start, so all of them are
+// aligned vector loads and a warp covers 512 + 1024 contiguous bytes per chunk), then the 12
+// gathers of x, then parks the products: the dependent chain of a CTA is
+// rowptr -> (col, val) -> x -> shared memory, once for a block of edge / mid-side rows (~9
+// entries per row) and twice for a block of vertex / node rows (~19 per row).
 __global__ void __launch_bounds__(SPMV_ROWS)
-k_spmv_stream(int64_t N, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
+k_spmv_stream(int64_t N, int64_t nnz, int cap, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
               const double* __restrict__ vals, const double* __restrict__ x, double* __restrict__ y) {
-    __shared__ double prod[SPMV_CAP];
+    extern __shared__ double prod[];
     __shared__ int rp[SPMV_ROWS + 1];
     const int64_t r0 = (int64_t)blockIdx.x * SPMV_ROWS;
     const int nr = (int)min((int64_t)SPMV_ROWS, N - r0);
@@ -29,19 +38,56 @@ k_spmv_stream(int64_t N, const int32_t* __restrict__ rowptr, const int32_t* __re
     __syncthreads();
     const int p0 = rp[0], p1 = rp[nr];
     const int cnt = p1 - p0;
-    if (cnt <= SPMV_CAP) {
-        int s = tid;
-        for (; s + 3 * SPMV_ROWS < cnt; s += 4 * SPMV_ROWS) {
-            const int c0 = __ldg(colidx + p0 + s), c1 = __ldg(colidx + p0 + s + SPMV_ROWS);
-            const int c2 = __ldg(colidx + p0 + s + 2 * SPMV_ROWS), c3 = __ldg(colidx + p0 + s + 3 * SPMV_ROWS);
-            const double v0 = __ldg(vals + p0 + s), v1 = __ldg(vals + p0 + s + SPMV_ROWS);
-            const double v2 = __ldg(vals + p0 + s + 2 * SPMV_ROWS), v3 = __ldg(vals + p0 + s + 3 * SPMV_ROWS);
-            prod[s] = v0 * __ldg(x + c0);
-            prod[s + SPMV_ROWS] = v1 * __ldg(x + c1);
-            prod[s + 2 * SPMV_ROWS] = v2 * __ldg(x + c2);
-            prod[s + 3 * SPMV_ROWS] = v3 * __ldg(x + c3);
+    if (cnt <= cap) {
+        const int a0 = p0 & ~3;                       // aligned start of the slice
+        const int nchunk = (p1 - a0 + 3) >> 2;
+        for (int cb = 0; cb < nchunk; cb += SPMV_ROWS * SPMV_CHUNKS) {
+            int4 c[SPMV_CHUNKS];
+            double2 va[SPMV_CHUNKS], vb[SPMV_CHUNKS];
+#pragma unroll
+            for (int i = 0; i < SPMV_CHUNKS; ++i) {
+                const int ch = cb + tid + i * SPMV_ROWS;
+                const int64_t g = (int64_t)a0 + 4 * (int64_t)ch;       // global entry index of the chunk
+                c[i] = make_int4(0, 0, 0, 0);
+                va[i] = vb[i] = make_double2(0.0, 0.0);
+                if (ch < nchunk) {
+                    if (g + 4 <= nnz) {
+                        c[i] = __ldg(reinterpret_cast<const int4*>(colidx + g));
+                        va[i] = __ldg(reinterpret_cast<const double2*>(vals + g));
+                        vb[i] = __ldg(reinterpret_cast<const double2*>(vals + g + 2));
+                    } else {                                           // last chunk of the matrix
+                        int cc[4] = {0, 0, 0, 0};
+                        double vv[4] = {0.0, 0.0, 0.0, 0.0};
+                        for (int e = 0; e < 4; ++e)
+                            if (g + e < nnz) { cc[e] = colidx[g + e]; vv[e] = vals[g + e]; }
+                        c[i] = make_int4(cc[0], cc[1], cc[2], cc[3]);
+                        va[i] = make_double2(vv[0], vv[1]);
+                        vb[i] = make_double2(vv[2], vv[3]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < SPMV_CHUNKS; ++i) {
+                // entries outside [p0, p1) belong to neighbouring blocks: their columns are valid
+                // indices, the products are simply not stored
+                va[i].x *= __ldg(x + c[i].x);
+                va[i].y *= __ldg(x + c[i].y);
+                vb[i].x *= __ldg(x + c[i].z);
+                vb[i].y *= __ldg(x + c[i].w);
+            }
+#pragma unroll
+            for (int i = 0; i < SPMV_CHUNKS; ++i) {
+                const int s = (a0 - p0) + 4 * (cb + tid + i * SPMV_ROWS);   // slot of the chunk's first entry
+                if (s >= 0 && s + 3 < cnt) {
+                    prod[s] = va[i].x; prod[s + 1] = va[i].y; prod[s + 2] = vb[i].x; prod[s + 3] = vb[i].y;
+                } else {
+                    if (s >= 0 && s < cnt) prod[s] = va[i].x;
+                    if (s + 1 >= 0 && s + 1 < cnt) prod[s + 1] = va[i].y;
+                    if (s + 2 >= 0 && s + 2 < cnt) prod[s + 2] = vb[i].x;
+                    if (s + 3 >= 0 && s + 3 < cnt) prod[s + 3] = vb[i].y;
+                }
+            }
         }
-        for (; s < cnt; s += SPMV_ROWS) prod[s] = __ldg(vals + p0 + s) * __ldg(x + __ldg(colidx + p0 + s));
         __syncthreads();
         if (tid < nr) {
             double acc = 0.0;
@@ -58,7 +104,16 @@ k_spmv_stream(int64_t N, const int32_t* __restrict__ rowptr, const int32_t* __re
 
 void spmv_launch(const ws_pattern* p, const double* vals, const double* x, double* y, cudaStream_t st) {
     if (p->N == 0) return;
-    k_spmv_stream<<<ceil_div(p->N, SPMV_ROWS), SPMV_ROWS, 0, st>>>(p->N, p->rowptr.get(), p->colidx.get(), vals, x, y);
+    static bool configured = false;
+    if (!configured) {
+        WS_CUDA(cudaFuncSetAttribute(k_spmv_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, SPMV_MAX_SMEM));
+        configured = true;
+    }
+    // shared-memory tile sized for this pattern's densest 128-row block (known from K2)
+    int cap = std::min(std::max(p->max_block_slots, 256), SPMV_MAX_SMEM / 8);
+    cap = (cap + 63) & ~63;
+    k_spmv_stream<<<ceil_div(p->N, SPMV_ROWS), SPMV_ROWS, (size_t)cap * sizeof(double), st>>>(
+        p->N, p->nnz, cap, p->rowptr.get(), p->colidx.get(), vals, x, y);
     WS_CUDA(cudaGetLastError());
     count_launch(1);
 }
