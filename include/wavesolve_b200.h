@@ -142,6 +142,15 @@ int ws_spmv(const ws_pattern* p, const double* vals, const double* x, double* y,
 int ws_symbolic_create(const int32_t* h_dofs, int64_t Ne, int64_t N, const double* h_xy, int64_t Np,
                        int vert_col, int64_t vert_offset, int64_t first_class_start, int leaf_elems,
                        ws_symbolic** out);
+/* The same analysis on the DEVICE (the product path): dofs [Ne*6] and xy [Np*2] are device
+ * arrays; k-d bisection by per-level radix sorts, ownership by atomic min/max, boundaries by
+ * sort + unique of (front, unknown) keys.  The large index arrays stay in HBM and are handed to
+ * ws_solver_create without crossing PCIe; query / export work as for the host analysis.  The
+ * tree is the same balanced halving tree; ties at a split are broken by quantised coordinate
+ * and stable order, so individual leaves may differ from the host analysis of the same mesh. */
+int ws_symbolic_create_device(const int32_t* dofs, int64_t Ne, int64_t N, const double* xy, int64_t Np,
+                              int vert_col, int64_t vert_offset, int64_t first_class_start, int leaf_elems,
+                              ws_symbolic** out, int device, void* stream);
 int ws_symbolic_query(const ws_symbolic* s, int64_t* h_info, double* h_dinfo);
 int ws_symbolic_export(const ws_symbolic* s, int32_t* h_perm, int32_t* h_p, int32_t* h_q,
                        int64_t* h_start, int64_t* h_bndoff, int32_t* h_bnd, int32_t* h_rel);

@@ -19,20 +19,27 @@ def ws():
     return wavesolve_b200
 
 
+def _symbolic(sv, prob, fcs, leaf, where):
+    if where == "host":
+        return sv.Symbolic(prob.h_dofs, prob.h_xy, prob.N, fcs, leaf)
+    return sv.Symbolic.on_device(prob.dofs, prob.xy, prob.N, fcs, leaf)
+
+
 def _csr(prob, vals):
     indptr, indices = prob.pattern.export()
     return sp.csr_matrix((vals.cpu().numpy(), indices.cpu().numpy(), indptr.cpu().numpy()), shape=(prob.N,) * 2)
 
 
+@pytest.mark.parametrize("where", ["device", "host"])
 @pytest.mark.parametrize("ne,leaf,target", [(800, 16, None), (20000, 48, None), (60000, 48, None), (20000, 32, 1.447)])
-def test_scalar_factor_solve(ws, ne, leaf, target):
+def test_scalar_factor_solve(ws, ne, leaf, target, where):
     from wavesolve_b200 import fe_solver as fs, solver as sv
     mg = ws.meshgen
     mesh = mg.fiber_disc(ne, seed=3)
     prob = fs.ScalarProblem(mesh, mg.FIBER_IOR, K0)
     A, B = prob.assemble()
     sigma = (K0 * (max(mg.FIBER_IOR.values()) if target is None else target)) ** 2
-    sym = sv.Symbolic(prob.h_dofs, prob.h_xy, prob.N, 0, leaf)
+    sym = _symbolic(sv, prob, 0, leaf, where)
     S = sv.Solver(prob.pattern, sym)
     st = S.factor(A, B, sigma)
     M = (_csr(prob, A) - sigma * _csr(prob, B)).tocsc()
@@ -57,9 +64,10 @@ def test_scalar_factor_solve(ws, ne, leaf, target):
         assert np.linalg.norm(M @ x2[i] - b2[i]) <= 1e-11 * np.linalg.norm(b2[i])
 
 
+@pytest.mark.parametrize("where", ["device", "host"])
 @pytest.mark.parametrize("gen,arg,target", [("fiber_disc", 20000, None), ("structured_square", 60, None),
                                             ("fiber_disc", 20000, 1.448)])
-def test_vector_quasidefinite_factor_solve(ws, gen, arg, target):
+def test_vector_quasidefinite_factor_solve(ws, gen, arg, target, where):
     from wavesolve_b200 import fe_solver as fs, solver as sv
     mg = ws.meshgen
     mesh = getattr(mg, gen)(arg, order=1)
@@ -86,7 +94,7 @@ def test_vector_quasidefinite_factor_solve(ws, gen, arg, target):
     assert np.allclose(prob.apply_T(vd).cpu().numpy(), T @ v, rtol=1e-13, atol=1e-13)
     assert np.allclose(prob.apply_T(vd, transpose=True).cpu().numpy(), T.T @ v, rtol=1e-13, atol=1e-13)
     # factor M' (nodes first inside every front), solve M x = b as x = T M'^-1 T^T b
-    sym = sv.Symbolic(prob.h_dofs, prob.h_xy, N, Ntt, 32)
+    sym = _symbolic(sv, prob, Ntt, 32, where)
     S = sv.Solver(prob.pattern, sym)
     st = S.factor(Mq)
     b = np.random.default_rng(2).standard_normal(N)
@@ -107,3 +115,57 @@ def test_solver_rejects_use_before_factor(ws):
     S = sv.Solver(prob.pattern, sym)
     with pytest.raises(_lib.WavesolveB200Error):
         S.solve(torch.zeros(prob.N, dtype=torch.float64, device="cuda"))
+
+
+@pytest.mark.parametrize("kind,ne,leaf", [("scalar", 3000, 16), ("vector", 20000, 32), ("vector", 40, 48), ("scalar", 150000, 48)])
+def test_device_symbolic_structure(ws, kind, ne, leaf):
+    """The device analysis (K8a on the GPU) yields a valid nested dissection: a permutation, the
+    same balanced tree shape as the host model, sorted boundaries made of ancestor-owned
+    unknowns, parent-relative positions that point at the same unknown, and a fill within a few
+    percent of the host analysis of the same mesh (ties at the k-d splits are broken differently)."""
+    from wavesolve_b200 import fe_solver as fs, solver as sv
+    mg = ws.meshgen
+    if kind == "scalar":
+        prob = fs.ScalarProblem(mg.fiber_disc(ne, seed=5), mg.FIBER_IOR, K0)
+        fcs = 0
+    else:
+        mesh = mg.fiber_disc(ne, order=1, seed=5)
+        ws.get_unique_edges(mesh)
+        prob = fs.VectorProblem(mesh, mg.FIBER_IOR, K0)
+        fcs = prob.Ntt
+    d = sv.Symbolic.on_device(prob.dofs, prob.xy, prob.N, fcs, leaf)
+    h = sv.Symbolic(prob.h_dofs, prob.h_xy, prob.N, fcs, leaf)
+    assert (d.N, d.depth, d.nfronts) == (h.N, h.depth, h.nfronts)
+    assert abs(d.nnzL - h.nnzL) <= 0.05 * h.nnzL + 1000
+    E = d.export()
+    perm, p, q, start, bndoff, bnd, rel = (E[k] for k in ("perm", "p", "q", "start", "bndoff", "bnd", "rel"))
+    N = prob.N
+    assert np.array_equal(np.sort(perm), np.arange(N))
+    assert int(p[1:].sum()) == N and p[0] == 0
+    # fronts own contiguous, level-major (leaves first) index ranges
+    order = np.concatenate([np.arange(1 << l, 1 << (l + 1)) for l in range(d.depth, -1, -1)])
+    assert np.array_equal(start[order], np.concatenate([[0], np.cumsum(p[order])[:-1]]))
+    iperm = np.empty(N, dtype=np.int64)
+    iperm[perm] = np.arange(N)
+    owner = np.repeat(order, p[order])                      # owner front of every new index
+    assert np.array_equal(np.diff(bndoff)[1:], q[1:]) and q[1] == 0
+    # every element's unknowns are owned by ancestors-or-self of one leaf (its own)
+    dofs = prob.h_dofs.astype(np.int64)
+    own = owner[iperm[dofs]]                                # (Ne, 6) owner fronts
+    lvl = np.floor(np.log2(own)).astype(np.int64)
+    deepest = own[np.arange(len(own)), lvl.argmax(axis=1)]
+    for a in range(6):
+        sh = lvl.max(axis=1) - lvl[:, a]
+        assert np.array_equal(deepest >> sh, own[:, a])
+    for t in range(1, d.nfronts):
+        b = bnd[bndoff[t]:bndoff[t + 1]]
+        if len(b) == 0:
+            continue
+        assert np.all(np.diff(b) > 0)
+        ob = owner[b]
+        lt = int(np.log2(t))
+        lo = np.floor(np.log2(ob)).astype(np.int64)
+        assert np.all(lo < lt) and np.array_equal(t >> (lt - lo), ob)      # owned by proper ancestors
+        par = t >> 1
+        front_par = np.concatenate([np.arange(start[par], start[par] + p[par]), bnd[bndoff[par]:bndoff[par + 1]]])
+        assert np.array_equal(front_par[rel[bndoff[t]:bndoff[t + 1]]], b)

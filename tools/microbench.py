@@ -41,7 +41,8 @@ def main():
     mesh = mg.fiber_disc(a.elements, order=2, seed=0, spatial_sort=bool(a.sorted))
     prob = fs.ScalarProblem(mesh, mg.FIBER_IOR, k)
     ne, nnz, N, npts = mesh.num_elements, prob.pattern.nnz, prob.N, mesh.points.shape[0]
-    ms = timeit(torch, prob.assemble)
+    AB = prob.assemble()
+    ms = timeit(torch, lambda: prob.assemble(out=AB))
     by = ne * (24 + 8) + 16 * (N - 0) * 0 + 16 * (npts) + 16 * nnz
     out["scalar_assemble_ms"] = ms
     out["scalar_assemble_GBs"] = by / ms / 1e6
@@ -55,13 +56,15 @@ def main():
     out["scalar_spmv_frac"] = (12 * nnz + 20 * N) / ms / 1e6 / peak
     ms = timeit(torch, lambda: fs.DevicePattern(prob.dofs, prob.N).close(), n=5, warm=1)
     out["scalar_pattern_ms"] = ms
-    del prob, A, B
+    del prob, A, B, AB
     # ---- vector
     mesh = mg.fiber_disc(a.elements, order=1, seed=0, spatial_sort=bool(a.sorted))
     ws.get_unique_edges(mesh)
     prob = fs.VectorProblem(mesh, mg.FIBER_IOR, k)
     ne, nnz, N, npts = mesh.num_elements, prob.pattern.nnz, prob.N, mesh.points.shape[0]
-    ms = timeit(torch, prob.assemble)
+    AB = prob.assemble()
+    ms = timeit(torch, lambda: prob.assemble(out=AB))
+    del AB
     by = ne * 20 + 16 * npts + 16 * nnz
     out["vector_assemble_ms"] = ms
     out["vector_assemble_GBs"] = by / ms / 1e6
@@ -82,7 +85,7 @@ def main():
     out["vector_pattern_ms"] = timeit(torch, lambda: fs.DevicePattern(prob.dofs, prob.N).close(), n=5, warm=1)
     if a.solver:
         Mq = prob.assemble_qd(sigma)
-        sym = sv.Symbolic(prob.h_dofs, prob.h_xy, prob.N, prob.Ntt)
+        sym = sv.Symbolic.on_device(prob.dofs, prob.xy, prob.N, prob.Ntt)
         out["symbolic_ms"] = [round(v * 1e3, 1) for v in (sym.t_kd, sym.t_order, sym.t_bnd)]
         S = sv.Solver(prob.pattern, sym)
         st = S.factor(Mq)

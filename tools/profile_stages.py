@@ -19,6 +19,7 @@ def main():
     ap.add_argument("--leaf", type=int, default=0)
     ap.add_argument("--reps", type=int, default=2)
     ap.add_argument("--nsolves", type=int, default=20)
+    ap.add_argument("--host-symbolic", action="store_true")
     a = ap.parse_args()
     import torch
     import wavesolve_b200 as ws
@@ -55,8 +56,8 @@ def main():
             Mq = prob.assemble_qd(sigma)
             T["assemble_qd"] = sync() - t0
         t0 = sync()
-        sym = sv.Symbolic(prob.h_dofs, prob.h_xy, prob.N, prob.first_class_start, leaf)
-        T["symbolic(host)"] = sync() - t0
+        sym = (sv.Symbolic if a.host_symbolic else sv.Symbolic.on_device)(*((prob.h_dofs, prob.h_xy) if a.host_symbolic else (prob.dofs, prob.xy)), prob.N, prob.first_class_start, leaf)
+        T["symbolic"] = sync() - t0
         T["sym.kd(1)"], T["sym.order(1)"], T["sym.bnd(1)"] = sym.t_kd, sym.t_order, sym.t_bnd
         t0 = sync()
         S = sv.Solver(prob.pattern, sym)

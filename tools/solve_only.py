@@ -29,7 +29,7 @@ def main():
     prob = fs.VectorProblem(mesh, mg.FIBER_IOR, k)
     A, B = prob.assemble()
     Mq = prob.assemble_qd(sigma)
-    sym = sv.Symbolic(prob.h_dofs, prob.h_xy, prob.N, prob.Ntt, a.leaf or sv.DEFAULT_LEAF_ELEMS)
+    sym = sv.Symbolic.on_device(prob.dofs, prob.xy, prob.N, prob.Ntt, a.leaf or sv.DEFAULT_LEAF_ELEMS)
     S = sv.Solver(prob.pattern, sym)
     for _ in range(a.factors):
         st = S.factor(Mq)

@@ -21,6 +21,7 @@ SOURCES = {
     "ws_assemble.cu": ["-fmad=false"],
     "ws_spmv.cu": [],
     "ws_symbolic.cu": [],
+    "ws_symbolic_dev.cu": [],
     "ws_factor.cu": [],
     "ws_eig.cu": [],
 }

@@ -38,6 +38,8 @@ _SIGNATURES = {
     "ws_axpby": (c_int, [c_i64, C.c_double, c_vp, C.c_double, c_vp, c_int, c_vp]),
     "ws_spmv": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_vp]),
     "ws_symbolic_create": (c_int, [c_vp, c_i64, c_i64, c_vp, c_i64, c_int, c_i64, c_i64, c_int, C.POINTER(c_vp)]),
+    "ws_symbolic_create_device": (c_int, [c_vp, c_i64, c_i64, c_vp, c_i64, c_int, c_i64, c_i64, c_int, C.POINTER(c_vp),
+                                          c_int, c_vp]),
     "ws_symbolic_query": (c_int, [c_vp, c_vp, c_vp]),
     "ws_symbolic_export": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "ws_symbolic_destroy": (c_int, [c_vp]),

@@ -339,17 +339,27 @@ struct VectorP1 {
 // the arithmetic of the current one starts (software prefetch: the incidence -> connectivity ->
 // coordinates chain is three dependent loads deep), and the row's slots live in a shared-memory
 // tile that is written back with coalesced stores.
-template <class Op, bool WRITE_A, bool PREFETCH>
-__global__ void __launch_bounds__(ROWS_PER_CTA)
+// SMEM = true: every 128-row block of the launch fits the tile (the normal case) and the
+// accumulators are addressed in the shared window (LDS/STS, not generic LD/ST); SMEM = false is
+// the fallback for unusually dense blocks, which accumulate straight into the (zeroed) output.
+// MINB = resident CTAs per SM the register allocation is sized for.
+template <class Op, bool WRITE_A, bool PREFETCH, bool SMEM, int MINB>
+__global__ void __launch_bounds__(ROWS_PER_CTA, MINB)
 k_assemble_rows(RowCtx cx, Op op, double* __restrict__ A, double* __restrict__ B) {
     extern __shared__ double tile[];
     const int64_t r0 = (cx.first_block + blockIdx.x) * ROWS_PER_CTA;
     const int64_t r1 = min(r0 + ROWS_PER_CTA, cx.N);
     const int s0 = cx.rowptr[r0], s1 = cx.rowptr[r1];
     const int S = s1 - s0;
-    const bool in_smem = S <= cx.cap;
-    double* tB = in_smem ? tile : B + s0;
-    double* tA = in_smem ? tile + cx.cap : (WRITE_A ? A + s0 : nullptr);
+    double* tB;
+    double* tA;
+    if (SMEM) {
+        tB = tile;
+        tA = tile + cx.cap;
+    } else {
+        tB = B + s0;
+        tA = WRITE_A ? A + s0 : nullptr;
+    }
     for (int t = threadIdx.x; t < S; t += ROWS_PER_CTA) {
         tB[t] = 0.0;
         if (WRITE_A) tA[t] = 0.0;
@@ -392,7 +402,7 @@ k_assemble_rows(RowCtx cx, Op op, double* __restrict__ A, double* __restrict__ B
             }
         }
     }
-    if (in_smem) {
+    if (SMEM) {
         __syncthreads();
         for (int t = threadIdx.x; t < S; t += ROWS_PER_CTA) {
             B[s0 + t] = tB[t];
@@ -401,6 +411,41 @@ k_assemble_rows(RowCtx cx, Op op, double* __restrict__ A, double* __restrict__ B
     }
 }
 
+struct AsmTuning {
+    int n_ranges, prefetch, minb;
+};
+
+static const AsmTuning& asm_tuning() {
+    static AsmTuning t = [] {
+        AsmTuning v;
+        const char* e = getenv("WS_ASM_RANGES");
+        v.n_ranges = e ? std::max(1, std::min(atoi(e), (int)ws_pattern::NRANGE)) : 1;
+        const char* f = getenv("WS_ASM_PREFETCH");
+        v.prefetch = f ? atoi(f) : 0;
+        const char* m = getenv("WS_ASM_MINB");
+        v.minb = m ? atoi(m) : 4;
+        return v;
+    }();
+    return t;
+}
+
+template <class Op, bool WRITE_A>
+struct AsmKernels {
+    using Fn = void (*)(RowCtx, Op, double*, double*);
+    // [prefetch][minb index: 4, 6, 8]
+    static Fn smem(int prefetch, int minb) {
+        if (prefetch) {
+            if (minb >= 8) return k_assemble_rows<Op, WRITE_A, true, true, 8>;
+            if (minb >= 6) return k_assemble_rows<Op, WRITE_A, true, true, 6>;
+            return k_assemble_rows<Op, WRITE_A, true, true, 4>;
+        }
+        if (minb >= 8) return k_assemble_rows<Op, WRITE_A, false, true, 8>;
+        if (minb >= 6) return k_assemble_rows<Op, WRITE_A, false, true, 6>;
+        return k_assemble_rows<Op, WRITE_A, false, true, 4>;
+    }
+    static Fn global() { return k_assemble_rows<Op, WRITE_A, false, false, 4>; }
+};
+
 // The row blocks are launched in up to 16 contiguous groups, each with a shared-memory tile
 // sized for its own densest block: sparse stretches of the matrix (edge rows, mid-side rows)
 // then run at a much higher occupancy than the dense ones (vertex / node rows).
@@ -408,31 +453,27 @@ template <class Op, bool WRITE_A>
 static void launch_rows(const ws_pattern* p, const Op& op, double* A, double* B, cudaStream_t st) {
     if (p->N == 0 || p->nnz == 0) return;
     const int per_slot = 8 * (WRITE_A ? 2 : 1);
-    static int n_ranges = -1, prefetch = -1;
-    if (n_ranges < 0) {
-        const char* e = getenv("WS_ASM_RANGES");
-        n_ranges = e ? std::max(1, std::min(atoi(e), (int)ws_pattern::NRANGE)) : 1;
-        const char* f = getenv("WS_ASM_PREFETCH");
-        prefetch = f ? atoi(f) : 0;
-    }
-    auto kern = prefetch ? k_assemble_rows<Op, WRITE_A, true> : k_assemble_rows<Op, WRITE_A, false>;
+    const AsmTuning& tn = asm_tuning();
+    auto kern = AsmKernels<Op, WRITE_A>::smem(tn.prefetch, tn.minb);
+    auto kern_g = AsmKernels<Op, WRITE_A>::global();
     static bool configured = false;
     if (!configured) {
-        WS_CUDA(cudaFuncSetAttribute(k_assemble_rows<Op, WRITE_A, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_TILE_BYTES));
-        WS_CUDA(cudaFuncSetAttribute(k_assemble_rows<Op, WRITE_A, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_TILE_BYTES));
+        WS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_TILE_BYTES));
         configured = true;
     }
     const int nblocks = ceil_div(p->N, ROWS_PER_CTA);
     const int per_group = std::max(1, ceil_div(nblocks, ws_pattern::NRANGE));
-    const int groups_per_launch = ws_pattern::NRANGE / n_ranges;
+    const int groups_per_launch = ws_pattern::NRANGE / tn.n_ranges;
     for (int g = 0; g * per_group < nblocks; g += groups_per_launch) {
         const int b0 = g * per_group, b1 = std::min(nblocks, (g + groups_per_launch) * per_group);
         int cap = 32;
         for (int gg = g; gg < g + groups_per_launch && gg < ws_pattern::NRANGE; ++gg) cap = std::max(cap, p->range_block_slots[gg]);
         cap = (cap + 31) & ~31;
-        if ((size_t)cap * per_slot > MAX_TILE_BYTES) cap = MAX_TILE_BYTES / per_slot;
         RowCtx cx{p->rowptr.get(), p->incptr.get(), p->inc.get(), p->pos.get(), p->N, b0, cap};
-        kern<<<b1 - b0, ROWS_PER_CTA, (size_t)cap * per_slot, st>>>(cx, op, A, B);
+        if ((size_t)cap * per_slot <= MAX_TILE_BYTES)
+            kern<<<b1 - b0, ROWS_PER_CTA, (size_t)cap * per_slot, st>>>(cx, op, A, B);
+        else
+            kern_g<<<b1 - b0, ROWS_PER_CTA, 0, st>>>(cx, op, A, B);   // a block denser than the largest tile
         count_launch(1);
     }
     WS_CUDA(cudaGetLastError());

@@ -723,6 +723,12 @@ static void upload(DevBuf<T>& buf, const std::vector<T>& v, cudaStream_t st) {
     if (!v.empty()) WS_CUDA(cudaMemcpyAsync(buf.get(), v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, st));
 }
 
+template <class T>
+static void clone(DevBuf<T>& dst, const DevBuf<T>& src, size_t n, cudaStream_t st) {
+    dst.alloc(n, st);
+    if (n) WS_CUDA(cudaMemcpyAsync(dst.get(), src.get(), n * sizeof(T), cudaMemcpyDeviceToDevice, st));
+}
+
 static FrontView view(const ws_solver* s) {
     return FrontView{s->fr_p.get(), s->fr_q.get(), s->fr_start.get(), s->fr_Loff.get(), s->fr_Uoff.get(),
                      s->fr_woff.get(), s->fr_bndoff.get(), s->bnd.get(), s->rel.get()};
@@ -1033,9 +1039,20 @@ int ws_solver_create(const ws_pattern* p, const ws_symbolic* sym, ws_solver** ou
         s->nnz = p->nnz;
         s->nfronts = Y.nfronts;
         s->depth = Y.depth;
-        upload(s->perm, Y.perm, st);
-        upload(s->iperm, Y.iperm, st);
-        upload(s->node_of_new, Y.node_of_new, st);
+        if (sym->on_device) {
+            WS_REQUIRE(sym->device == device, "symbolic analysis lives on another device");
+            clone(s->perm, sym->d_perm, (size_t)Y.N, st);
+            clone(s->iperm, sym->d_iperm, (size_t)Y.N, st);
+            clone(s->node_of_new, sym->d_node_of_new, (size_t)Y.N, st);
+            clone(s->bnd, sym->d_bnd, (size_t)sym->sumq, st);
+            clone(s->rel, sym->d_rel, (size_t)sym->sumq, st);
+        } else {
+            upload(s->perm, Y.perm, st);
+            upload(s->iperm, Y.iperm, st);
+            upload(s->node_of_new, Y.node_of_new, st);
+            upload(s->bnd, Y.bnd, st);
+            upload(s->rel, Y.rel, st);
+        }
         upload(s->fr_p, Y.p, st);
         upload(s->fr_q, Y.q, st);
         upload(s->fr_start, Y.start, st);
@@ -1043,8 +1060,6 @@ int ws_solver_create(const ws_pattern* p, const ws_symbolic* sym, ws_solver** ou
         upload(s->fr_Uoff, Y.Uoff, st);
         upload(s->fr_woff, Y.woff, st);
         upload(s->fr_bndoff, Y.bndoff, st);
-        upload(s->bnd, Y.bnd, st);
-        upload(s->rel, Y.rel, st);
         s->L.alloc(Y.Ltotal, st);
         s->S.alloc(Y.Ltotal, st);
         s->T.alloc(Y.Ltotal, st);

@@ -44,8 +44,15 @@ struct Symbolic {
 
 }  // namespace ws
 
+// Host analysis (ws_symbolic_create): every array of S is filled on the host.
+// Device analysis (ws_symbolic_create_device): the per-front arrays of S (p, q, start, bndoff,
+// Loff, Uoff, woff) are on the host, the large index arrays live in the d_* buffers only.
 struct ws_symbolic {
     ws::Symbolic S;
+    bool on_device = false;
+    int device = 0;
+    int64_t sumq = 0;
+    ws::DevBuf<int32_t> d_perm, d_iperm, d_node_of_new, d_bnd, d_rel;
 };
 
 namespace ws {

@@ -358,7 +358,8 @@ int ws_symbolic_query(const ws_symbolic* s, int64_t* h_info, double* h_dinfo) {
     const Symbolic& S = s->S;
     if (h_info) {
         h_info[0] = S.N; h_info[1] = S.depth; h_info[2] = S.nfronts; h_info[3] = S.nnzL;
-        h_info[4] = S.Utotal; h_info[5] = S.maxfront; h_info[6] = S.maxp; h_info[7] = (int64_t)S.bnd.size();
+        h_info[4] = S.Utotal; h_info[5] = S.maxfront; h_info[6] = S.maxp;
+        h_info[7] = s->on_device ? s->sumq : (int64_t)S.bnd.size();
     }
     if (h_dinfo) {
         h_dinfo[0] = S.flops; h_dinfo[1] = S.t_kd; h_dinfo[2] = S.t_order; h_dinfo[3] = S.t_bnd;
@@ -371,6 +372,14 @@ int ws_symbolic_export(const ws_symbolic* s, int32_t* h_perm, int32_t* h_p, int3
     WS_API_BEGIN
     WS_REQUIRE(s, "symbolic == NULL");
     const Symbolic& S = s->S;
+    if (s->on_device) {
+        DeviceGuard g(s->device);
+        if (h_perm) WS_CUDA(cudaMemcpy(h_perm, s->d_perm.get(), S.N * sizeof(int32_t), cudaMemcpyDeviceToHost));
+        if (h_bnd && s->sumq) WS_CUDA(cudaMemcpy(h_bnd, s->d_bnd.get(), s->sumq * sizeof(int32_t), cudaMemcpyDeviceToHost));
+        if (h_rel && s->sumq) WS_CUDA(cudaMemcpy(h_rel, s->d_rel.get(), s->sumq * sizeof(int32_t), cudaMemcpyDeviceToHost));
+        h_perm = nullptr;
+        h_bnd = h_rel = nullptr;
+    }
     if (h_perm) std::copy(S.perm.begin(), S.perm.end(), h_perm);
     if (h_p) std::copy(S.p.begin(), S.p.end(), h_p);
     if (h_q) std::copy(S.q.begin(), S.q.end(), h_q);
@@ -383,7 +392,12 @@ int ws_symbolic_export(const ws_symbolic* s, int32_t* h_perm, int32_t* h_p, int3
 
 int ws_symbolic_destroy(ws_symbolic* s) {
     WS_API_BEGIN
-    delete s;
+    if (s && s->on_device) {
+        DeviceGuard g(s->device);
+        delete s;
+    } else {
+        delete s;
+    }
     WS_API_END
 }
 

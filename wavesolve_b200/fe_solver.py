@@ -148,12 +148,14 @@ class ScalarProblem:
         with torch.cuda.device(self.dev):
             self.k2n2.copy_(torch.from_numpy(k2), non_blocking=False)
 
-    def assemble(self, fast=False):
+    def assemble(self, fast=False, out=None):
         """A, B values on the pattern.  fast=True: reciprocal arithmetic (<= 2 ulp off the
-        reference's), used inside the solve pipeline only."""
+        reference's), used inside the solve pipeline only.  ``out=(A, B)``: reuse value arrays
+        (re-assembly per wavelength on a shared pattern, K11)."""
         p = self.build_pattern()
-        A = torch.empty(p.nnz, dtype=torch.float64, device=self.dev)
-        B = torch.empty(p.nnz, dtype=torch.float64, device=self.dev)
+        A, B = out if out is not None else (torch.empty(p.nnz, dtype=torch.float64, device=self.dev),
+                                            torch.empty(p.nnz, dtype=torch.float64, device=self.dev))
+        assert A.numel() == p.nnz and B.numel() == p.nnz and A.is_contiguous() and B.is_contiguous()
         if self.order == 1:
             _lib.check(_lib.lib().ws_assemble_scalar_p1(p.handle, _dev.ptr(self.xy), _dev.ptr(self.dofs),
                                                         _dev.ptr(self.k2n2), _dev.ptr(A), _dev.ptr(B),
@@ -224,10 +226,11 @@ class VectorProblem:
             self.pattern = DevicePattern(self.dofs, self.N) if build_pattern else None
         self.h2d_bytes = xy.nbytes + tris.nbytes + dofs.nbytes + k2.nbytes + self.h_edges.nbytes
 
-    def assemble(self, transpose=False, fast=False):
+    def assemble(self, transpose=False, fast=False, out=None):
         p = self.build_pattern()
-        A = torch.empty(p.nnz, dtype=torch.float64, device=self.dev)
-        B = torch.empty(p.nnz, dtype=torch.float64, device=self.dev)
+        A, B = out if out is not None else (torch.empty(p.nnz, dtype=torch.float64, device=self.dev),
+                                            torch.empty(p.nnz, dtype=torch.float64, device=self.dev))
+        assert A.numel() == p.nnz and B.numel() == p.nnz and A.is_contiguous() and B.is_contiguous()
         _lib.check(_lib.lib().ws_assemble_vector_p1(p.handle, _dev.ptr(self.xy), _dev.ptr(self.tris),
                                                     _dev.ptr(self.k2n2), self.Ntt, _dev.ptr(A),
                                                     _dev.ptr(B),
@@ -438,17 +441,15 @@ def solve_vector_resident(prob, sigma, Nmax, leaf_elems=None, symbolic=None, sol
     device tensors (w, V) and diagnostics.  ``solver``: a Solver already bound to this pattern
     (sweeps reuse the task plan and the front storage across wavelengths)."""
     from . import solver as _sv
-    fut = None
-    if symbolic is None and solver is None:
-        # host analysis in a worker thread, overlapped with the pattern build and the assembly
-        fut = _sv.SymbolicFuture(prob.h_dofs, prob.h_xy, prob.N, prob.Ntt,
-                                 leaf_elems or _sv.DEFAULT_LEAF_ELEMS)
     prob.build_pattern()
     Mq, B = prob.assemble_qd(sigma, with_B=True, fast=True)
     if solver is not None:
         S = solver
     else:
-        S = _sv.Solver(prob.pattern, symbolic if fut is None else fut.result())
+        if symbolic is None:
+            symbolic = _sv.Symbolic.on_device(prob.dofs, prob.xy, prob.N, prob.Ntt,
+                                              leaf_elems or _sv.DEFAULT_LEAF_ELEMS)
+        S = _sv.Solver(prob.pattern, symbolic)
     try:
         st = S.factor(Mq)
         wd, Vd, info = _eig_device(prob.pattern, S, B, sigma, 1, Nmax, prob.N, prob.dev,
@@ -463,15 +464,14 @@ def solve_vector_resident(prob, sigma, Nmax, leaf_elems=None, symbolic=None, sol
 def solve_scalar_resident(prob, sigma, Nmax, leaf_elems=None, symbolic=None, solver=None, out=None):
     """Device part of the scalar solve on a resident ScalarProblem (see solve_vector_resident)."""
     from . import solver as _sv
-    fut = None
-    if symbolic is None and solver is None:
-        fut = _sv.SymbolicFuture(prob.h_dofs, prob.h_xy, prob.N, 0, leaf_elems or _sv.DEFAULT_LEAF_ELEMS)
     prob.build_pattern()
     A, B = prob.assemble(fast=True)
     if solver is not None:
         S = solver
     else:
-        S = _sv.Solver(prob.pattern, symbolic if fut is None else fut.result())
+        if symbolic is None:
+            symbolic = _sv.Symbolic.on_device(prob.dofs, prob.xy, prob.N, 0, leaf_elems or _sv.DEFAULT_LEAF_ELEMS)
+        S = _sv.Solver(prob.pattern, symbolic)
     try:
         st = S.factor(A, B, sigma)
         wd, Vd, info = _eig_device(prob.pattern, S, B, sigma, 0, Nmax, prob.N, prob.dev, out=out)

@@ -1,5 +1,5 @@
-"""Python handles for the sparse direct solver (symbolic analysis on the host, numeric
-factorisation and solves on the device) and the Krylov eigensolver."""
+"""Python handles for the sparse direct solver (symbolic analysis, numeric factorisation and
+solves on the device; a host model of the symbolic analysis for the CPU tests)."""
 from __future__ import annotations
 
 import ctypes as C
@@ -29,9 +29,33 @@ class Symbolic:
                                                  int(first_class_start) if vector else 0,
                                                  int(first_class_start), int(leaf_elems), C.byref(h)))
         self.handle = h
+        self._query()
+
+    @classmethod
+    def on_device(cls, dofs_d, xy_d, N: int, first_class_start: int = 0, leaf_elems: int = DEFAULT_LEAF_ELEMS):
+        """The same analysis run on the device (``ws_symbolic_create_device``): ``dofs_d`` (Ne,6)
+        int32 and ``xy_d`` (Np,2) float64 CUDA tensors.  This is what the solve pipeline uses; the
+        host constructor above is the model the CPU tests check it against."""
+        from . import device as _dev
+        assert dofs_d.is_cuda and xy_d.is_cuda and dofs_d.is_contiguous() and xy_d.is_contiguous()
+        assert dofs_d.dim() == 2 and dofs_d.shape[1] == 6 and xy_d.dim() == 2 and xy_d.shape[1] == 2
+        self = object.__new__(cls)
+        vector = first_class_start > 0
+        h = C.c_void_p()
+        dev = dofs_d.device
+        _lib.check(_lib.lib().ws_symbolic_create_device(_dev.ptr(dofs_d), dofs_d.shape[0], int(N), _dev.ptr(xy_d),
+                                                        xy_d.shape[0], 3 if vector else 0,
+                                                        int(first_class_start) if vector else 0,
+                                                        int(first_class_start), int(leaf_elems), C.byref(h),
+                                                        dev.index, _dev.stream_ptr(dev)))
+        self.handle = h
+        self._query()
+        return self
+
+    def _query(self):
         info = np.zeros(8, dtype=np.int64)
         dinfo = np.zeros(4, dtype=np.float64)
-        _lib.check(_lib.lib().ws_symbolic_query(h, info.ctypes.data, dinfo.ctypes.data))
+        _lib.check(_lib.lib().ws_symbolic_query(self.handle, info.ctypes.data, dinfo.ctypes.data))
         (self.N, self.depth, self.nfronts, self.nnzL, self.Utotal, self.maxfront, self.maxp,
          self.sumq) = [int(x) for x in info]
         self.flops, self.t_kd, self.t_order, self.t_bnd = [float(x) for x in dinfo]

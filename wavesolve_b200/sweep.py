@@ -179,10 +179,9 @@ class _MeshContext:
         else:
             self.prob = fs.ScalarProblem(mesh, IOR_dict, k, device, build_pattern=False)
             fcs = 0
-        fut = sv.SymbolicFuture(self.prob.h_dofs, self.prob.h_xy, self.prob.N, fcs,
-                                leaf_elems or sv.DEFAULT_LEAF_ELEMS)
         self.prob.build_pattern()
-        self.symbolic = fut.result()
+        self.symbolic = sv.Symbolic.on_device(self.prob.dofs, self.prob.xy, self.prob.N, fcs,
+                                              leaf_elems or sv.DEFAULT_LEAF_ELEMS)
         self.solver = sv.Solver(self.prob.pattern, self.symbolic)
 
     def close(self):
