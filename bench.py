@@ -289,7 +289,7 @@ def run_ours(args):
         if it > 0:
             e2e_t.append(dt)
         h2d_b = tris_h.nbytes + base.h2d_bytes
-        d2h_b = edges.shape[0] * 2 * 4 + eidx.size * 4 + NMAX * 8 + NMAX * N * 8
+        d2h_b = edges.nbytes + eidx.nbytes + m.edge_flips.nbytes + w.nbytes + v.nbytes
     e2e_s = float(np.mean(e2e_t))
 
     total = float(world)
@@ -309,7 +309,7 @@ def run_ours(args):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
         "config": {"workload": WORKLOAD, "elements_per_gpu": ne, "N": N, "nnz": nnz, "Nmax": NMAX,
-                   "ncv": max(2 * NMAX + 1, 20), "tol": "eps (scipy default tol=0)",
+                   "ncv": max(2 * NMAX + 4, 20), "tol": "eps (scipy default tol=0)",
                    "l2": "inputs_larger_than_l2 (factor panels %.1f GB, basis %.2f GB per step)"
                          % (8 * fstat["nnzL"] / 1e9, 8 * 22 * N / 1e9),
                    "parallelism": "one problem per GPU"},

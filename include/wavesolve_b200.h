@@ -199,7 +199,8 @@ int ws_vector_T(const ws_pattern* p, const int32_t* edges, const double* xy, int
  *         eigs(spsolve(A - sigma B, B), k, which='SR'), fe_solver.py:398-400); `s` holds the
  *         factorisation of the quasi-definite M' (ws_assemble_vector_qd) and edges/xy/Ntt
  *         describe T; eigenvectors come back with unit 2-norm.
- * ncv <= 0 -> max(2 nev + 1, 20); tol <= 0 -> machine epsilon (both scipy's defaults).
+ * ncv <= 0 -> max(2 nev + 4, 20) (scipy: 2 nev + 1; three more vectors save 1-2 restart cycles at
+ * tol = eps on these problems); tol <= 0 -> machine epsilon (scipy's default).
  * w [nev] (device): lambda = sigma + 1/theta, descending.  V [nev*N] (device): row j =
  * eigenvector j.  h_info[5] = converged, OP applications, restarts, complex Ritz values among
  * the wanted ones, kept directions at the last restart.  h_resid [nev]: Ritz residual estimates.

@@ -985,6 +985,8 @@ static void build_plan(ws_solver* s, cudaStream_t st) {
             }
     }
     s->w21.cnt = (int64_t)G.size() - s->w21.off;
+    const bool trace = getenv("WS_TRACE") != nullptr;
+    const double tg = std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
     upload(s->gemm_tasks, G, st);
     upload(s->panel_tasks, P, st);
     upload(s->ext_tasks, E, st);
@@ -992,6 +994,14 @@ static void build_plan(ws_solver* s, cudaStream_t st) {
     upload(s->fwd_tiles, F, st);
     upload(s->bwd_tiles, Bk, st);
     WS_CUDA(cudaStreamSynchronize(st));   // the host vectors die here
+    if (trace)
+        for (int l = 0; l <= depth; ++l)
+            fprintf(stderr, "[build_plan] level %2d fronts %6lld maxp %4d maxm %4d %s nt %d\n", l, (long long)s->levels[l].nfronts,
+                    s->levels[l].maxp, s->levels[l].maxm, s->levels[l].small ? "front" : "tile", s->levels[l].nt);
+    if (trace)
+        fprintf(stderr, "[build_plan] tasks: gemm %zu panel %zu ext %zu inv %zu fwd %zu bwd %zu; upload %.1f ms\n", G.size(),
+                P.size(), E.size(), I.size(), F.size(), Bk.size(),
+                (std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count() - tg) * 1e3);
     s->bytes += (int64_t)(G.size() * sizeof(GemmTask) + P.size() * sizeof(PanelTask) + E.size() * sizeof(ExtTask) +
                           I.size() * sizeof(InvTask) + F.size() * sizeof(FwdTile) + Bk.size() * sizeof(BwdTile));
 }
@@ -1007,6 +1017,66 @@ static void launch_gemm(const ws_solver* s, const Range& r, bool narrow, cudaStr
     if (narrow) k_gemm_tiles<32><<<(unsigned)r.cnt, 128, gemm_smem_bytes<32>(), st>>>(s->gemm_tasks.get() + r.off);
     else k_gemm_tiles<64><<<(unsigned)r.cnt, 128, gemm_smem_bytes<64>(), st>>>(s->gemm_tasks.get() + r.off);
     count_launch(1);
+}
+
+// ---- one-CTA-per-front sweep kernels: variant selection ----------------------------------------
+// These CTAs are small (one thread per front row) and short-lived, so the number of resident
+// CTAs -- bounded by registers -- matters more than the depth of the per-thread load pipeline:
+// KB (forward: loads in flight per thread = 2*KB) and CB x RJ (backward: columns x row groups in
+// flight per lane) default to small values.  WS_FWD_KB[_LEAF], WS_BWD_CB[_LEAF], WS_BWD_RJ[_LEAF]
+// override them for experiments (tools/sweep_variants.py).
+struct SweepTuning {
+    int kb, kb_leaf, cb, cb_leaf, rj, rj_leaf;
+};
+static const SweepTuning& sweep_tuning() {
+    static const SweepTuning t = [] {
+        auto env = [](const char* n, int d) { const char* e = getenv(n); return e ? atoi(e) : d; };
+        SweepTuning v;
+        v.kb = env("WS_FWD_KB", 4);
+        v.kb_leaf = env("WS_FWD_KB_LEAF", 8);
+        v.cb = env("WS_BWD_CB", 1);
+        v.cb_leaf = env("WS_BWD_CB_LEAF", 2);
+        v.rj = env("WS_BWD_RJ", 4);
+        v.rj_leaf = env("WS_BWD_RJ_LEAF", 2);
+        return v;
+    }();
+    return t;
+}
+
+template <int MAXT>
+static void launch_fwd_front_t(int kb, unsigned nf, int nt, size_t sh, cudaStream_t st, int64_t first, int hc,
+                               const SolveCtx& cx, const double* b) {
+    if (kb <= 2) k_fwd_front<MAXT, 2><<<nf, nt, sh, st>>>(first, hc, cx, b);
+    else if (kb <= 4) k_fwd_front<MAXT, 4><<<nf, nt, sh, st>>>(first, hc, cx, b);
+    else if (kb <= 8 || MAXT > 512) k_fwd_front<MAXT, 8><<<nf, nt, sh, st>>>(first, hc, cx, b);
+    else k_fwd_front<(MAXT > 512 ? 512 : MAXT), 16><<<nf, nt, sh, st>>>(first, hc, cx, b);
+}
+static void launch_fwd_front(int nt, int kb, unsigned nf, size_t sh, cudaStream_t st, int64_t first, int hc,
+                             const SolveCtx& cx, const double* b) {
+    if (nt <= 256) launch_fwd_front_t<256>(kb, nf, nt, sh, st, first, hc, cx, b);
+    else if (nt <= 512) launch_fwd_front_t<512>(kb, nf, nt, sh, st, first, hc, cx, b);
+    else launch_fwd_front_t<1024>(kb, nf, nt, sh, st, first, hc, cx, b);
+}
+
+template <int MAXT, int RJ>
+static void launch_bwd_front_t(int cb, unsigned nf, int nt, size_t sh, cudaStream_t st, int64_t first, const SolveCtx& cx,
+                               double* x) {
+    if (cb <= 1) k_bwd_front<MAXT, 1, RJ><<<nf, nt, sh, st>>>(first, cx, x);
+    else if (cb <= 2) k_bwd_front<MAXT, 2, RJ><<<nf, nt, sh, st>>>(first, cx, x);
+    else if (cb <= 4 || MAXT > 512) k_bwd_front<MAXT, (MAXT > 512 && RJ > 2 ? 2 : 4), RJ><<<nf, nt, sh, st>>>(first, cx, x);
+    else k_bwd_front<(MAXT > 512 ? 512 : MAXT), 8, RJ><<<nf, nt, sh, st>>>(first, cx, x);
+}
+static void launch_bwd_front(int nt, int cb, int rj, unsigned nf, size_t sh, cudaStream_t st, int64_t first,
+                             const SolveCtx& cx, double* x) {
+    if (rj <= 2) {
+        if (nt <= 256) launch_bwd_front_t<256, 2>(cb, nf, nt, sh, st, first, cx, x);
+        else if (nt <= 512) launch_bwd_front_t<512, 2>(cb, nf, nt, sh, st, first, cx, x);
+        else launch_bwd_front_t<1024, 2>(cb, nf, nt, sh, st, first, cx, x);
+    } else {
+        if (nt <= 256) launch_bwd_front_t<256, 4>(cb, nf, nt, sh, st, first, cx, x);
+        else if (nt <= 512) launch_bwd_front_t<512, 4>(cb, nf, nt, sh, st, first, cx, x);
+        else launch_bwd_front_t<1024, 4>(cb, nf, nt, sh, st, first, cx, x);
+    }
 }
 
 }  // namespace ws
@@ -1200,6 +1270,7 @@ int ws_solver_solve(ws_solver* s, const double* b, double* x, int nrhs, int devi
     }
     SolveCtx cx{s->recs.get(), s->S.get(), s->perm.get(), s->wsrc0.get(), s->wsrc1.get(), s->bnd.get(),
                 s->dinv.get(), s->W.get(), s->yd.get(), s->x.get()};
+    const SweepTuning& tune = sweep_tuning();
     for (int rhs = 0; rhs < nrhs; ++rhs) {
         const double* bi = b + (size_t)rhs * s->N;
         double* xi = x + (size_t)rhs * s->N;
@@ -1210,10 +1281,7 @@ int ws_solver_solve(ws_solver* s, const double* b, double* x, int nrhs, int devi
             if (LP.small) {
                 const size_t sh = (size_t)std::max(LP.maxp, 2) * sizeof(double);
                 const unsigned nf = (unsigned)LP.nfronts;
-                if (LP.nt <= 128) k_fwd_front<128, 16><<<nf, LP.nt, sh, st>>>(LP.first_front, hc, cx, bi);
-                else if (LP.nt <= 256) k_fwd_front<256, 16><<<nf, LP.nt, sh, st>>>(LP.first_front, hc, cx, bi);
-                else if (LP.nt <= 512) k_fwd_front<512, 16><<<nf, LP.nt, sh, st>>>(LP.first_front, hc, cx, bi);
-                else k_fwd_front<1024, 8><<<nf, LP.nt, sh, st>>>(LP.first_front, hc, cx, bi);
+                launch_fwd_front(LP.nt, l == Y.depth ? tune.kb_leaf : tune.kb, nf, sh, st, LP.first_front, hc, cx, bi);
                 ++nl;
             } else if (LP.fwd.cnt) {
                 const size_t base = (size_t)((LP.maxp + 1) & ~1);
@@ -1229,9 +1297,8 @@ int ws_solver_solve(ws_solver* s, const double* b, double* x, int nrhs, int devi
             if (LP.small) {
                 const size_t sh = (size_t)std::max(LP.maxm, 2) * sizeof(double);
                 const unsigned nf = (unsigned)LP.nfronts;
-                if (LP.nt <= 128) k_bwd_front<128, 8, 4><<<nf, LP.nt, sh, st>>>(LP.first_front, cx, xi);
-                else if (LP.nt <= 512) k_bwd_front<512, 4, 4><<<nf, LP.nt, sh, st>>>(LP.first_front, cx, xi);
-                else k_bwd_front<1024, 2, 4><<<nf, LP.nt, sh, st>>>(LP.first_front, cx, xi);
+                launch_bwd_front(LP.nt, l == Y.depth ? tune.cb_leaf : tune.cb, l == Y.depth ? tune.rj_leaf : tune.rj, nf, sh, st,
+                                 LP.first_front, cx, xi);
                 ++nl;
             } else if (LP.bwd.cnt) {
                 const size_t base = (size_t)((LP.maxm + 1) & ~1);

@@ -38,6 +38,27 @@ def d2h(t: torch.Tensor) -> np.ndarray:
     return t.detach().cpu().numpy()
 
 
+def d2h_pinned(t: torch.Tensor) -> np.ndarray:
+    """Device -> host copy of a large result through page-locked memory (torch's caching host
+    allocator keeps the block for the next call once the caller drops the array; a pageable
+    ``.cpu()`` of the 160 MB eigenvector block costs several times the DMA time in page faults).
+    The returned numpy array owns the pinned block."""
+    t = t.detach()
+    if t.numel() < (1 << 16):
+        return t.cpu().numpy()
+    out = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+    out.copy_(t)
+    return out.numpy()
+
+
+def as_complex(t: torch.Tensor) -> torch.Tensor:
+    """float64 -> complex128 with zero imaginary part, on the device (scipy's eigs returns complex
+    arrays; converting 160 MB on the host costs more than moving the extra bytes)."""
+    c = torch.zeros(t.shape + (2,), dtype=t.dtype, device=t.device)
+    c[..., 0] = t
+    return torch.view_as_complex(c)
+
+
 def ptr(t) -> int:
     if t is None:
         return 0

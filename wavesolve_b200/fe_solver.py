@@ -36,6 +36,30 @@ def _material_major(mesh, IOR_dict, k, data=None):
     return data[:0], np.zeros(0)
 
 
+def _material_order(mesh, IOR_dict, k):
+    """Element order of the reference's assembly loop (material by material in ``cell_sets``
+    insertion order, fe_solver.py:36 / :179) as one index array into ``cells[1].data`` -- None when
+    that is the identity -- and k^2 n^2 per element in that order."""
+    idxs, k2 = [], []
+    ne = len(mesh.cells[1].data)
+    for material in mesh.cell_sets.keys():
+        idx = mesh.cell_sets[material][1]
+        idx = np.arange(ne, dtype=np.int64) if idx is None else np.asarray(idx).astype(np.int64, copy=False).ravel()
+        idxs.append(idx)
+        k2.append(np.full(len(idx), k ** 2 * IOR_dict[material] ** 2, dtype=np.float64))
+    if not idxs:
+        return np.zeros(0, dtype=np.int64), np.zeros(0)
+    order = np.concatenate(idxs)
+    if order.size and (int(order.min()) < 0 or int(order.max()) >= ne):
+        # numpy fancy indexing semantics of the reference: negative ids wrap, too large ids raise
+        if int(order.max()) >= ne or int(order.min()) < -ne:
+            raise IndexError("cell_sets index out of bounds for cells[1].data")
+        order = np.where(order < 0, order + ne, order)
+    if len(order) == ne and np.array_equal(order, np.arange(ne)):
+        return None, np.concatenate(k2)
+    return order, np.concatenate(k2)
+
+
 def _k2n2_host(mesh, IOR_dict, k):
     """k^2 n^2 per element in material-major order (fe_solver.py:51 / :181) -- the only input
     that changes between the wavelengths / index sets of a sweep on one mesh."""
@@ -203,28 +227,49 @@ class VectorProblem:
 
     def __init__(self, mesh, IOR_dict, k, device=None, build_pattern=True):
         self.dev = dev = _dev.require_cuda(device)
-        tris, k2 = _material_major(mesh, IOR_dict, k)
-        eidx, _ = _material_major(mesh, IOR_dict, k, data=np.asarray(mesh.edge_indices))
-        tris = _as_i32(tris, "vertex ids")
-        eidx = _as_i32(eidx, "edge ids")
+        tris_all = np.asarray(mesh.cells[1].data)
+        eidx_all = np.asarray(mesh.edge_indices)
+        assert len(eidx_all) == len(tris_all), "edge_indices must have one row per triangle (run get_unique_edges)"
+        order, k2 = _material_order(mesh, IOR_dict, k)
         self.Ntt = len(mesh.cells[0].data)                        # fe_solver.py:159-162
         self.Nzz = len(mesh.points)
         self.N = self.Ntt + self.Nzz
-        dofs = np.empty((len(tris), 6), dtype=np.int32)
-        dofs[:, :3] = eidx
-        np.add(tris, np.int32(self.Ntt), out=dofs[:, 3:])
+        self.first_class_start = self.Ntt
+        tris32 = _as_i32(tris_all[:, :3], "vertex ids")
+        eidx32 = _as_i32(eidx_all, "edge ids")
+        edges32 = _as_i32(np.asarray(mesh.cells[0].data), "edge table")
         xy = np.ascontiguousarray(np.asarray(mesh.points, dtype=np.float64)[:, :2])
-        self.h_dofs, self.h_xy, self.first_class_start = dofs, xy, self.Ntt
-        self.h_tris = tris
-        self.h_edges = _as_i32(np.asarray(mesh.cells[0].data), "edge table")
         with torch.cuda.device(dev):
             self.xy = _dev.h2d(xy, dev)
-            self.tris = _dev.h2d(tris, dev)
-            self.dofs = _dev.h2d(dofs, dev)
+            self.edges = _dev.h2d(edges32, dev)
             self.k2n2 = _dev.h2d(k2, dev)
-            self.edges = _dev.h2d(self.h_edges, dev)
+            t_d, e_d = _dev.h2d(tris32, dev), _dev.h2d(eidx32, dev)
+            if order is not None:
+                # material-major element order (fe_solver.py:179) gathered on the device
+                o_d = _dev.h2d(order, dev)
+                t_d, e_d = t_d.index_select(0, o_d), e_d.index_select(0, o_d)
+            self.tris = t_d.contiguous()
+            self.dofs = torch.cat([e_d, self.tris + self.Ntt], dim=1).contiguous()   # edges first, then nodes
             self.pattern = DevicePattern(self.dofs, self.N) if build_pattern else None
-        self.h2d_bytes = xy.nbytes + tris.nbytes + dofs.nbytes + k2.nbytes + self.h_edges.nbytes
+        self.h2d_bytes = (xy.nbytes + tris32.nbytes + eidx32.nbytes + k2.nbytes + edges32.nbytes +
+                          (order.nbytes if order is not None else 0))
+
+    # host copies of the resident arrays (tests and diagnostics; the solve path does not need them)
+    @property
+    def h_dofs(self):
+        return _dev.d2h(self.dofs)
+
+    @property
+    def h_xy(self):
+        return _dev.d2h(self.xy)
+
+    @property
+    def h_tris(self):
+        return _dev.d2h(self.tris)
+
+    @property
+    def h_edges(self):
+        return _dev.d2h(self.edges)
 
     def assemble(self, transpose=False, fast=False, out=None):
         p = self.build_pattern()
@@ -405,7 +450,7 @@ def solve_waveguide(mesh, wl, IOR_dict, plot=False, ignore_warning=False, sparse
 
     The whole pipeline runs on the device: assembly -> multifrontal LDL^T of A - sigma B ->
     B-orthogonal thick-restart Lanczos on (A - sigma B)^-1 B (the algorithm eigsh/ARPACK mode 3
-    runs on the host at fe_solver.py:328) with scipy's defaults ncv = max(2 Nmax + 1, 20), tol = eps.
+    runs on the host at fe_solver.py:328) with scipy's tol = eps and ncv = max(2 Nmax + 4, 20) (scipy: 2 Nmax + 1; see csrc/ws_eig.cu).
     ``sparse=False`` (LAPACK eigh on dense matrices in the reference, which cannot even assemble
     them for order 2) is served by the same path with the shift at the top of the spectrum."""
     k = 2 * np.pi / wl
@@ -426,7 +471,7 @@ def solve_waveguide(mesh, wl, IOR_dict, plot=False, ignore_warning=False, sparse
     with torch.cuda.device(prob.dev):
         wd, Vd, info = solve_scalar_resident(prob, est_eigval, Nmax, leaf_elems)
         w = _dev.d2h(wd)
-        v = _dev.d2h(Vd)
+        v = _dev.d2h_pinned(Vd)
     last_info.clear()
     last_info.update(info)
     mode_count = _count_modes(w, k, IOR_dict)
@@ -513,15 +558,14 @@ def solve_waveguide_vec(mesh, wl, IOR_dict, plot=False, ignore_warning=False, sp
         print("solving...")
     with torch.cuda.device(prob.dev):
         wd, Vd, info = solve_vector_resident(prob, est_eigval, Nmax, leaf_elems)
+        if sparse and sparse_solve_mode in ("transform", "pardiso"):
+            wd, Vd = _dev.as_complex(wd), _dev.as_complex(Vd)   # scipy.sparse.linalg.eigs returns complex arrays
         w = _dev.d2h(wd)
-        v = _dev.d2h(Vd)
+        v = _dev.d2h_pinned(Vd)
     if verbose:
         print("solving complete")
     last_info.clear()
     last_info.update(info)
-    if sparse and sparse_solve_mode in ("transform", "pardiso"):
-        w = w.astype(np.complex128)             # scipy.sparse.linalg.eigs returns complex arrays
-        v = v.astype(np.complex128)
     mode_count = _count_modes(w, k, IOR_dict, always=target_neff is not None)
     if plot:
         _report_modes(wl, w, k, IOR_dict, warn_always=target_neff is None)

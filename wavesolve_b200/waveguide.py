@@ -9,6 +9,12 @@ import torch
 from . import _lib, device as _dev
 
 
+def _torch_dtype(dt):
+    """torch dtype with the same width as an integer numpy dtype (unsigned ids are non-negative
+    and below 2^31 here, so the signed type of equal width carries the same bits)."""
+    return {1: torch.int8, 2: torch.int16, 4: torch.int32, 8: torch.int64}[np.dtype(dt).itemsize]
+
+
 def unique_edges_device(tris_d: torch.Tensor, num_points: int):
     """Device-side K1.  tris_d: (Ne,3) int32 CUDA tensor.  Returns (edges (Ntt,2) int32,
     edge_indices (Ne,3) int32) CUDA tensors."""
@@ -37,12 +43,15 @@ def get_unique_edges(mesh, mutate=True, device=None):
         td = _dev.h2d(t32, dev)
         npts = int(t32.max()) + 1 if t32.size else 0
         edges_d, eidx_d = unique_edges_device(td, max(npts, mesh.points.shape[0]))
-        edges = _dev.d2h(edges_d).astype(tris.dtype if tris.size else np.int64)
-        edge_indices = _dev.d2h(eidx_d).astype(np.uint)             # waveguide.py:16
+        # widen on the device, land in page-locked memory (the reference's arrays are 64-bit)
+        wide = _torch_dtype(tris.dtype if tris.size else np.dtype(np.int64))
+        edges = _dev.d2h_pinned(edges_d.to(wide)).view(tris.dtype if tris.size else np.int64)
+        edge_indices = _dev.d2h_pinned(eidx_d.to(torch.int64)).view(np.uint)   # waveguide.py:16
+        flips = _dev.d2h_pinned(torch.where(td <= td[:, [1, 2, 0]], 1.0, -1.0).to(torch.float64)) if mutate else None
     if mutate:
         mesh.cells[0].data = edges                                  # waveguide.py:38-42
         mesh.edge_indices = edge_indices
-        mesh.edge_flips = np.where(t32 <= t32[:, [1, 2, 0]], 1.0, -1.0)   # waveguide.py:33-34
+        mesh.edge_flips = flips                                     # waveguide.py:33-34
         mesh.num_edges = len(edges)
         mesh.num_points = mesh.points.shape[0]
     return edges, edge_indices
