@@ -43,7 +43,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--elements", type=int, default=1_000_000)
-    ap.add_argument("--cpu-sample-elements", type=int, default=50_000)
+    ap.add_argument("--cpu-sample-elements", type=int, default=80_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-clock-sampler", action="store_true",
                     help="do not spawn nvidia-smi during the timed region (profiler runs)")
@@ -277,7 +277,11 @@ def run_ours(args):
     # ---- end to end through the public API with host buffers ---------------------------------
     e2e_t = []
     h2d_b = d2h_b = 0
-    for it in range(max(1, min(args.steps, 3)) + 1):
+    # untimed passes first: the result arrays land in page-locked memory that torch's caching host
+    # allocator only recycles once the previous call's arrays are dropped, so steady state (what a
+    # sweep sees) is reached after two calls
+    n_warm = max(1, min(args.warmup, 2))
+    for it in range(max(1, min(args.steps, 3)) + n_warm):
         m = copy.copy(mesh)
         m.cells = [copy.copy(c) for c in mesh.cells]
         barrier()
@@ -286,7 +290,7 @@ def run_ours(args):
         w, v, cnt = ws.solve_waveguide_vec(m, WL, ior, Nmax=NMAX, verbose=False)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
-        if it > 0:
+        if it >= n_warm:
             e2e_t.append(dt)
         h2d_b = tris_h.nbytes + base.h2d_bytes
         d2h_b = edges.nbytes + eidx.nbytes + m.edge_flips.nbytes + w.nbytes + v.nbytes

@@ -49,6 +49,7 @@ struct LevelPlan {
     int nt = 32;                          // threads of those kernels: largest front rounded up to a warp
     int maxp = 0, maxm = 0;
     bool right_looking = false;
+    bool fused = false;                   // factorised by k_front_fused (one CTA per front, no tile tasks)
 };
 
 }  // namespace ws
@@ -407,6 +408,251 @@ __global__ void __launch_bounds__(256) k_extend_add(const ExtTask* __restrict__ 
     }
 }
 
+// ---- small fronts: the whole front in one CTA -------------------------------------------------
+// Below the top ~10 levels of the tree the fronts are tiny (m <= 256 rows, p <= 64 pivots) and
+// there are tens of thousands of them: as tile tasks they cost more in task records, launches
+// and tile padding than in arithmetic.  Here one CTA takes one front through every step --
+// extend-add of the children, LDL^T of the pivot columns, Schur complement, selective inversion
+// -- with the m x p panel resident in shared memory, and writes only what later phases read:
+// the update matrix U (parent's extend-add), the inverted panel S and the pivots d (solve sweeps).
+//   LDL^T: thread i owns row i of the panel (so the right-looking update needs no atomics and
+//   one barrier per pivot: only the pivot column of the p x p block is exchanged, double-buffered).
+struct FusedCtx {
+    FrontView fv;
+    const double* L;     // scattered matrix entries (panel layout), read only
+    double* S;
+    double* U;
+    double* d;
+    unsigned long long* stats;
+};
+
+__host__ __device__ inline size_t fused_smem_doubles(int m, int p) {
+    return 5 * (size_t)((p + 1) & ~1) + 8 + (size_t)(m | 1) * p;
+}
+
+template <int PMAX>
+__global__ void k_front_fused(int64_t first, int has_children, FusedCtx cx) {
+    extern __shared__ __align__(16) double fsm[];
+    const int64_t t = first + blockIdx.x;
+    const FrontView& fv = cx.fv;
+    const int p = fv.p[t], q = fv.q[t], m = p + q;
+    const int ld = m | 1, pe = (p + 1) & ~1;
+    double* vb = fsm;                       // pivot column exchange, 2 x pe (16-byte aligned halves)
+    double* rb = vb + 2 * pe;               // reciprocal pivots, then row staging of the inversion, 2 x pe
+    double* dd = rb + 2 * pe;               // pivots
+    double* P = dd + pe + 8;                // panel, column-major, ld
+    const int tid = threadIdx.x, NT = blockDim.x;
+    const double* Lg = cx.L + fv.Loff[t];
+    double* Ut = cx.U + fv.Uoff[t];
+    // (1) panel -> shared memory
+    if (tid < m) {
+        const double* src = Lg + tid;
+        double* dst = P + tid;
+        for (int j = 0; j < p; ++j, src += m, dst += ld) *dst = *src;
+    }
+    __syncthreads();
+    // (2) extend-add of the two children (their boundaries are subsets of this front: q_c <= m)
+    if (has_children) {
+        for (int side = 0; side < 2; ++side) {
+            const int64_t c = 2 * t + side;
+            const int qc = fv.q[c];
+            const int32_t* rel = fv.rel + fv.bndoff[c];
+            const double* Uc = cx.U + fv.Uoff[c];
+            if (tid < qc) {
+                const int ri = rel[tid];
+                for (int j = 0; j <= tid; ++j) {
+                    const int rj = rel[j];
+                    const double v = Uc[tid + (size_t)j * qc];
+                    if (rj < p) P[ri + rj * ld] += v;
+                    else Ut[(ri - p) + (size_t)(rj - p) * q] += v;
+                }
+            }
+            __syncthreads();
+        }
+    }
+    // (3) LDL^T of the p pivot columns, right-looking, thread i owns row i (no atomics, one barrier per
+    // pivot: only the pivot column of the p x p block is exchanged, double-buffered).  The owner of
+    // row k+1 has the shortest update of step k, so it also inverts the next pivot while the others
+    // finish: the division is off the critical path and rows are scaled by multiplication.
+    double* rd = rb;
+    if constexpr (PMAX > 0) {
+        // wide pivot blocks (leaf fronts): the row lives in REGISTERS (PMAX columns, statically
+        // indexed: the k and j loops are fully unrolled), so one update is one DFMA plus half a
+        // broadcast LDS.128; entries above the diagonal or beyond column p are updated with whatever
+        // the exchange buffer holds and never read.
+        double row[PMAX > 0 ? PMAX : 1];
+#pragma unroll
+        for (int j = 0; j < PMAX; ++j) row[j] = (tid < m && j < p) ? P[tid + j * ld] : 0.0;
+        if (tid == 0 && p > 0) rd[0] = 1.0 / row[0];
+#pragma unroll
+        for (int k = 0; k < PMAX; ++k) {
+            if (k >= p) break;
+            double* buf = vb + (k & 1) * pe;
+            if (tid >= k && tid < p) buf[tid] = row[k];
+            __syncthreads();
+            if (tid == k) dd[k] = row[k];
+            if (tid > k && tid < m) {
+                const double li = row[k] * rd[k];
+                row[k] = li;
+#pragma unroll
+                for (int c = 0; c < PMAX / 8; ++c) {
+                    if (c * 8 + 7 > k && c * 8 < p) {           // first test static, second uniform
+                        const double2* b2 = reinterpret_cast<const double2*>(buf + c * 8);
+                        const double2 v0 = b2[0], v1 = b2[1], v2 = b2[2], v3 = b2[3];
+                        if (c * 8 + 0 > k) row[c * 8 + 0] -= li * v0.x;
+                        if (c * 8 + 1 > k) row[c * 8 + 1] -= li * v0.y;
+                        if (c * 8 + 2 > k) row[c * 8 + 2] -= li * v1.x;
+                        if (c * 8 + 3 > k) row[c * 8 + 3] -= li * v1.y;
+                        if (c * 8 + 4 > k) row[c * 8 + 4] -= li * v2.x;
+                        if (c * 8 + 5 > k) row[c * 8 + 5] -= li * v2.y;
+                        if (c * 8 + 6 > k) row[c * 8 + 6] -= li * v3.x;
+                        if (c * 8 + 7 > k) row[c * 8 + 7] -= li * v3.y;
+                    }
+                }
+                if (k + 1 < PMAX && tid == k + 1 && tid < p) rd[k + 1] = 1.0 / row[k + 1 < PMAX ? k + 1 : 0];
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < PMAX; ++j)
+            if (tid < m && j < p && j <= tid) P[tid + j * ld] = row[j];
+    } else {
+        // narrow pivot blocks (separator fronts): the panel stays in shared memory -- fewer registers,
+        // more resident CTAs, no work on columns that do not exist
+        if (tid == 0 && p > 0) rd[0] = 1.0 / P[0];
+        for (int k = 0; k < p; ++k) {
+            double* buf = vb + (k & 1) * pe;
+            if (tid >= k && tid < p) buf[tid] = P[tid + k * ld];
+            __syncthreads();
+            if (tid == k) dd[k] = buf[k];
+            if (tid > k && tid < m) {
+                const double* __restrict__ bj = buf;
+                double* __restrict__ pr = P + tid + k * ld;
+                const double li = *pr * rd[k];
+                *pr = li;
+                const int jmax = min(tid, p - 1);
+                pr += ld;
+                int j = k + 1;
+                for (; j + 3 <= jmax; j += 4, pr += 4 * ld) {
+                    const double a0 = pr[0], a1 = pr[ld], a2 = pr[2 * ld], a3 = pr[3 * ld];
+                    const double b0 = bj[j], b1 = bj[j + 1], b2 = bj[j + 2], b3 = bj[j + 3];
+                    pr[0] = a0 - li * b0;
+                    pr[ld] = a1 - li * b1;
+                    pr[2 * ld] = a2 - li * b2;
+                    pr[3 * ld] = a3 - li * b3;
+                }
+                for (; j <= jmax; ++j, pr += ld) *pr -= li * bj[j];
+                if (tid == k + 1 && tid < p) rd[tid] = 1.0 / P[tid + tid * ld];
+            }
+        }
+    }
+    __syncthreads();
+    // pivots + statistics (one set of atomics per warp that holds pivots)
+    if (tid < ((p + 31) & ~31)) {
+        const bool on = tid < p;
+        const double dv = on ? dd[tid] : 1.0;
+        const double av = fabs(dv);
+        const bool bad = on && (!(av > 0.0) || !isfinite(dv));
+        if (on) cx.d[fv.start[t] + tid] = dv;
+        const unsigned nneg = __popc(__ballot_sync(0xffffffffu, on && dv < 0.0));
+        const unsigned nbad = __popc(__ballot_sync(0xffffffffu, bad));
+        unsigned long long lo = (on && !bad) ? (unsigned long long)__double_as_longlong(av) : ~0ull;
+        unsigned long long hi = (on && !bad) ? (unsigned long long)__double_as_longlong(av) : 0ull;
+        for (int o = 16; o; o >>= 1) {
+            lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+            hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+        }
+        if ((tid & 31) == 0) {
+            if (nneg) atomicAdd(&cx.stats[0], (unsigned long long)nneg);
+            if (nbad) atomicAdd(&cx.stats[1], (unsigned long long)nbad);
+            if (lo != ~0ull) {
+                atomicMin(&cx.stats[2], lo);
+                atomicMax(&cx.stats[3], hi);
+            }
+        }
+    }
+    // (4) Schur complement U -= L21 D L21^T (lower triangle) and (5) X = L11^-1 in place.  They touch
+    // disjoint parts of the panel, so with three or more warps the first two invert while the rest
+    // update (the inversion has only p-way parallelism).
+    const bool split = NT >= 96 && p <= 64;
+    auto schur = [&](int t0, int nthr) {
+        for (int idx = t0; idx < q * q; idx += nthr) {
+            const int a = idx % q, b = idx / q;
+            if (a < b) continue;
+            const double* la = P + p + a;
+            const double* lb = P + p + b;
+            double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
+            int k = 0;
+            for (; k + 3 < p; k += 4, la += 4 * ld, lb += 4 * ld) {
+                acc0 += la[0] * (dd[k] * lb[0]);
+                acc1 += la[ld] * (dd[k + 1] * lb[ld]);
+                acc2 += la[2 * ld] * (dd[k + 2] * lb[2 * ld]);
+                acc3 += la[3 * ld] * (dd[k + 3] * lb[3 * ld]);
+            }
+            for (; k < p; ++k, la += ld, lb += ld) acc0 += la[0] * (dd[k] * lb[0]);
+            acc0 += acc2;
+            acc1 += acc3;
+            Ut[a + (size_t)b * q] -= acc0 + acc1;
+        }
+    };
+    // row-oriented in-place inversion of the unit lower triangle: row i of X is
+    //   X[i][j] = -( L[i][j] + sum_{j<k<i} L[i][k] X[k][j] ),  thread j owns column j (it only ever reads
+    //   its own column of X), row i of L is staged so that it can be overwritten.
+    auto invert = [&](bool named) {
+        for (int i = 1; i < p; ++i) {
+            double* row = rb + (i & 1) * pe;
+            if (tid < i) row[tid] = P[i + tid * ld];
+            if (named) asm volatile("bar.sync 1, 64;" ::: "memory");
+            else __syncthreads();
+            if (tid < i) {
+                const double* __restrict__ xc = P + tid * ld;
+                const double* __restrict__ rw = row;
+                double s0 = rw[tid], s1 = 0.0, s2 = 0.0, s3 = 0.0;
+                int k = tid + 1;
+                for (; k + 3 < i; k += 4) {
+                    s0 += rw[k] * xc[k];
+                    s1 += rw[k + 1] * xc[k + 1];
+                    s2 += rw[k + 2] * xc[k + 2];
+                    s3 += rw[k + 3] * xc[k + 3];
+                }
+                for (; k < i; ++k) s0 += rw[k] * xc[k];
+                P[i + tid * ld] = -((s0 + s1) + (s2 + s3));
+            }
+        }
+    };
+    if (split) {
+        if (tid < 64) invert(true);
+        else schur(tid - 64, NT - 64);
+    } else {
+        schur(tid, NT);
+        __syncthreads();
+        invert(false);
+    }
+    __syncthreads();
+    // (6) inverted panel: S11 = X (unit diagonal), S21 = L21 X
+    double* Sg = cx.S + fv.Loff[t];
+    if (tid < p) {
+        for (int j = 0; j < tid; ++j) Sg[tid + (size_t)j * m] = P[tid + j * ld];
+        Sg[tid + (size_t)tid * m] = 1.0;
+    }
+    for (int idx = tid; idx < q * p; idx += NT) {
+        const int a = idx % q, j = idx / q;
+        const double* la = P + p + a + j * ld;
+        const double* xj = P + j * ld;              // X[k][j], k > j; X[j][j] = 1
+        double acc0 = la[0], acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
+        la += ld;
+        int k = j + 1;
+        for (; k + 3 < p; k += 4, la += 4 * ld) {
+            acc0 += la[0] * xj[k];
+            acc1 += la[ld] * xj[k + 1];
+            acc2 += la[2 * ld] * xj[k + 2];
+            acc3 += la[3 * ld] * xj[k + 3];
+        }
+        for (; k < p; ++k, la += ld) acc0 += la[0] * xj[k];
+        Sg[p + a + (size_t)j * m] = (acc0 + acc1) + (acc2 + acc3);
+    }
+}
+
 // ---- solve sweeps -----------------------------------------------------------------------------
 // x = M^-1 b with the selectively inverted panels S:  forward  y_own = S11 w_own, w_bnd -= S21 w_own
 // (w = b restricted to the front + the children's boundary remainders), backward
@@ -734,6 +980,13 @@ static FrontView view(const ws_solver* s) {
                      s->fr_woff.get(), s->fr_bndoff.get(), s->bnd.get(), s->rel.get()};
 }
 
+constexpr int FUSED_MAX_M = 256;                  // one thread per front row
+constexpr size_t FUSED_MAX_SMEM = 72 * 1024;     // >= 3 resident CTAs per SM
+static bool fused_enabled() {
+    static const bool on = !(getenv("WS_NO_FUSED") && atoi(getenv("WS_NO_FUSED")));
+    return on;
+}
+
 static void build_plan(ws_solver* s, cudaStream_t st) {
     const Symbolic& Y = s->sym;
     const int depth = Y.depth;
@@ -770,8 +1023,10 @@ static void build_plan(ws_solver* s, cudaStream_t st) {
         // few large fronts: a left-looking block-column update has too few tiles to fill the GPU
         // (and a long serial k loop); update the whole trailing panel after every block column.
         LP.right_looking = (f1 - f0) <= 64 && maxp > 4 * NB;
+        LP.fused = fused_enabled() && maxm <= FUSED_MAX_M && maxp <= 64 &&
+                   fused_smem_doubles(maxm, maxp) * sizeof(double) <= FUSED_MAX_SMEM;
         // extend-add of the children of this level's fronts (left children first, then right)
-        if (l < depth) {
+        if (l < depth && !LP.fused) {
             for (int side = 0; side < 2; ++side) {
                 Range& R = side ? LP.ext_right : LP.ext_left;
                 R.off = (int64_t)E.size();
@@ -784,7 +1039,7 @@ static void build_plan(ws_solver* s, cudaStream_t st) {
                 R.cnt = (int64_t)E.size() - R.off;
             }
         }
-        for (int kb = 0; kb < nkb; ++kb) {
+        for (int kb = 0; kb < (LP.fused ? 0 : nkb); ++kb) {
             const int k0 = kb * NB;
             LP.upd[kb].off = (int64_t)G.size();
             if (kb > 0 && !LP.right_looking)
@@ -859,7 +1114,7 @@ static void build_plan(ws_solver* s, cudaStream_t st) {
         }
         // Schur complement U -= L21 D L21^T (lower tiles)
         LP.syrk.off = (int64_t)G.size();
-        for (int64_t t = f0; t < f1; ++t) {
+        for (int64_t t = f0; t < f1 && !LP.fused; ++t) {
             const int p = Y.p[t], q = Y.q[t], m = p + q;
             if (!p || !q) continue;
             double* Lt = Lb + Y.Loff[t];
@@ -901,9 +1156,11 @@ static void build_plan(ws_solver* s, cudaStream_t st) {
         LP.fwd.cnt = (int64_t)F.size() - LP.fwd.off;
         LP.bwd.cnt = (int64_t)Bk.size() - LP.bwd.off;
     }
-    // ---- selective inversion (all fronts, independent of the tree)
+    // ---- selective inversion (all fronts that are not handled by k_front_fused, independent of the tree)
+    auto tiled = [&](int64_t t) { return !s->levels[63 - __builtin_clzll((unsigned long long)t)].fused; };
     s->inv0.off = 0;
     for (int64_t t = 1; t < Y.nfronts; ++t) {
+        if (!tiled(t)) continue;
         const int p = Y.p[t], m = p + Y.q[t];
         for (int k0 = 0; k0 < p; k0 += NB)
             I.push_back(InvTask{Sb + Y.Loff[t] + k0 + (size_t)k0 * m, m, std::min(NB, p - k0)});
@@ -914,6 +1171,7 @@ static void build_plan(ws_solver* s, cudaStream_t st) {
         Range r1, r2;
         r1.off = (int64_t)G.size();
         for (int64_t t = 1; t < Y.nfronts; ++t) {
+            if (!tiled(t)) continue;
             const int p = Y.p[t], m = p + Y.q[t];
             const double* Lt = Lb + Y.Loff[t];
             double* St = Sb + Y.Loff[t];
@@ -939,6 +1197,7 @@ static void build_plan(ws_solver* s, cudaStream_t st) {
         r1.cnt = (int64_t)G.size() - r1.off;
         r2.off = (int64_t)G.size();
         for (int64_t t = 1; t < Y.nfronts; ++t) {
+            if (!tiled(t)) continue;
             const int p = Y.p[t], m = p + Y.q[t];
             double* St = Sb + Y.Loff[t];
             const double* Tt = Tb + Y.Loff[t];
@@ -967,7 +1226,7 @@ static void build_plan(ws_solver* s, cudaStream_t st) {
     s->w21.off = (int64_t)G.size();
     for (int64_t t = 1; t < Y.nfronts; ++t) {
         const int p = Y.p[t], q = Y.q[t], m = p + q;
-        if (!p || !q) continue;
+        if (!p || !q || !tiled(t)) continue;
         const double* Lt = Lb + Y.Loff[t];
         double* St = Sb + Y.Loff[t];
         for (int i0 = 0; i0 < q; i0 += GT)
@@ -997,7 +1256,7 @@ static void build_plan(ws_solver* s, cudaStream_t st) {
     if (trace)
         for (int l = 0; l <= depth; ++l)
             fprintf(stderr, "[build_plan] level %2d fronts %6lld maxp %4d maxm %4d %s nt %d\n", l, (long long)s->levels[l].nfronts,
-                    s->levels[l].maxp, s->levels[l].maxm, s->levels[l].small ? "front" : "tile", s->levels[l].nt);
+                    s->levels[l].maxp, s->levels[l].maxm, s->levels[l].fused ? "fused" : (s->levels[l].small ? "front" : "tile"), s->levels[l].nt);
     if (trace)
         fprintf(stderr, "[build_plan] tasks: gemm %zu panel %zu ext %zu inv %zu fwd %zu bwd %zu; upload %.1f ms\n", G.size(),
                 P.size(), E.size(), I.size(), F.size(), Bk.size(),
@@ -1202,8 +1461,22 @@ int ws_solver_factor(ws_solver* s, const double* A_vals, const double* B_vals, d
         count_launch(1);
     }
     FrontView fv = view(s);
+    static bool fused_configured = false;
+    if (!fused_configured) {
+        WS_CUDA(cudaFuncSetAttribute(k_front_fused<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FUSED_MAX_SMEM));
+        WS_CUDA(cudaFuncSetAttribute(k_front_fused<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FUSED_MAX_SMEM));
+        fused_configured = true;
+    }
     for (int l = Y.depth; l >= 0; --l) {
         const LevelPlan& LP = s->levels[l];
+        if (LP.fused) {
+            FusedCtx fc{fv, s->L.get(), s->S.get(), s->U.get(), s->d.get(), s->stats.get()};
+            const size_t sh = fused_smem_doubles(LP.maxm, LP.maxp) * sizeof(double);
+            if (LP.maxp <= 48) k_front_fused<0><<<(unsigned)LP.nfronts, LP.nt, sh, st>>>(LP.first_front, l < Y.depth ? 1 : 0, fc);
+            else k_front_fused<64><<<(unsigned)LP.nfronts, LP.nt, sh, st>>>(LP.first_front, l < Y.depth ? 1 : 0, fc);
+            count_launch(1);
+            continue;
+        }
         if (LP.ext_left.cnt) {
             k_extend_add<<<(unsigned)LP.ext_left.cnt, 256, 0, st>>>(s->ext_tasks.get() + LP.ext_left.off, fv, s->L.get(), s->U.get());
             count_launch(1);
