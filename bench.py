@@ -45,6 +45,9 @@ def parse():
     ap.add_argument("--elements", type=int, default=1_000_000)
     ap.add_argument("--cpu-sample-elements", type=int, default=80_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--lite", action="store_true",
+                    help="time the steps only: skip the kernel micro-measurements and the end-to-end pass "
+                         "(the command the ncu launch list under profiles/ is taken from)")
     ap.add_argument("--no-clock-sampler", action="store_true",
                     help="do not spawn nvidia-smi during the timed region (profiler runs)")
     return ap.parse_args()
@@ -61,7 +64,10 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+    """nvidia-smi clocks / throttle reasons DURING the timed region: ONE `nvidia-smi -lms 200`
+    process (B200_PROFILING.md's clocks line) started before and terminated after -- spawning a
+    fresh nvidia-smi per sample re-initialises NVML every time and stalls the driver calls of the
+    step being measured."""
 
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -70,30 +76,40 @@ class ClockSampler:
     def __init__(self, index):
         self.index = index
         self.samples = []
-        self.stop = threading.Event()
-        self.th = threading.Thread(target=self._run, daemon=True)
+        self.proc = None
+        self.th = None
 
     def _run(self):
-        while not self.stop.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True,
-                                     timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([s.strip() for s in out.split(",")])
-            except Exception:
-                pass
-            self.stop.wait(0.1)
+        try:
+            for line in self.proc.stdout:
+                line = line.strip()
+                if line:
+                    self.samples.append([s.strip() for s in line.split(",")])
+        except Exception:
+            pass
 
     def __enter__(self):
         if self.index is not None:
-            self.th.start()
+            try:
+                self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                              "--format=csv,noheader,nounits", "-lms", "200"],
+                                             stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                self.th = threading.Thread(target=self._run, daemon=True)
+                self.th.start()
+                time.sleep(0.3)          # NVML initialisation of the sampler happens before the timed region
+            except Exception:
+                self.proc = None
         return self
 
     def __exit__(self, *a):
-        self.stop.set()
-        if self.index is not None:
-            self.th.join(timeout=6)
+        if self.proc is not None:
+            try:
+                self.proc.terminate()
+                self.proc.wait(timeout=5)
+            except Exception:
+                pass
+            if self.th is not None:
+                self.th.join(timeout=5)
 
     def summary(self):
         if not self.samples:
@@ -104,6 +120,14 @@ class ClockSampler:
         reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "reasons": reasons, "samples": len(self.samples)}
+
+
+def measured_traffic():
+    """DRAM bytes of one shift-invert solve from the committed ncu capture (None if absent)."""
+    try:
+        return int(json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))["solve_dram_bytes"])
+    except Exception:
+        return None
 
 
 def make_mesh(n_elements, seed=0):
@@ -229,7 +253,16 @@ def run_ours(args):
     nnz = base.pattern.nnz
     fstat = stats["factor"]
 
-    # ---- dominant kernel family: the two solve sweeps (k_fwd_gemv + k_bwd_gemvT), timed live ---
+    if args.lite:
+        if rank == 0:
+            print(json.dumps({"metric": METRIC, "value": world * 1e3 / dev_ms, "unit": "eigensolves/s", "n_gpus": world,
+                              "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms, "lite": True,
+                              "gpu_launches": int(launches), "eig": {"op_applications": int(stats.get("n_op", 0))}}), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- dominant kernel family: the two solve sweeps (k_fwd_* + k_bwd_*), timed live -----------
     prob = base.fresh_pattern()
     prob.build_pattern()
     A, B = prob.assemble()
@@ -326,10 +359,13 @@ def run_ours(args):
         "factor": {"ms": factor_ms, "flops": fstat["flops"], "TFLOPs": fstat["flops"] / (factor_ms * 1e-3) / 1e12,
                    "nnzL": fstat["nnzL"], "sweep_entries": sweep_entries, "fronts": fstat["fronts"], "max_front": fstat["maxfront"]},
         "eig": {"op_applications": n_op, "restarts": int(stats.get("restarts", 0)), "converged": int(stats.get("nconv", 0))},
-        "roofline": {"bound": "hbm", "kernel": "k_fwd_gemv + k_bwd_gemvT (one shift-invert solve: both sweeps over the inverted panels; "
-                                               "%d solves per eigensolve, the largest share of the step)" % n_op,
+        "roofline": {"bound": "hbm", "kernel": "k_fwd_front/k_fwd_tile + k_bwd_tile/k_bwd_front (one shift-invert solve = both sweeps "
+                                               "over the inverted panels, one launch per tree level and direction; %d solves per "
+                                               "eigensolve, the largest share of the step)" % n_op,
                      "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
-                     "algorithmic_bytes": solve_bytes, "kernel_ms": solve_ms, "traffic": None},
+                     "algorithmic_bytes": solve_bytes, "kernel_ms": solve_ms, "traffic": measured_traffic(),
+                     "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum summed over the launches of one solve, "
+                                       "profiles/r01_traffic.json (ncu capture of tools/solve_only.py)"},
         "e2e": {"value": total / e2e_s, "unit": "eigensolves/s", "h2d_bytes_per_step": int(h2d_b),
                 "d2h_bytes_per_step": int(d2h_b), "seconds": e2e_s,
                 "api": "get_unique_edges(mesh) + solve_waveguide_vec(mesh, wl, IOR_dict, Nmax=10) with host numpy in/out"},

@@ -126,7 +126,7 @@ int ws_axpby(int64_t n, double alpha, const double* x, double beta, double* y, i
 int ws_spmv(const ws_pattern* p, const double* vals, const double* x, double* y, int device,
             void* stream);
 
-/* ---- K8a: symbolic analysis of the sparse factorisation (host) ---------------------------
+/* ---- K8a: symbolic analysis of the sparse factorisation (host model; the device version follows) --
  * Replaces the COLAMD ordering + symbolic phase of SuperLU inside scipy splu / spsolve
  * (fe_solver.py:328 through eigsh sigma mode, fe_solver.py:398).  Element-based geometric
  * nested dissection: h_dofs [Ne*6] as for ws_pattern_create, h_xy [Np*2] node coordinates

@@ -1,7 +1,8 @@
 #!/bin/bash
 # Runs on the GPU box (gpurun).  1) `ncu --set full` capture of the hot kernels (assembly, SpMV,
-# solve sweeps) on the 1M-element vector problem, reduced ON THE BOX to csv pages (the .ncu-rep
-# itself is too large to travel back); 2) ncu launch list of one bench.py step.
+# solve sweeps, fused small-front factorisation) on the 1M-element vector problem, reduced ON THE
+# BOX to csv pages (the .ncu-rep itself is too large to travel back); 2) per-launch list of one
+# shift-invert solve with DRAM bytes; 3) ncu launch list of one bench.py step.
 # Every profiler step sits behind the plain run of the same command and a hard timeout.
 # (WS_NO_GRAPH=1: same kernels, launched directly instead of through CUDA graphs -- ncu on the
 #  graph-replayed bench did not make progress in 25 minutes.)
@@ -14,21 +15,20 @@ KERN="python tools/solve_only.py --solves 1"
 REP=/tmp/prof_$TAG
 $KERN > gpurun_out/plain_kern_$TAG.log 2>&1 &&
 timeout -s KILL 700 ncu --set full --clock-control none --import-source on \
-    -k 'regex:k_assemble_rows|k_spmv_stream|k_fwd_gemv|k_bwd_gemvT|k_fwd_small|k_bwd_small' -c 64 \
+    -k 'regex:k_assemble_rows|k_spmv_stream|k_fwd_front|k_bwd_front|k_fwd_tile|k_bwd_tile|k_front_fused' -c 48 \
     -f -o $REP $KERN > gpurun_out/ncu_kern_$TAG.log 2>&1
 echo "full capture rc=$?"; tail -2 gpurun_out/ncu_kern_$TAG.log
 if [ -f $REP.ncu-rep ]; then
   ncu -i $REP.ncu-rep --page raw --csv > gpurun_out/prof_${TAG}_raw.csv 2>/dev/null
   ncu -i $REP.ncu-rep --page details --csv > gpurun_out/prof_${TAG}_details.csv 2>/dev/null
-  # per-line stall pages for one launch of each kernel family (largest-grid instance is picked offline from raw)
-  for K in k_assemble_rows k_spmv_stream k_fwd_small k_bwd_small k_fwd_gemv k_bwd_gemvT; do
-    ncu -i $REP.ncu-rep --page source --csv --print-source sass -k regex:$K -c 1 > gpurun_out/prof_${TAG}_src_$K.csv 2>/dev/null
-  done
   ls -la $REP.ncu-rep
 fi
-BENCH="python bench.py --steps 1 --warmup 0 --no-cpu-baseline --no-clock-sampler"
+timeout -s KILL 300 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed --clock-control none \
+   -k 'regex:k_fwd|k_bwd|k_spmv' --csv --log-file gpurun_out/solve_list.csv $KERN > gpurun_out/ncu_solve.log 2>&1
+echo "solve list rc=$?"
+BENCH="python bench.py --steps 1 --warmup 0 --no-cpu-baseline --no-clock-sampler --lite"
 $BENCH > gpurun_out/plain_bench_$TAG.log 2>&1 &&
-timeout -s KILL 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 9500 --csv \
+timeout -s KILL 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 12000 --csv \
     --log-file gpurun_out/launches_$TAG.csv $BENCH > gpurun_out/ncu_bench_$TAG.log 2>&1
 echo "launch list rc=$?"; wc -l gpurun_out/launches_$TAG.csv
-du -sh gpurun_out; ls -la gpurun_out
+du -sh gpurun_out

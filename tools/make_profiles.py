@@ -57,7 +57,7 @@ def launches(tag):
         agg[n][0] += 1
         agg[n][1] += t
     out = io.StringIO()
-    out.write("# ncu launch list of `python bench.py --steps 1 --warmup 0 --no-cpu-baseline --no-clock-sampler`\n")
+    out.write("# ncu launch list of `python bench.py --steps 1 --warmup 0 --no-cpu-baseline --no-clock-sampler --lite` (one step)\n")
     out.write("# (WS_NO_GRAPH=1: same kernels launched directly; per-launch times under ncu are cold-cache and\n")
     out.write("#  serialised, so read SHARES, not absolutes.)  launches %d, total device time %.3f ms\n" % (len(rows), tot / 1e3))
     out.write("%-72s %7s %12s %10s %7s\n" % ("kernel", "count", "total_us", "mean_us", "share"))
@@ -67,7 +67,7 @@ def launches(tag):
     for n, (c, t) in agg.items():
         if re.search(r"k_fwd|k_bwd|k_permute", n):
             fam["solve sweeps (K8c)"] += t
-        elif re.search(r"k_gemm_tiles|k_panel|k_diag_inverse|k_extend_add|k_scatter|k_trail|k_syrk", n):
+        elif re.search(r"k_gemm_tiles|k_panel|k_diag_inverse|k_extend_add|k_scatter|k_front_fused|k_recip|k_dest_map|k_build_wsrc|k_count_bad", n):
             fam["numeric factorisation (K8b)"] += t
         elif re.search(r"k_spmv", n):
             fam["SpMV (K5)"] += t
@@ -75,8 +75,10 @@ def launches(tag):
             fam["Krylov vector kernels (K6/K7/K10)"] += t
         elif re.search(r"k_assemble", n):
             fam["assembly (K3/K4)"] += t
+        elif re.search(r"k_centroids|k_bbox|k_kd_keys|k_leaf_of|k_owner|k_bucket|k_after_order|k_front_own|k_count_pairs|k_emit_pairs|k_bnd_split|k_front_bounds|k_rel|k_fill_i32", n):
+            fam["symbolic analysis (K8a)"] += t
         else:
-            fam["pattern / edges / sort / misc (K1/K2)"] += t
+            fam["pattern / edges / sort / scan (K1/K2, CUB inside K8a)"] += t
     out.write("\n# by family\n")
     for n, t in sorted(fam.items(), key=lambda kv: -kv[1]):
         out.write("%-44s %12.1f us %6.1f%%\n" % (n, t, 100 * t / tot))
@@ -125,8 +127,24 @@ def solve_list(tag):
         tot_b += mb
         out.write("%-30s grid %-14s block %-12s %8.1f us  read %7.1f MB  dram %5.1f%%  (%.0f GB/s)\n" %
                   (d["name"][-30:], d["grid"], d["block"], tu, mb, pc[0], mb / tu * 1e3 if tu else 0))
-    out.write("total %.1f us, %.1f MB\n" % (tot, tot_b))
+    out.write("total %.1f us, %.1f MB read\n" % (tot, tot_b))
     open(os.path.join(P, "%s_solve_sweep_launches.txt" % tag), "w").write(out.getvalue())
+    # DRAM traffic of one solve (sweep kernels only, SpMV excluded) for bench.py's roofline.traffic
+    rd = wr = 0.0
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    for k in sel:
+        d = L[k]
+        if "spmv" in d["name"]:
+            continue
+        b = d["dram__bytes_read.sum"]
+        rd += b[0] * scale[b[1]]
+        w = d.get("dram__bytes_write.sum")
+        if w:
+            wr += w[0] * scale[w[1]]
+    json.dump({"solve_dram_bytes": int(rd + wr), "read": int(rd), "write": int(wr),
+               "source": "ncu dram__bytes_read.sum / dram__bytes_write.sum summed over the %d sweep launches of one "
+                         "shift-invert solve (tools/solve_only.py, 1M-element vector problem)" % (len(sel) - 1)},
+              open(os.path.join(P, "%s_traffic.json" % tag.split("_")[0][:3]), "w"), indent=1)
 
 
 def bench_line(tag):
