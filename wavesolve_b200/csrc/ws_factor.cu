@@ -665,6 +665,14 @@ __global__ void k_front_fused(int64_t first, int has_children, FusedCtx cx) {
 //     loads in flight and only then resolves the vector dependency (the kernels are bound by
 //     the latency of that chain, not by arithmetic);
 //   * the row / column permutation and the D^-1 scaling are folded into the first and last touch.
+// Programmatic dependent launch: consecutive sweep kernels form a chain (level l needs level l+1), but
+// the matrix loads of a level do not depend on the previous one.  A kernel lets its successor start
+// as soon as all of its own CTAs are resident (launch_dependents), the successor puts its panel loads
+// in flight and only then waits for the predecessor's vector data (wait): ramp-up and tail of these
+// 20-40 us launches overlap.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 struct FrontRec {
     int64_t Loff, start, woff, bndoff;
     int32_t p, q, pad0, pad1;
@@ -704,6 +712,7 @@ template <int MAXT, int KB>
 __global__ void __launch_bounds__(MAXT) k_fwd_front(int64_t first, int has_children, SolveCtx cx,
                                                     const double* __restrict__ b) {
     extern __shared__ double sw[];
+    pdl_launch_dependents();
     const FrontRec R = cx.recs[first + blockIdx.x];
     const int p = R.p, m = p + R.q, r = threadIdx.x;
     const bool act = r < m;
@@ -716,6 +725,7 @@ __global__ void __launch_bounds__(MAXT) k_fwd_front(int64_t first, int has_child
 #pragma unroll
     for (int j = 0; j < KB; ++j) c[j] = (KB + j < kend) ? __ldg(Sr + (size_t)(KB + j) * ld) : 0.0;
     double wv = 0.0;
+    pdl_wait();
     if (act) {
         wv = fwd_gather(cx, R, r, has_children, b);
         if (r < p) sw[r] = wv;
@@ -753,6 +763,7 @@ template <int KL>
 __global__ void __launch_bounds__(32 * KL) k_fwd_tile(const FwdTile* __restrict__ tasks, int has_children, SolveCtx cx,
                                                       const double* __restrict__ b) {
     extern __shared__ double sm[];
+    pdl_launch_dependents();
     const FwdTile t = tasks[blockIdx.x];
     const FrontRec R = cx.recs[t.front];
     const int p = R.p, m = p + R.q;
@@ -769,6 +780,7 @@ __global__ void __launch_bounds__(32 * KL) k_fwd_tile(const FwdTile* __restrict_
     double a[NL];
 #pragma unroll
     for (int j = 0; j < NL; ++j) a[j] = (kl + j * KL < kend) ? __ldg(Sr + (size_t)(kl + j * KL) * ld) : 0.0;
+    pdl_wait();
     for (int k = threadIdx.x; k < kend_tile; k += 32 * KL) sw[k] = fwd_gather(cx, R, k, has_children, b);
     double wv = 0.0;
     if (kl == 0 && valid && r >= p) wv = fwd_gather(cx, R, r, has_children, b);
@@ -804,6 +816,7 @@ __global__ void __launch_bounds__(32 * KL) k_fwd_tile(const FwdTile* __restrict_
 template <int MAXT, int BWD_CB, int BWD_RJ>
 __global__ void __launch_bounds__(MAXT) k_bwd_front(int64_t first, SolveCtx cx, double* __restrict__ xout) {
     extern __shared__ double sg[];
+    pdl_launch_dependents();
     const FrontRec R = cx.recs[first + blockIdx.x];
     const int p = R.p, m = p + R.q;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, NW = blockDim.x >> 5;
@@ -818,6 +831,7 @@ __global__ void __launch_bounds__(MAXT) k_bwd_front(int64_t first, SolveCtx cx, 
             a[i][j] = (c < p && r < m) ? __ldg(Sf + r + (size_t)c * m) : 0.0;
         }
     }
+    pdl_wait();
     for (int i = threadIdx.x; i < m; i += blockDim.x)
         sg[i] = (i < p) ? cx.yd[R.start + i] : -cx.x[cx.bnd[R.bndoff + i - p]];
     __syncthreads();
@@ -889,6 +903,7 @@ template <int WPC>
 __global__ void __launch_bounds__(32 * GEMVT_COLS * WPC) k_bwd_tile(const BwdTile* __restrict__ tasks, SolveCtx cx,
                                                                     double* __restrict__ xout) {
     extern __shared__ double sm[];
+    pdl_launch_dependents();
     const BwdTile t = tasks[blockIdx.x];
     const FrontRec R = cx.recs[t.front];
     const int p = R.p, m = p + R.q;
@@ -905,6 +920,7 @@ __global__ void __launch_bounds__(32 * GEMVT_COLS * WPC) k_bwd_tile(const BwdTil
     double a[NL];
 #pragma unroll
     for (int j = 0; j < NL; ++j) a[j] = (on && rb + j * step < m) ? __ldg(Sc + rb + j * step) : 0.0;
+    pdl_wait();
     for (int i = t.c0 + threadIdx.x; i < m; i += blockDim.x)
         sg[i - t.c0] = (i < p) ? cx.yd[R.start + i] : -cx.x[cx.bnd[R.bndoff + i - p]];
     __syncthreads();
@@ -1284,6 +1300,24 @@ static void launch_gemm(const ws_solver* s, const Range& r, bool narrow, cudaStr
 // KB (forward: loads in flight per thread = 2*KB) and CB x RJ (backward: columns x row groups in
 // flight per lane) default to small values.  WS_FWD_KB[_LEAF], WS_BWD_CB[_LEAF], WS_BWD_RJ[_LEAF]
 // override them for experiments (tools/sweep_variants.py).
+// launch with the programmatic-stream-serialisation attribute (the kernel may start before its
+// predecessor in the stream has finished; it synchronises itself with griddepcontrol.wait)
+template <class... KArgs, class... Args>
+static void launch_pdl(void (*kern)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t st, Args... args) {
+    static const bool pdl = !(getenv("WS_NO_PDL") && atoi(getenv("WS_NO_PDL")));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(block);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    WS_CUDA(cudaLaunchKernelEx(&cfg, kern, KArgs(args)...));
+}
+
 struct SweepTuning {
     int kb, kb_leaf, cb, cb_leaf, rj, rj_leaf;
 };
@@ -1305,10 +1339,10 @@ static const SweepTuning& sweep_tuning() {
 template <int MAXT>
 static void launch_fwd_front_t(int kb, unsigned nf, int nt, size_t sh, cudaStream_t st, int64_t first, int hc,
                                const SolveCtx& cx, const double* b) {
-    if (kb <= 2) k_fwd_front<MAXT, 2><<<nf, nt, sh, st>>>(first, hc, cx, b);
-    else if (kb <= 4) k_fwd_front<MAXT, 4><<<nf, nt, sh, st>>>(first, hc, cx, b);
-    else if (kb <= 8 || MAXT > 512) k_fwd_front<MAXT, 8><<<nf, nt, sh, st>>>(first, hc, cx, b);
-    else k_fwd_front<(MAXT > 512 ? 512 : MAXT), 16><<<nf, nt, sh, st>>>(first, hc, cx, b);
+    if (kb <= 2) launch_pdl(k_fwd_front<MAXT, 2>, nf, nt, sh, st, first, hc, cx, b);
+    else if (kb <= 4) launch_pdl(k_fwd_front<MAXT, 4>, nf, nt, sh, st, first, hc, cx, b);
+    else if (kb <= 8 || MAXT > 512) launch_pdl(k_fwd_front<MAXT, 8>, nf, nt, sh, st, first, hc, cx, b);
+    else launch_pdl(k_fwd_front<(MAXT > 512 ? 512 : MAXT), 16>, nf, nt, sh, st, first, hc, cx, b);
 }
 static void launch_fwd_front(int nt, int kb, unsigned nf, size_t sh, cudaStream_t st, int64_t first, int hc,
                              const SolveCtx& cx, const double* b) {
@@ -1320,10 +1354,10 @@ static void launch_fwd_front(int nt, int kb, unsigned nf, size_t sh, cudaStream_
 template <int MAXT, int RJ>
 static void launch_bwd_front_t(int cb, unsigned nf, int nt, size_t sh, cudaStream_t st, int64_t first, const SolveCtx& cx,
                                double* x) {
-    if (cb <= 1) k_bwd_front<MAXT, 1, RJ><<<nf, nt, sh, st>>>(first, cx, x);
-    else if (cb <= 2) k_bwd_front<MAXT, 2, RJ><<<nf, nt, sh, st>>>(first, cx, x);
-    else if (cb <= 4 || MAXT > 512) k_bwd_front<MAXT, (MAXT > 512 && RJ > 2 ? 2 : 4), RJ><<<nf, nt, sh, st>>>(first, cx, x);
-    else k_bwd_front<(MAXT > 512 ? 512 : MAXT), 8, RJ><<<nf, nt, sh, st>>>(first, cx, x);
+    if (cb <= 1) launch_pdl(k_bwd_front<MAXT, 1, RJ>, nf, nt, sh, st, first, cx, x);
+    else if (cb <= 2) launch_pdl(k_bwd_front<MAXT, 2, RJ>, nf, nt, sh, st, first, cx, x);
+    else if (cb <= 4 || MAXT > 512) launch_pdl(k_bwd_front<MAXT, (MAXT > 512 && RJ > 2 ? 2 : 4), RJ>, nf, nt, sh, st, first, cx, x);
+    else launch_pdl(k_bwd_front<(MAXT > 512 ? 512 : MAXT), 8, RJ>, nf, nt, sh, st, first, cx, x);
 }
 static void launch_bwd_front(int nt, int cb, int rj, unsigned nf, size_t sh, cudaStream_t st, int64_t first,
                              const SolveCtx& cx, double* x) {
@@ -1559,9 +1593,9 @@ int ws_solver_solve(ws_solver* s, const double* b, double* x, int nrhs, int devi
             } else if (LP.fwd.cnt) {
                 const size_t base = (size_t)((LP.maxp + 1) & ~1);
                 if (LP.fwd.cnt >= 500)
-                    k_fwd_tile<8><<<(unsigned)LP.fwd.cnt, 32 * 8, (base + 8 * 33) * sizeof(double), st>>>(s->fwd_tiles.get() + LP.fwd.off, hc, cx, bi);
+                    launch_pdl(k_fwd_tile<8>, (unsigned)LP.fwd.cnt, 32 * 8, (base + 8 * 33) * sizeof(double), st, s->fwd_tiles.get() + LP.fwd.off, hc, cx, bi);
                 else
-                    k_fwd_tile<32><<<(unsigned)LP.fwd.cnt, 32 * 32, (base + 32 * 33) * sizeof(double), st>>>(s->fwd_tiles.get() + LP.fwd.off, hc, cx, bi);
+                    launch_pdl(k_fwd_tile<32>, (unsigned)LP.fwd.cnt, 32 * 32, (base + 32 * 33) * sizeof(double), st, s->fwd_tiles.get() + LP.fwd.off, hc, cx, bi);
                 ++nl;
             }
         }
@@ -1576,9 +1610,9 @@ int ws_solver_solve(ws_solver* s, const double* b, double* x, int nrhs, int devi
             } else if (LP.bwd.cnt) {
                 const size_t base = (size_t)((LP.maxm + 1) & ~1);
                 if (LP.bwd.cnt >= 430)
-                    k_bwd_tile<1><<<(unsigned)LP.bwd.cnt, 32 * GEMVT_COLS, (base + GEMVT_COLS) * sizeof(double), st>>>(s->bwd_tiles.get() + LP.bwd.off, cx, xi);
+                    launch_pdl(k_bwd_tile<1>, (unsigned)LP.bwd.cnt, 32 * GEMVT_COLS, (base + GEMVT_COLS) * sizeof(double), st, s->bwd_tiles.get() + LP.bwd.off, cx, xi);
                 else
-                    k_bwd_tile<4><<<(unsigned)LP.bwd.cnt, 32 * GEMVT_COLS * 4, (base + GEMVT_COLS * 4) * sizeof(double), st>>>(s->bwd_tiles.get() + LP.bwd.off, cx, xi);
+                    launch_pdl(k_bwd_tile<4>, (unsigned)LP.bwd.cnt, 32 * GEMVT_COLS * 4, (base + GEMVT_COLS * 4) * sizeof(double), st, s->bwd_tiles.get() + LP.bwd.off, cx, xi);
                 ++nl;
             }
         }
