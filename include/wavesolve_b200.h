@@ -214,6 +214,37 @@ int ws_eig_solve(const ws_pattern* p, ws_solver* s, const double* B_vals, double
 int ws_host_eig_general(int n, const double* h_A, double* h_wr, double* h_wi, double* h_V,
                         int symmetric);
 
+/* ---- K13-K15: resampling of modes onto points (grid / mesh-to-mesh interpolation) -------------
+ * Replaces get_tri_idxs_KDtree / find_triangle_KDtree (fe_solver.py:848-872: one KD-tree query per
+ * try and per point), get_tri_idxs / find_triangle (fe_solver.py:615-668), get_interp_weights
+ * (fe_solver.py:670-696), get_interp_weights_vec (fe_solver.py:698-717) and the gather + sum of
+ * interpolate / interpolate_vec (fe_solver.py:719-774).
+ * ws_locator_create : uniform bin grid over the bounding box [bx0,bx1] x [by0,by1] of the mesh;
+ *                     conn [Ne*stride] int32, the first three columns are the vertex ids.
+ * ws_locate         : points are the grid xa[nx] x ya[ny] (ny > 0; point (i,j) at i*ny + j) or the
+ *                     list (xa[k], ya[k]), k < nx (ny == 0).  tri_idx[...] = index of the containing
+ *                     triangle under the reference's inclusive inside-test (fe_solver.py:597-612),
+ *                     -1 if none or if maxr > 0 and |point| > maxr; ties between containing
+ *                     triangles (points on edges / vertices): tie_rule 0 = nearest centroid (the
+ *                     KD-tree search order), 1 = lowest index (the brute-force search order).
+ * ws_interp_weights : kind 2: P2 weights [npts*6]; 1: P1 [npts*3]; 3: Whitney edge [npts*3*2];
+ *                     NaN where tri_idx == -1.
+ * ws_interp_apply   : out[pt, c] = sum_k field[dof[tri, k]] * weights[pt, k, c]; nd = 3 | 6 unknowns
+ *                     per element, wdim = 1 | 2 components per weight, ncomp = 1 (real field) | 2
+ *                     (complex128 field, interleaved).                                            */
+typedef struct ws_locator ws_locator;
+int ws_locator_create(const double* xy, const int32_t* conn, int64_t Ne, int stride, double bx0, double by0,
+                      double bx1, double by1, ws_locator** out, int device, void* stream);
+int ws_locator_destroy(ws_locator* L);
+int ws_locate(const ws_locator* L, const double* xy, const int32_t* conn, int stride, const double* xa,
+              const double* ya, int64_t nx, int64_t ny, double maxr, int tie_rule, int64_t* tri_idx, int device,
+              void* stream);
+int ws_interp_weights(const double* xy, const int32_t* conn, int64_t Ne, int stride, int kind, const double* xa,
+                      const double* ya, int64_t nx, int64_t ny, const int64_t* tri_idx, double* weights, int device,
+                      void* stream);
+int ws_interp_apply(const int64_t* tri_idx, int64_t npts, int64_t Ne, const int32_t* dof, int stride, int nd, int wdim,
+                    const double* weights, const double* field, int ncomp, double* out, int device, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

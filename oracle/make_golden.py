@@ -118,10 +118,69 @@ def vector_case(fe, wg, name, mesh, ior, Nmax=6, target_neff=None, solve=True):
           "neff", np.sqrt(out["w"].real) / k if solve else None, "count", out.get("count"))
 
 
+def interp_cases(fe, wg):
+    """Mode resampling (fe_solver.py:594-872, mesher.py:235): KD-tree point location, brute-force
+    point location, P2 / P1 / Whitney weights, interpolate, interpolate_vec, mesh_interpolate."""
+    import importlib
+    ms = importlib.import_module("wavesolve.mesher")
+    rng = np.random.default_rng(7)
+    # ---- scalar P2
+    mesh = mg.fiber_disc(600, seed=1)
+    out = mesh_arrays(mesh)
+    x, y = mesh.points[:, 0], mesh.points[:, 1]
+    v = np.sin(0.3 * x) * np.cos(0.2 * y) + 0.1 * x - 0.05 * y * y
+    vc = v * (1.0 + 0.5j) + 0.2j * x
+    xa, ya = np.linspace(-10.5, 10.5, 23), np.linspace(-9.7, 10.9, 19)
+    tree = ms.construct_meshtree(mesh)
+    out.update(v=v, vc=vc, xa=xa, ya=ya)
+    # (without maxr the reference raises IndexError for a point outside a P2 mesh: it asks the tree for
+    #  up to Npoints-1 > Ne neighbours, fe_solver.py:853-857; its callers always pass maxr)
+    out["tri_idxs"] = fe.get_tri_idxs_KDtree(mesh, tree, xa, ya, maxr=9.9)
+    out["tri_idxs_maxr"] = fe.get_tri_idxs_KDtree(mesh, tree, xa, ya, maxr=7.5)
+    out["tri_idxs_brute"] = fe.get_tri_idxs(mesh, xa[::2], ya[::2])
+    out["weights"] = fe.get_interp_weights(mesh, xa, ya, out["tri_idxs"], order=2)
+    out["interp"] = fe.interpolate(v, mesh, xa, ya, meshtree=tree, order=2, maxr=9.9)
+    out["interp_c"] = fe.interpolate(vc, mesh, xa, ya, tri_idxs=out["tri_idxs"], interp_weights=out["weights"])
+    out["interp_maxr"] = fe.interpolate(v, mesh, xa, ya, meshtree=tree, order=2, maxr=7.5)
+    outmesh = mg.fiber_disc(150, r_clad=9.0, seed=9)
+    out["out_points"] = outmesh.points
+    out["mesh_interp"] = fe.mesh_interpolate(v, mesh, outmesh, tree, max_tries=40)
+    out["point_interp"] = np.array([fe.unstructured_interpolate(v, mesh, p, tree, max_tries=40)
+                                    for p in [[0.3, -0.2], [4.99, 0.01], [9.2, 3.0]]])
+    np.savez_compressed(os.path.join(GOLD, "interp_p2_disc600.npz"), **out)
+    print("interp_p2_disc600", "inside", int((out["tri_idxs"] >= 0).sum()), "of", out["tri_idxs"].size,
+          "nan in mesh_interp", int(np.isnan(out["mesh_interp"]).sum()))
+    # ---- vector (Whitney edge functions) and P1 weights
+    mesh = mg.fiber_disc(500, order=1, seed=2)
+    m = copy.deepcopy(mesh)
+    edges, eidx = wg.get_unique_edges(m)
+    out = mesh_arrays(mesh)
+    out["edges"], out["edge_indices"] = edges, eidx
+    N = len(edges) + len(mesh.points)
+    vv = rng.standard_normal(N) + 1j * rng.standard_normal(N)
+    xa, ya = np.linspace(-9.3, 9.1, 17), np.linspace(-10.2, 8.8, 15)
+    tree = ms.construct_meshtree(m)
+    out.update(v=vv, xa=xa, ya=ya)
+    out["tri_idxs"] = fe.get_tri_idxs_KDtree(m, tree, xa, ya)
+    out["weights_vec"] = fe.get_interp_weights_vec(m, xa, ya, out["tri_idxs"])
+    out["weights_p1"] = fe.get_interp_weights(m, xa, ya, out["tri_idxs"], order=1)
+    out["interp_vec"] = fe.interpolate_vec(vv, m, xa, ya, meshtree=tree)
+    out["interp_vec_real"] = fe.interpolate_vec(vv.real, m, xa, ya, tri_idxs=out["tri_idxs"],
+                                                interp_weights=out["weights_vec"])
+    vz = rng.standard_normal(len(mesh.points))
+    out["vz"] = vz
+    out["interp_p1"] = fe.interpolate(vz, m, xa, ya, meshtree=tree, order=1)
+    np.savez_compressed(os.path.join(GOLD, "interp_vec_disc500.npz"), **out)
+    print("interp_vec_disc500", "inside", int((out["tri_idxs"] >= 0).sum()), "of", out["tri_idxs"].size)
+
+
 def main():
     fe, sf, wg = refshim.load()
     os.makedirs(GOLD, exist_ok=True)
     ior = mg.FIBER_IOR
+    if "--interp-only" in sys.argv:      # added later; leaves the earlier fixtures untouched
+        interp_cases(fe, wg)
+        return
     if "--p1-only" in sys.argv:          # added later; leaves the earlier fixtures untouched
         scalar_p1_case(fe, "scalar_p1_sq8", mg.structured_square(8, order=1), ior, Nmax=4)
         scalar_p1_case(fe, "scalar_p1_disc800", mg.fiber_disc(800, order=1, seed=6), ior, Nmax=6)

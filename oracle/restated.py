@@ -375,3 +375,154 @@ def get_eff_index(wl, w):
     """fe_solver.py:431-434."""
     k = 2 * np.pi / wl
     return np.sqrt(w / k ** 2)
+
+
+# ---------------------------------------------------------------------------------------------
+# mode resampling (SURVEY.md 8(f) rank 1): point location, weights, grid interpolation
+# ---------------------------------------------------------------------------------------------
+def _isinside_all(px, py, P0, P1, P2):
+    """fe_solver.py:597-612 (include_vertex=True) for one point against arrays of triangles; same
+    operation order as the scalar Python code."""
+    v1x, v1y = P1[:, 0] - P0[:, 0], P1[:, 1] - P0[:, 1]
+    v2x, v2y = P2[:, 0] - P0[:, 0], P2[:, 1] - P0[:, 1]
+    d12 = v1x * v2y - v1y * v2x
+    with np.errstate(divide="ignore", invalid="ignore"):
+        a = ((px * v2y - py * v2x) - (P0[:, 0] * v2y - P0[:, 1] * v2x)) / d12
+        b = -((px * v1y - py * v1x) - (P0[:, 0] * v1y - P0[:, 1] * v1x)) / d12
+        return (a >= 0) & (b >= 0) & (a + b <= 1)
+
+
+def get_tri_idxs_points(mesh, px, py, maxr=0, kdtree_order=True):
+    """Containing triangle of every point: the one with the nearest centroid (what the KD-tree search
+    of fe_solver.py:848-863 finds first) or the first in mesh order (fe_solver.py:615-633); -1 if none
+    or beyond maxr.  Brute force over all triangles, chunked."""
+    pts = np.asarray(mesh.points, dtype=np.float64)
+    tris = np.asarray(mesh.cells[1].data)[:, :3].astype(np.int64)
+    P0, P1, P2 = pts[tris[:, 0], :2], pts[tris[:, 1], :2], pts[tris[:, 2], :2]
+    cen = np.mean(pts[tris][:, :3, :2], axis=1)                    # mesher.py:239
+    out = np.full(len(px), -1, dtype=int)
+    for i, (x, y) in enumerate(zip(px, py)):
+        if maxr > 0 and np.sqrt(x ** 2 + y ** 2) > maxr:           # fe_solver.py:849-851
+            continue
+        hit = np.nonzero(_isinside_all(x, y, P0, P1, P2))[0]
+        if len(hit) == 0:
+            continue
+        if kdtree_order:
+            d = (x - cen[hit, 0]) ** 2 + (y - cen[hit, 1]) ** 2
+            out[i] = hit[np.argmin(d)]
+        else:
+            out[i] = hit[0]
+    return out
+
+
+def get_tri_idxs_KDtree(mesh, xa, ya, maxr=0):
+    """fe_solver.py:865-872."""
+    X, Y = np.meshgrid(np.asarray(xa, dtype=np.float64), np.asarray(ya, dtype=np.float64), indexing="ij")
+    return get_tri_idxs_points(mesh, X.ravel(), Y.ravel(), maxr, True).reshape(len(xa), len(ya))
+
+
+def get_tri_idxs(mesh, xa, ya):
+    """fe_solver.py:662-668."""
+    X, Y = np.meshgrid(np.asarray(xa, dtype=np.float64), np.asarray(ya, dtype=np.float64), indexing="ij")
+    return get_tri_idxs_points(mesh, X.ravel(), Y.ravel(), 0, False).reshape(len(xa), len(ya))
+
+
+def _affine_uv(mesh, X, Y, T):
+    """shape_funcs.py:36-49 for arrays of points X, Y inside triangles T (valid entries only)."""
+    pts = np.asarray(mesh.points, dtype=np.float64)
+    tris = np.asarray(mesh.cells[1].data).astype(np.int64)
+    t = tris[T]
+    P0, P1, P2 = pts[t[:, 0], :2], pts[t[:, 1], :2], pts[t[:, 2], :2]
+    x21, y21 = P1[:, 0] - P0[:, 0], P1[:, 1] - P0[:, 1]
+    x31, y31 = P2[:, 0] - P0[:, 0], P2[:, 1] - P0[:, 1]
+    J = x21 * y31 - x31 * y21
+    m00, m01, m10, m11 = y31 / J, (-x31) / J, (-y21) / J, x21 / J
+    dx, dy = X - P0[:, 0], Y - P0[:, 1]
+    return m00 * dx + m01 * dy, m10 * dx + m11 * dy, (t, P0, P1, P2, x21, y21, x31, y31, J)
+
+
+def get_interp_weights(mesh, xa, ya, tri_idxs, order=2):
+    """fe_solver.py:670-696 with shape_funcs.py:5-10 / 286-288."""
+    n = 6 if order == 2 else 3
+    X, Y = np.meshgrid(np.asarray(xa, dtype=np.float64), np.asarray(ya, dtype=np.float64), indexing="ij")
+    w = np.full((len(xa), len(ya), n), np.nan)
+    ok = tri_idxs != -1
+    u, v, _ = _affine_uv(mesh, X[ok], Y[ok], tri_idxs[ok])
+    if order == 2:
+        cols = [2 * (1 - u - v) * (0.5 - u - v), 2 * u * (u - 0.5), 2 * v * (v - 0.5),
+                4 * u * (1 - u - v), 4 * u * v, 4 * v * (1 - u - v)]
+    else:
+        cols = [1 - u - v, u, v]
+    w[ok] = np.stack(cols, axis=-1)
+    return w
+
+
+def get_interp_weights_vec(mesh, xa, ya, tri_idxs):
+    """fe_solver.py:698-717 with shape_funcs.py:331-353 (signs: shape_funcs.py:317-322)."""
+    X, Y = np.meshgrid(np.asarray(xa, dtype=np.float64), np.asarray(ya, dtype=np.float64), indexing="ij")
+    w = np.full((len(xa), len(ya), 3, 2), np.nan)
+    ok = tri_idxs != -1
+    x, y = X[ok], Y[ok]
+    _, _, (t, P0, P1, P2, x21, y21, x31, y31, J) = _affine_uv(mesh, x, y, tri_idxs[ok])
+    x32, y32 = P2[:, 0] - P1[:, 0], P2[:, 1] - P1[:, 1]
+    l12 = np.sqrt(x21 * x21 + y21 * y21) * np.where(t[:, 0] < t[:, 1], 1, -1)
+    l23 = np.sqrt(x32 * x32 + y32 * y32) * np.where(t[:, 1] < t[:, 2], 1, -1)
+    l31 = np.sqrt(x31 * x31 + y31 * y31) * np.where(t[:, 2] < t[:, 0], 1, -1)
+    x1, y1 = P0[:, 0], P0[:, 1]
+    vals = np.empty((len(x), 3, 2))
+    vals[:, 0, 0] = (-y + y31 + y1) / J * l12
+    vals[:, 0, 1] = (x - x31 - x1) / J * l12
+    vals[:, 1, 0] = (-y + y1) / J * l23
+    vals[:, 1, 1] = (x - x1) / J * l23
+    vals[:, 2, 0] = (-y + y21 + y1) / J * l31
+    vals[:, 2, 1] = (x - x21 - x1) / J * l31
+    w[ok] = vals
+    return w
+
+
+def interpolate(v, mesh, xa, ya, tri_idxs=None, interp_weights=None, order=2, maxr=0):
+    """fe_solver.py:719-744."""
+    tri_idxs = get_tri_idxs_KDtree(mesh, xa, ya, maxr) if tri_idxs is None else tri_idxs
+    interp_weights = get_interp_weights(mesh, xa, ya, tri_idxs, order) if interp_weights is None else interp_weights
+    tris = np.asarray(mesh.cells[1].data).astype(np.int64)
+    return np.sum(np.asarray(v)[tris[tri_idxs]] * interp_weights, axis=2)
+
+
+def interpolate_vec(v, mesh, xa, ya, tri_idxs=None, interp_weights=None, maxr=0):
+    """fe_solver.py:746-774."""
+    Ntt = len(mesh.cells[0].data)
+    vtt = np.asarray(v)[:Ntt]
+    tri_idxs = get_tri_idxs_KDtree(mesh, xa, ya, maxr) if tri_idxs is None else tri_idxs
+    interp_weights = get_interp_weights_vec(mesh, xa, ya, tri_idxs) if interp_weights is None else interp_weights
+    field_points = vtt[np.asarray(mesh.edge_indices).astype(np.int64)[tri_idxs]]
+    return np.sum(field_points[:, :, :, None] * interp_weights, axis=2)
+
+
+def interpolate_kdtree_loop(v, mesh, xa, ya, maxr=0):
+    """The reference's own control flow for a P2 mode (fe_solver.py:719-744 with the per-point KD-tree
+    search of fe_solver.py:848-872 and the per-point weight loop of fe_solver.py:670-696), kept as a
+    loop: this is what bench / tools time as the CPU baseline of the resampling path."""
+    from scipy.spatial import KDTree
+    pts = np.asarray(mesh.points, dtype=np.float64)
+    tris = np.asarray(mesh.cells[1].data).astype(np.int64)
+    tree = KDTree(np.mean(pts[tris][:, :3, :2], axis=1))                       # mesher.py:235-240
+    out = np.full((len(xa), len(ya)), np.nan, dtype=np.asarray(v).dtype)
+    max_tries = min(pts.shape[0] - 1, len(tris))
+    for i in range(len(xa)):
+        for j in range(len(ya)):
+            p = np.array([xa[i], ya[j]])
+            if maxr > 0 and np.sqrt(p[0] ** 2 + p[1] ** 2) > maxr:
+                continue
+            for tryno in range(max_tries):
+                e = tree.query(p, [tryno + 1])[1][0]
+                T = pts[tris[e, :3], :2]
+                if _isinside_all(p[0], p[1], T[0:1], T[1:2], T[2:3])[0]:
+                    x21, y21 = T[1, 0] - T[0, 0], T[1, 1] - T[0, 1]
+                    x31, y31 = T[2, 0] - T[0, 0], T[2, 1] - T[0, 1]
+                    J = x21 * y31 - x31 * y21
+                    u, w = np.dot(np.array([[y31, -x31], [-y21, x21]]) / J, p - T[0])
+                    N = np.array([2 * (1 - u - w) * (0.5 - u - w), 2 * u * (u - 0.5), 2 * w * (w - 0.5),
+                                  4 * u * (1 - u - w), 4 * u * w, 4 * w * (1 - u - w)])
+                    out[i, j] = np.sum(np.asarray(v)[tris[e]] * N)
+                    break
+    return out

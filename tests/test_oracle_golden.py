@@ -94,3 +94,37 @@ def test_scalar_p1_assembly_and_solve(name):
     w, v, cnt = R.solve_waveguide(mesh, float(z["wl"]), ior, Nmax=int(z["Nmax"]), order=1)
     assert cnt == int(z["count"])
     assert np.allclose(util.neff(w), util.neff(z["w"]), rtol=1e-10, atol=0)
+
+
+# ---- mode resampling (fe_solver.py:594-872) ---------------------------------------------------
+def _close(a, b, tol=1e-13):
+    a, b = np.asarray(a), np.asarray(b)
+    assert a.shape == b.shape
+    assert np.array_equal(np.isnan(a), np.isnan(b))
+    ok = ~np.isnan(a)
+    assert np.all(np.abs(a[ok] - b[ok]) <= tol * (1.0 + np.abs(b[ok])))
+
+
+def test_interp_p2_restatement_matches_literal_reference():
+    mesh, z = util.load_golden_mesh("interp_p2_disc600")
+    xa, ya = z["xa"], z["ya"]
+    t = R.get_tri_idxs_KDtree(mesh, xa, ya, maxr=9.9)
+    assert np.array_equal(t, z["tri_idxs"])
+    assert np.array_equal(R.get_tri_idxs_KDtree(mesh, xa, ya, maxr=7.5), z["tri_idxs_maxr"])
+    assert np.array_equal(R.get_tri_idxs(mesh, xa[::2], ya[::2]), z["tri_idxs_brute"])
+    w = R.get_interp_weights(mesh, xa, ya, t, order=2)
+    _close(w, z["weights"])
+    _close(R.interpolate(z["v"], mesh, xa, ya, maxr=9.9), z["interp"])
+    _close(R.interpolate(z["vc"], mesh, xa, ya, tri_idxs=t, interp_weights=w), z["interp_c"])
+    _close(R.interpolate(z["v"], mesh, xa, ya, maxr=7.5), z["interp_maxr"])
+
+
+def test_interp_vec_restatement_matches_literal_reference():
+    mesh, z = util.load_golden_mesh("interp_vec_disc500")
+    xa, ya = z["xa"], z["ya"]
+    t = R.get_tri_idxs_KDtree(mesh, xa, ya)
+    assert np.array_equal(t, z["tri_idxs"])
+    _close(R.get_interp_weights_vec(mesh, xa, ya, t), z["weights_vec"])
+    _close(R.get_interp_weights(mesh, xa, ya, t, order=1), z["weights_p1"])
+    _close(R.interpolate_vec(z["v"], mesh, xa, ya), z["interp_vec"])
+    _close(R.interpolate(z["vz"], mesh, xa, ya, order=1), z["interp_p1"])

@@ -19,6 +19,20 @@ def load_golden(name):
     return mesh, ior, z
 
 
+def load_golden_mesh(name):
+    """Fixtures without material data (mode resampling): mesh + arrays."""
+    z = np.load(os.path.join(GOLD, name + ".npz"), allow_pickle=False)
+    labels = [str(s) for s in z["labels"]]
+    sets = {lab: [None, z["set_%d" % i], None] for i, lab in enumerate(labels)}
+    mesh = Mesh(z["points"], z["tris"], sets)
+    if "edges" in z.files:
+        mesh.cells[0].data = z["edges"]
+        mesh.edge_indices = z["edge_indices"]
+        mesh.num_edges = len(z["edges"])
+        mesh.num_points = mesh.points.shape[0]
+    return mesh, z
+
+
 def golden_matrix(z, prefix):
     fmt = str(z[prefix + "_format"])
     cls = sp.csr_matrix if fmt == "csr" else sp.csc_matrix

@@ -24,6 +24,7 @@ SOURCES = {
     "ws_symbolic_dev.cu": [],
     "ws_factor.cu": [],
     "ws_eig.cu": [],
+    "ws_interp.cu": ["-fmad=false"],
 }
 
 

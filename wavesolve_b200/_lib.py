@@ -52,6 +52,12 @@ _SIGNATURES = {
     "ws_eig_solve": (c_int, [c_vp, c_vp, c_vp, C.c_double, c_int, c_int, c_int, C.c_double, c_int, C.c_uint64,
                              c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_int, c_vp]),
     "ws_host_eig_general": (c_int, [c_int, c_vp, c_vp, c_vp, c_vp, c_int]),
+    "ws_locator_create": (c_int, [c_vp, c_vp, c_i64, c_int, C.c_double, C.c_double, C.c_double, C.c_double,
+                                  C.POINTER(c_vp), c_int, c_vp]),
+    "ws_locator_destroy": (c_int, [c_vp]),
+    "ws_locate": (c_int, [c_vp, c_vp, c_vp, c_int, c_vp, c_vp, c_i64, c_i64, C.c_double, c_int, c_vp, c_int, c_vp]),
+    "ws_interp_weights": (c_int, [c_vp, c_vp, c_i64, c_int, c_int, c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_int, c_vp]),
+    "ws_interp_apply": (c_int, [c_vp, c_i64, c_i64, c_vp, c_int, c_int, c_int, c_vp, c_vp, c_int, c_vp, c_int, c_vp]),
     "ws_vector_T": (c_int, [c_vp, c_vp, c_vp, c_i64, c_int, c_vp, c_vp, c_int, c_vp]),
 }
 
