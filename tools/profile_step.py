@@ -19,7 +19,7 @@ def main():
 
     mg = ws.meshgen
     k = 2 * np.pi / 1.55
-    mesh = mg.fiber_disc(1_000_000, order=1, seed=0)
+    mesh = mg.fiber_disc(int(os.environ.get("WS_PROFILE_ELEMENTS", "1000000")), order=1, seed=0)
     ior = mg.FIBER_IOR
     sigma = float(np.power(k * max(ior.values()), 2))
     tris_h = np.ascontiguousarray(np.asarray(mesh.cells[1].data)[:, :3].astype(np.int32))

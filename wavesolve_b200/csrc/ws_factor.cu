@@ -75,6 +75,13 @@ struct ws_solver {
     ws::DevBuf<ws::FwdTile> fwd_tiles;
     ws::DevBuf<ws::BwdTile> bwd_tiles;
     std::vector<ws::LevelPlan> levels;      // index = tree level
+    bool plan_built = false;                // tile tasks are emitted on the first factorisation (see build_plan)
+    std::vector<ws::GemmTask> h_gemm;       // host copies stay alive: the uploads are asynchronous
+    std::vector<ws::PanelTask> h_panel;
+    std::vector<ws::ExtTask> h_ext;
+    std::vector<ws::InvTask> h_inv;
+    std::vector<ws::FwdTile> h_fwd;
+    std::vector<ws::BwdTile> h_bwd;
     ws::Range inv0;
     std::vector<std::pair<ws::Range, ws::Range>> inv_stages;   // (step1, step2) per doubling stage
     ws::Range w21;
@@ -1003,35 +1010,25 @@ static bool fused_enabled() {
     return on;
 }
 
-static void build_plan(ws_solver* s, cudaStream_t st) {
+// per-level shape and kernel choice (cheap: one pass over the per-front sizes); done at creation
+static void classify_levels(ws_solver* s) {
     const Symbolic& Y = s->sym;
     const int depth = Y.depth;
-    std::vector<GemmTask> G;
-    std::vector<PanelTask> P;
-    std::vector<ExtTask> E;
-    std::vector<InvTask> I;
-    std::vector<FwdTile> F;
-    std::vector<BwdTile> Bk;
-    double* Lb = s->L.get();
-    double* Sb = s->S.get();
-    double* Tb = s->T.get();
-    double* Ub = s->U.get();
-    double* Wb = s->W.get();
-    double* db = s->d.get();
     s->levels.assign(depth + 1, LevelPlan());
     for (int l = depth; l >= 0; --l) {
         LevelPlan& LP = s->levels[l];
         const int64_t f0 = (int64_t)1 << l, f1 = (int64_t)1 << (l + 1);
         LP.first_front = f0;
         LP.nfronts = f1 - f0;
-        int maxp = 0;
-        for (int64_t t = f0; t < f1; ++t) maxp = std::max(maxp, (int)Y.p[t]);
+        int maxp = 0, maxm = 0;
+        for (int64_t t = f0; t < f1; ++t) {
+            maxp = std::max(maxp, (int)Y.p[t]);
+            maxm = std::max(maxm, (int)(Y.p[t] + Y.q[t]));
+        }
         const int nkb = (maxp + NB - 1) / NB;
         LP.upd.assign(nkb, Range());
         LP.pan.assign(nkb, Range());
         LP.trail.assign(nkb, Range());
-        int maxm = 0;
-        for (int64_t t = f0; t < f1; ++t) maxm = std::max(maxm, (int)(Y.p[t] + Y.q[t]));
         LP.small = maxm <= FRONT_MAX_M;
         LP.nt = std::max(32, (maxm + 31) & ~31);
         LP.maxp = maxp;
@@ -1041,6 +1038,32 @@ static void build_plan(ws_solver* s, cudaStream_t st) {
         LP.right_looking = (f1 - f0) <= 64 && maxp > 4 * NB;
         LP.fused = fused_enabled() && maxm <= FUSED_MAX_M && maxp <= 64 &&
                    fused_smem_doubles(maxm, maxp) * sizeof(double) <= FUSED_MAX_SMEM;
+    }
+}
+
+// Tile-task records of the fronts that are not handled by k_front_fused.  Emitted by the first
+// factorisation AFTER it has launched the fused levels, so that the host loop (8 ms at 1M triangles)
+// runs while the GPU works on the small fronts; uploads are asynchronous (host copies live in *s).
+static void build_plan(ws_solver* s, cudaStream_t st) {
+    const Symbolic& Y = s->sym;
+    const int depth = Y.depth;
+    std::vector<GemmTask>& G = s->h_gemm;
+    std::vector<PanelTask>& P = s->h_panel;
+    std::vector<ExtTask>& E = s->h_ext;
+    std::vector<InvTask>& I = s->h_inv;
+    std::vector<FwdTile>& F = s->h_fwd;
+    std::vector<BwdTile>& Bk = s->h_bwd;
+    G.clear(); P.clear(); E.clear(); I.clear(); F.clear(); Bk.clear();
+    double* Lb = s->L.get();
+    double* Sb = s->S.get();
+    double* Tb = s->T.get();
+    double* Ub = s->U.get();
+    double* db = s->d.get();
+    for (int l = depth; l >= 0; --l) {
+        LevelPlan& LP = s->levels[l];
+        const int64_t f0 = (int64_t)1 << l, f1 = (int64_t)1 << (l + 1);
+        const int maxp = LP.maxp;
+        const int nkb = (maxp + NB - 1) / NB;
         // extend-add of the children of this level's fronts (left children first, then right)
         if (l < depth && !LP.fused) {
             for (int side = 0; side < 2; ++side) {
@@ -1268,7 +1291,7 @@ static void build_plan(ws_solver* s, cudaStream_t st) {
     upload(s->inv_tasks, I, st);
     upload(s->fwd_tiles, F, st);
     upload(s->bwd_tiles, Bk, st);
-    WS_CUDA(cudaStreamSynchronize(st));   // the host vectors die here
+    s->plan_built = true;
     if (trace)
         for (int l = 0; l <= depth; ++l)
             fprintf(stderr, "[build_plan] level %2d fronts %6lld maxp %4d maxm %4d %s nt %d\n", l, (long long)s->levels[l].nfronts,
@@ -1462,7 +1485,8 @@ int ws_solver_create(const ws_pattern* p, const ws_symbolic* sym, ws_solver** ou
         WS_CUDA(cudaMemcpyAsync(&bad, s->stats.get(), sizeof bad, cudaMemcpyDeviceToHost, st));
         count_launch(2);
         const double tc2 = tnow();
-        build_plan(s, st);   // synchronises the stream
+        classify_levels(s);
+        WS_CUDA(cudaStreamSynchronize(st));
         if (trace)
             fprintf(stderr, "[ws_solver_create] copy+upload+alloc %.1f ms, dest map %.1f ms, plan %.1f ms\n",
                     (tc1 - tc0) * 1e3, (tc2 - tc1) * 1e3, (tnow() - tc2) * 1e3);
@@ -1511,6 +1535,7 @@ int ws_solver_factor(ws_solver* s, const double* A_vals, const double* B_vals, d
             count_launch(1);
             continue;
         }
+        if (!s->plan_built) build_plan(s, st);
         if (LP.ext_left.cnt) {
             k_extend_add<<<(unsigned)LP.ext_left.cnt, 256, 0, st>>>(s->ext_tasks.get() + LP.ext_left.off, fv, s->L.get(), s->U.get());
             count_launch(1);
@@ -1530,6 +1555,7 @@ int ws_solver_factor(ws_solver* s, const double* A_vals, const double* B_vals, d
         }
         launch_gemm(s, LP.syrk, false, st);
     }
+    if (!s->plan_built) build_plan(s, st);
     // selective inversion: S_top = L11^-1, S_bottom = L21 * L11^-1
     if (s->inv0.cnt) {
         k_diag_inverse<<<(unsigned)s->inv0.cnt, 32, 0, st>>>(s->inv_tasks.get());
