@@ -431,10 +431,12 @@ struct FusedCtx {
     double* U;
     double* d;
     unsigned long long* stats;
+    const int32_t* wsrc0;   // gather maps of the solve sweeps: row of the parent -> position of the
+    const int32_t* wsrc1;   // child's boundary entry in W (or -1); reused here for the extend-add
 };
 
 __host__ __device__ inline size_t fused_smem_doubles(int m, int p) {
-    return 5 * (size_t)((p + 1) & ~1) + 8 + (size_t)(m | 1) * p;
+    return 5 * (size_t)((p + 1) & ~1) + 8 + (size_t)(m | 1) * p + (size_t)(m | 1) + 1;
 }
 
 template <int PMAX>
@@ -451,32 +453,45 @@ __global__ void k_front_fused(int64_t first, int has_children, FusedCtx cx) {
     const int tid = threadIdx.x, NT = blockDim.x;
     const double* Lg = cx.L + fv.Loff[t];
     double* Ut = cx.U + fv.Uoff[t];
-    // (1) panel -> shared memory
+    // (1)+(2) panel -> shared memory, with the extend-add of the two children folded in as a GATHER:
+    // entry (r, c) of this front receives U_child[j(r), j(c)] where j() is the position of the
+    // row in the child's boundary list (-1 if absent), read from the sweep gather maps.  Every
+    // panel entry and every entry of the update matrix is written exactly once -- no read-modify-
+    // write chains through global memory (those serialised the separator fronts).
+    int32_t* jm0 = reinterpret_cast<int32_t*>(P + (size_t)ld * p);      // [m] child 0, [m] child 1
+    int32_t* jm1 = jm0 + m;
+    int qc0 = 0, qc1 = 0;
+    const double* U0 = nullptr;
+    const double* U1 = nullptr;
+    if (has_children) {
+        const int64_t c0 = 2 * t, c1 = 2 * t + 1;
+        qc0 = fv.q[c0];
+        qc1 = fv.q[c1];
+        U0 = cx.U + fv.Uoff[c0];
+        U1 = cx.U + fv.Uoff[c1];
+        if (tid < m) {
+            const int64_t w = fv.woff[t] + tid;
+            const int32_t s0 = cx.wsrc0[w], s1 = cx.wsrc1[w];
+            jm0[tid] = s0 >= 0 ? (int32_t)(s0 - (fv.woff[c0] + fv.p[c0])) : -1;
+            jm1[tid] = s1 >= 0 ? (int32_t)(s1 - (fv.woff[c1] + fv.p[c1])) : -1;
+        }
+        __syncthreads();
+    }
     if (tid < m) {
         const double* src = Lg + tid;
         double* dst = P + tid;
-        for (int j = 0; j < p; ++j, src += m, dst += ld) *dst = *src;
-    }
-    __syncthreads();
-    // (2) extend-add of the two children (their boundaries are subsets of this front: q_c <= m)
-    if (has_children) {
-        for (int side = 0; side < 2; ++side) {
-            const int64_t c = 2 * t + side;
-            const int qc = fv.q[c];
-            const int32_t* rel = fv.rel + fv.bndoff[c];
-            const double* Uc = cx.U + fv.Uoff[c];
-            if (tid < qc) {
-                const int ri = rel[tid];
-                for (int j = 0; j <= tid; ++j) {
-                    const int rj = rel[j];
-                    const double v = Uc[tid + (size_t)j * qc];
-                    if (rj < p) P[ri + rj * ld] += v;
-                    else Ut[(ri - p) + (size_t)(rj - p) * q] += v;
-                }
+        const int jr0 = has_children ? jm0[tid] : -1, jr1 = has_children ? jm1[tid] : -1;
+        for (int j = 0; j < p; ++j, src += m, dst += ld) {
+            double v = *src;
+            if (has_children && j <= tid) {
+                const int jc0 = jm0[j], jc1 = jm1[j];
+                if (jr0 >= 0 && jc0 >= 0) v += U0[jr0 + (size_t)jc0 * qc0];
+                if (jr1 >= 0 && jc1 >= 0) v += U1[jr1 + (size_t)jc1 * qc1];
             }
-            __syncthreads();
+            *dst = v;
         }
     }
+    __syncthreads();
     // (3) LDL^T of the p pivot columns, right-looking, thread i owns row i (no atomics, one barrier per
     // pivot: only the pivot column of the p x p block is exchanged, double-buffered).  The owner of
     // row k+1 has the shortest update of step k, so it also inverts the next pivot while the others
@@ -599,7 +614,13 @@ __global__ void k_front_fused(int64_t first, int has_children, FusedCtx cx) {
             for (; k < p; ++k, la += ld, lb += ld) acc0 += la[0] * (dd[k] * lb[0]);
             acc0 += acc2;
             acc1 += acc3;
-            Ut[a + (size_t)b * q] -= acc0 + acc1;
+            double g = 0.0;
+            if (has_children) {
+                const int ja0 = jm0[p + a], jb0 = jm0[p + b], ja1 = jm1[p + a], jb1 = jm1[p + b];
+                if (ja0 >= 0 && jb0 >= 0) g += U0[ja0 + (size_t)jb0 * qc0];
+                if (ja1 >= 0 && jb1 >= 0) g += U1[ja1 + (size_t)jb1 * qc1];
+            }
+            Ut[a + (size_t)b * q] = g - (acc0 + acc1);
         }
     };
     // row-oriented in-place inversion of the unit lower triangle: row i of X is
@@ -1528,7 +1549,7 @@ int ws_solver_factor(ws_solver* s, const double* A_vals, const double* B_vals, d
     for (int l = Y.depth; l >= 0; --l) {
         const LevelPlan& LP = s->levels[l];
         if (LP.fused) {
-            FusedCtx fc{fv, s->L.get(), s->S.get(), s->U.get(), s->d.get(), s->stats.get()};
+            FusedCtx fc{fv, s->L.get(), s->S.get(), s->U.get(), s->d.get(), s->stats.get(), s->wsrc0.get(), s->wsrc1.get()};
             const size_t sh = fused_smem_doubles(LP.maxm, LP.maxp) * sizeof(double);
             if (LP.maxp <= 48) k_front_fused<0><<<(unsigned)LP.nfronts, LP.nt, sh, st>>>(LP.first_front, l < Y.depth ? 1 : 0, fc);
             else k_front_fused<64><<<(unsigned)LP.nfronts, LP.nt, sh, st>>>(LP.first_front, l < Y.depth ? 1 : 0, fc);
