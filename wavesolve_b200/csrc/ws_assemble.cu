@@ -20,6 +20,8 @@
 #include <algorithm>
 #include <cstdlib>
 
+#include <cub/cub.cuh>
+
 #include "ws_common.cuh"
 
 namespace ws {
@@ -566,38 +568,83 @@ int ws_assemble_vector_qd(const ws_pattern* p, const double* xy, const int32_t* 
 
 // x = T y (mode 0):  x_t[i] = y_t[i] - (y_z[hi] - y_z[lo]) / len_i ,  x_z = y_z
 // y = T^T b (mode 1): y_t = b_t ,  y_z[j] = b_z[j] - sum_{i: hi=j} b_t[i]/len_i + sum_{i: lo=j} b_t[i]/len_i
-// The node rows gather over the pattern row (which lists every edge of the surrounding
-// triangles) so the sum order is fixed.
-__global__ void k_vector_T(int64_t N, int64_t Ntt, int mode, const int32_t* __restrict__ rowptr,
-                           const int32_t* __restrict__ colidx, const int2* __restrict__ edges,
-                           const double2* __restrict__ xy, const double* __restrict__ in, double* __restrict__ out) {
+// Edge lengths and the node -> incident-edge lists (ascending edge id, so the sum order is fixed)
+// are built once per (edge table, coordinates) and cached in the pattern object: both modes are
+// then two short gathers per entry instead of a walk over the pattern row with a square root per edge.
+__global__ void k_vt_len(int64_t Ntt, const int2* __restrict__ edges, const double2* __restrict__ xy, double* __restrict__ len,
+                         int32_t* __restrict__ deg) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= Ntt) return;
+    const int2 e = edges[i];
+    const double2 a = xy[e.x], b = xy[e.y];
+    len[i] = sqrt((b.x - a.x) * (b.x - a.x) + (b.y - a.y) * (b.y - a.y));
+    atomicAdd(&deg[e.x], 1);
+    atomicAdd(&deg[e.y], 1);
+}
+__global__ void k_vt_fill(int64_t Ntt, const int2* __restrict__ edges, const int32_t* __restrict__ nptr, int32_t* __restrict__ cur,
+                          int32_t* __restrict__ nadj) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= Ntt) return;
+    const int2 e = edges[i];
+    nadj[nptr[e.x] + atomicAdd(&cur[e.x], 1)] = (int32_t)(i << 1);
+    nadj[nptr[e.y] + atomicAdd(&cur[e.y], 1)] = (int32_t)(i << 1) | 1;
+}
+__global__ void k_vt_sort(int64_t Nzz, const int32_t* __restrict__ nptr, int32_t* __restrict__ nadj) {
+    const int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (j >= Nzz) return;
+    const int a = nptr[j], b = nptr[j + 1];
+    for (int i = a + 1; i < b; ++i) {          // insertion sort of a handful of entries
+        const int32_t v = nadj[i];
+        int k = i - 1;
+        while (k >= a && nadj[k] > v) { nadj[k + 1] = nadj[k]; --k; }
+        nadj[k + 1] = v;
+    }
+}
+__global__ void k_vector_T(int64_t N, int64_t Ntt, int mode, const int2* __restrict__ edges, const double* __restrict__ len,
+                           const int32_t* __restrict__ nptr, const int32_t* __restrict__ nadj, const double* __restrict__ in,
+                           double* __restrict__ out) {
     const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (r >= N) return;
+    double v = in[r];
     if (r < Ntt) {
-        double v = in[r];
         if (mode == 0) {
             const int2 e = edges[r];
-            const double2 a = xy[e.x], b = xy[e.y];
-            const double len = sqrt((b.x - a.x) * (b.x - a.x) + (b.y - a.y) * (b.y - a.y));
-            v -= (in[Ntt + e.y] - in[Ntt + e.x]) / len;
+            v -= (in[Ntt + e.y] - in[Ntt + e.x]) / len[r];
         }
-        out[r] = v;
-    } else {
-        double v = in[r];
-        if (mode == 1) {
-            const int j = (int)(r - Ntt);
-            for (int s = rowptr[r]; s < rowptr[r + 1]; ++s) {
-                const int c = colidx[s];
-                if (c >= Ntt) break;            // columns are sorted: edges first
-                const int2 e = edges[c];
-                if (e.x != j && e.y != j) continue;
-                const double2 a = xy[e.x], b = xy[e.y];
-                const double len = sqrt((b.x - a.x) * (b.x - a.x) + (b.y - a.y) * (b.y - a.y));
-                v += (e.y == j ? -in[c] : in[c]) / len;
-            }
+    } else if (mode == 1) {
+        const int64_t j = r - Ntt;
+        for (int s = nptr[j]; s < nptr[j + 1]; ++s) {
+            const int32_t a = nadj[s];
+            const int32_t c = a >> 1;
+            v += ((a & 1) ? -in[c] : in[c]) / len[c];
         }
-        out[r] = v;
     }
+    out[r] = v;
+}
+
+static void vt_prepare(const ws_pattern* p, const int32_t* edges, const double* xy, int64_t Ntt, cudaStream_t st) {
+    if (p->vt_edges == edges && p->vt_xy == xy && p->vt_Ntt == Ntt) return;
+    const int64_t Nzz = p->N - Ntt;
+    p->vt_len.alloc(std::max<int64_t>(Ntt, 1), st);
+    p->vt_nptr.alloc(Nzz + 1, st);
+    p->vt_nadj.alloc(std::max<int64_t>(2 * Ntt, 1), st);
+    DevBuf<int32_t> deg(Nzz + 1, st), cur(Nzz + 1, st);
+    WS_CUDA(cudaMemsetAsync(deg.get(), 0, deg.bytes(), st));
+    WS_CUDA(cudaMemsetAsync(cur.get(), 0, cur.bytes(), st));
+    const int T = 256;
+    if (Ntt) k_vt_len<<<ceil_div(Ntt, T), T, 0, st>>>(Ntt, (const int2*)edges, (const double2*)xy, p->vt_len.get(), deg.get());
+    size_t bytes = 0;
+    WS_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, bytes, deg.get(), p->vt_nptr.get(), Nzz + 1, st));
+    DevBuf<char> tmp(bytes, st);
+    WS_CUDA(cub::DeviceScan::ExclusiveSum(tmp.get(), bytes, deg.get(), p->vt_nptr.get(), Nzz + 1, st));
+    if (Ntt) k_vt_fill<<<ceil_div(Ntt, T), T, 0, st>>>(Ntt, (const int2*)edges, p->vt_nptr.get(), cur.get(), p->vt_nadj.get());
+    if (Nzz) k_vt_sort<<<ceil_div(Nzz, T), T, 0, st>>>(Nzz, p->vt_nptr.get(), p->vt_nadj.get());
+    WS_CUDA(cudaGetLastError());
+    count_launch(3);
+    p->vt_edges = edges;
+    p->vt_xy = xy;
+    p->vt_Ntt = Ntt;
+    // (deg / cur / tmp are released stream-ordered: cudaFreeAsync after the kernels that use them)
 }
 
 int ws_vector_T(const ws_pattern* p, const int32_t* edges, const double* xy, int64_t Ntt, int mode,
@@ -608,8 +655,9 @@ int ws_vector_T(const ws_pattern* p, const int32_t* edges, const double* xy, int
     WS_REQUIRE(Ntt >= 0 && Ntt <= p->N && (mode == 0 || mode == 1), "bad Ntt / mode");
     DeviceGuard g(device);
     if (p->N) {
-        k_vector_T<<<ceil_div(p->N, 256), 256, 0, (cudaStream_t)stream>>>(p->N, Ntt, mode, p->rowptr.get(), p->colidx.get(),
-                                                                          (const int2*)edges, (const double2*)xy, in, out);
+        vt_prepare(p, edges, xy, Ntt, (cudaStream_t)stream);
+        k_vector_T<<<ceil_div(p->N, 256), 256, 0, (cudaStream_t)stream>>>(p->N, Ntt, mode, (const int2*)edges, p->vt_len.get(),
+                                                                          p->vt_nptr.get(), p->vt_nadj.get(), in, out);
         WS_CUDA(cudaGetLastError());
         count_launch(1);
     }

@@ -134,4 +134,12 @@ struct ws_pattern {
     ws::DevBuf<int32_t> incptr;   // [N+1]
     ws::DevBuf<uint32_t> inc;     // [6*Ne]
     ws::DevBuf<uint16_t> pos;     // [36*Ne]
+    // cache of ws_vector_T (vector problem): edge lengths and the node -> incident-edge lists of the
+    // discrete gradient, built on the first application for a given (edge table, coordinates)
+    mutable const void* vt_edges = nullptr;
+    mutable const void* vt_xy = nullptr;
+    mutable int64_t vt_Ntt = -1;
+    mutable ws::DevBuf<double> vt_len;        // [Ntt]
+    mutable ws::DevBuf<int32_t> vt_nptr;      // [Nzz + 1]
+    mutable ws::DevBuf<int32_t> vt_nadj;      // [2*Ntt]  edge id << 1 | (node is the edge's head)
 };

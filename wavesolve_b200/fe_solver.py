@@ -73,8 +73,11 @@ def _k2n2_host(mesh, IOR_dict, k):
 
 def _as_i32(a, what):
     a = np.asarray(a)
-    if a.size and (int(a.max()) >= 2 ** 31 or int(a.min()) < 0):
-        raise ValueError("%s must be non-negative and fit in int32" % what)
+    if a.size:
+        # one pass: seen as unsigned bit patterns of the same width, negative ids are huge
+        bits = a.view(np.dtype("u%d" % a.dtype.itemsize)) if a.dtype.kind == "i" and a.flags.c_contiguous else a
+        if a.dtype.kind not in "iu" or int(bits.max()) >= 2 ** 31 or (bits is a and a.dtype.kind == "i" and int(a.min()) < 0):
+            raise ValueError("%s must be non-negative integers that fit in int32" % what)
     return np.ascontiguousarray(a.astype(np.int32))
 
 
