@@ -7,7 +7,7 @@ import wavesolve_b200 as ws
 from wavesolve_b200 import fe_solver as fs, solver as sv
 mg = ws.meshgen
 k = 2 * np.pi / 1.55
-for seed in (0, 1):
+for seed in (0, 1, 2):
     mesh = mg.fiber_disc(1_000_000, order=1, seed=seed)
     ws.get_unique_edges(mesh)
     sigma = (k * max(mg.FIBER_IOR.values())) ** 2
@@ -16,7 +16,7 @@ for seed in (0, 1):
     sym = sv.Symbolic.on_device(prob.dofs, prob.xy, prob.N, prob.Ntt)
     S = sv.Solver(prob.pattern, sym)
     S.factor(Mq)
-    for ncv in (21, 24, 28, 32, 40, 48):
+    for ncv in [int(x) for x in os.environ.get('WS_NCVS', '21,24,28,32,40,48').split(',')]:
         torch.cuda.synchronize(); t0 = time.perf_counter()
         w, V, info = fs._eig_device(prob.pattern, S, B, sigma, 1, 10, prob.N, prob.dev, ncv=ncv, edges=prob.edges, xy=prob.xy, Ntt=prob.Ntt)
         torch.cuda.synchronize(); dt = time.perf_counter() - t0

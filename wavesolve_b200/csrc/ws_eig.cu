@@ -788,7 +788,11 @@ int ws_eig_solve(const ws_pattern* p, ws_solver* s, const double* B_vals, double
             break;
         }
         // ---- thick restart: keep k Ritz directions (ARPACK-style: more as they converge)
+        static const int keep_policy = getenv("WS_EIG_KEEP") ? atoi(getenv("WS_EIG_KEEP")) : 0;
         int k = nev + std::min(nconv, (m - nev) / 2);
+        if (keep_policy == 1) k = nev + (m - nev) / 2;
+        else if (keep_policy == 2) k = nev + (m - nev) / 3;
+        else if (keep_policy == 3) k = nev + std::max(std::min(nconv, (m - nev) / 2), (m - nev) / 4);
         if (k >= m - 1) k = m - 2;
         // kept columns of Y; a complex-conjugate pair contributes its real and imaginary parts
         std::vector<int> keep;
