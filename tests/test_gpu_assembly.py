@@ -246,3 +246,29 @@ def test_fast_mode_and_fused_qd_assembly(ws):
     M3, B3 = vp.assemble_qd(sigma, with_B=True, fast=True)
     assert (M3 - M1).abs().max().item() <= 1e-13 * M1.abs().max().item()
     assert (B3 - B).abs().max().item() <= 1e-14 * B.abs().max().item()
+
+
+def test_pinned_result_buffers_are_recycled(ws):
+    """Large results come back through page-locked blocks that are recycled once the caller drops the
+    array and every view of it (wavesolve_b200.device.d2h_pinned)."""
+    import gc
+    from wavesolve_b200 import device as d
+    x = torch.arange(1 << 18, dtype=torch.float64, device="cuda")
+    nbytes = x.numel() * 8
+    d._pinned_free.pop(nbytes, None)
+    a = d.d2h_pinned(x)
+    assert a.dtype == np.float64 and np.array_equal(a, np.arange(1 << 18, dtype=np.float64))
+    p0 = a.ctypes.data
+    view = a[:16].view(np.uint64)
+    del a
+    gc.collect()
+    assert not d._pinned_free.get(nbytes)                 # a view still uses the block
+    b = d.d2h_pinned(x * 2)                               # needs a second block
+    assert b.ctypes.data != p0 and b[3] == 6.0
+    del view
+    gc.collect()
+    assert len(d._pinned_free[nbytes]) == 1
+    c = d.d2h_pinned(x + 1)
+    assert c.ctypes.data == p0 and c[0] == 1.0 and b[3] == 6.0   # recycled, and b is untouched
+    z = d.d2h_pinned(torch.view_as_complex(torch.ones(1 << 17, 2, dtype=torch.float64, device="cuda")))
+    assert z.dtype == np.complex128 and z[5] == 1 + 1j

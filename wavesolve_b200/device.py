@@ -1,6 +1,9 @@
 """Host <-> device plumbing (PyTorch is used for device memory and streams only)."""
 from __future__ import annotations
 
+import threading
+import weakref
+
 import numpy as np
 import torch
 
@@ -38,17 +41,38 @@ def d2h(t: torch.Tensor) -> np.ndarray:
     return t.detach().cpu().numpy()
 
 
+_pinned_lock = threading.Lock()
+_pinned_free = {}          # nbytes -> [page-locked uint8 tensors that no result array uses any more]
+_PINNED_KEEP = 3           # free buffers kept per size
+
+
+def _pinned_release(nbytes, buf):
+    with _pinned_lock:
+        lst = _pinned_free.setdefault(nbytes, [])
+        if len(lst) < _PINNED_KEEP:
+            lst.append(buf)
+
+
 def d2h_pinned(t: torch.Tensor) -> np.ndarray:
-    """Device -> host copy of a large result through page-locked memory (torch's caching host
-    allocator keeps the block for the next call once the caller drops the array; a pageable
-    ``.cpu()`` of the 160 MB eigenvector block costs several times the DMA time in page faults).
-    The returned numpy array owns the pinned block."""
-    t = t.detach()
-    if t.numel() < (1 << 16):
+    """Device -> host copy of a large result through page-locked memory.  A pageable ``.cpu()`` of
+    the 160-320 MB eigenvector block costs several times the DMA time in page faults, and so does
+    pinning a fresh block per call, so the blocks are recycled: the returned numpy array owns its
+    block, and when the caller drops the array (and every view of it) the block goes back to a small
+    free list for the next call of the same size."""
+    t = t.detach().contiguous()
+    nbytes = t.numel() * t.element_size()
+    if nbytes < (1 << 20):
         return t.cpu().numpy()
-    out = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
-    out.copy_(t)
-    return out.numpy()
+    with _pinned_lock:
+        lst = _pinned_free.get(nbytes)
+        buf = lst.pop() if lst else None
+    if buf is None:
+        buf = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+    host = buf.view(t.dtype).view(t.shape)
+    host.copy_(t)
+    arr = host.numpy()
+    weakref.finalize(arr, _pinned_release, nbytes, buf)
+    return arr
 
 
 def as_complex(t: torch.Tensor) -> torch.Tensor:
