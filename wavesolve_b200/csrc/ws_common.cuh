@@ -133,7 +133,8 @@ struct ws_pattern {
     // pos[6*i + b] is the position inside row r of column dofs[e*6+b].
     ws::DevBuf<int32_t> incptr;   // [N+1]
     ws::DevBuf<uint32_t> inc;     // [6*Ne]
-    ws::DevBuf<uint16_t> pos;     // [36*Ne]
+    ws::DevBuf<uint16_t> pos;     // [36*Ne]  bit 15: this is the first contribution to its slot
+    bool first_touch = false;     // the bit-15 flags are valid (no element lists an unknown twice)
     // cache of ws_vector_T (vector problem): edge lengths and the node -> incident-edge lists of the
     // discrete gradient, built on the first application for a given (edge table, coordinates)
     mutable const void* vt_edges = nullptr;

@@ -116,6 +116,33 @@ __global__ void k_positions(const uint64_t* __restrict__ inc_keys, int64_t n_inc
     pos[t] = (uint16_t)(lo - base);
 }
 
+// bit 15 of pos[6*i+b]: no earlier incidence of the same row (= lower element, the reference's
+// summation order) contributes to the same slot, so the assembly may STORE this contribution
+// instead of read-modify-write and needs no zero-fill.  dup is raised when an element lists an
+// unknown twice (scalar P1 rides the six-unknown machinery as v0 v1 v2 v0 v1 v2): then the flags are
+// not used.
+__global__ void k_first_touch(const uint64_t* __restrict__ inc_keys, int64_t n_inc, const int32_t* __restrict__ dofs,
+                              const int32_t* __restrict__ incptr, uint16_t* __restrict__ pos, int32_t* __restrict__ dup) {
+    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= n_inc * 6) return;
+    const int64_t i = t / 6;
+    const int b = (int)(t % 6);
+    const uint64_t key = inc_keys[i];
+    const int32_t r = (int32_t)(key >> 32);
+    const uint32_t e = (uint32_t)key >> 3;
+    const int32_t* de = dofs + (int64_t)e * 6;
+    const int32_t col = de[b];
+    for (int b2 = 0; b2 < 6; ++b2)
+        if (b2 != b && de[b2] == col) { *dup = 1; return; }
+    bool first = true;
+    for (int64_t i2 = incptr[r]; i2 < i && first; ++i2) {
+        const int32_t* d2 = dofs + (int64_t)((uint32_t)inc_keys[i2] >> 3) * 6;
+        for (int b2 = 0; b2 < 6; ++b2)
+            if (d2[b2] == col) first = false;
+    }
+    if (first) pos[t] |= 0x8000u;
+}
+
 // ---- K1 kernels ---------------------------------------------------------------------------
 __global__ void k_edge_keys(const int32_t* __restrict__ tris, int64_t n3, uint64_t* __restrict__ keys,
                             uint32_t* __restrict__ vals) {
@@ -337,11 +364,21 @@ int ws_pattern_create(const int32_t* dofs, int64_t Ne, int64_t N, ws_pattern** o
         k_max_blockslots<<<ceil_div(nblocks128, T), T, 0, st>>>(P->rowptr.get(), N, 128, per_group, d_counts.get() + 2);
         P->pos.alloc(n_pair, st);
         k_positions<<<ceil_div(n_pair, T), T, 0, st>>>(ik1.get(), n_inc, dofs, P->rowptr.get(), P->colidx.get(), P->pos.get());
+        DevBuf<int32_t> d_dup(1, st);
+        WS_CUDA(cudaMemsetAsync(d_dup.get(), 0, sizeof(int32_t), st));
+        int32_t h_dup = 0;
         int32_t h_mx[2 + NR] = {0};
         WS_CUDA(cudaMemcpyAsync(h_mx, d_counts.get() + 1, (2 + NR) * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
         WS_CUDA(cudaStreamSynchronize(st));
         WS_CUDA(cudaGetLastError());
         const int32_t h_max = h_mx[0];
+        if (h_max < 32768) {     // bit 15 of pos is free
+            k_first_touch<<<ceil_div(n_pair, T), T, 0, st>>>(ik1.get(), n_inc, dofs, P->incptr.get(), P->pos.get(), d_dup.get());
+            WS_CUDA(cudaMemcpyAsync(&h_dup, d_dup.get(), sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+            WS_CUDA(cudaStreamSynchronize(st));
+            P->first_touch = h_dup == 0;
+            count_launch(1);
+        }
         P->max_row_len = h_max;
         P->max_block_slots = h_mx[1];
         for (int g2 = 0; g2 < NR; ++g2) P->range_block_slots[g2] = h_mx[2 + g2];
