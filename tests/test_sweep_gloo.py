@@ -135,6 +135,11 @@ def test_sweep_matches_individual_solves():
     probs = [sweep.SweepProblem(mi, wl, mg.FIBER_IOR) for mi in range(2) for wl in wls]
     res = sweep.solve_sweep(meshes, probs, Nmax=6, kind="vector")
     assert [r.index for r in res] == list(range(len(probs)))
+    # concurrent lanes (own stream + solver storage + host thread each) must give the same answers
+    res3 = sweep.solve_sweep(meshes, probs, Nmax=6, kind="vector", lanes=3)
+    for a, b in zip(res, res3):
+        assert a.index == b.index and a.mode_count == b.mode_count
+        assert np.max(np.abs(a.w - b.w) / np.abs(a.w)) < 1e-10
     for r, pr in zip(res, probs):
         w, v, cnt = ws.solve_waveguide_vec(meshes[pr.mesh_id], pr.wl, pr.IOR_dict, Nmax=6, verbose=False)
         k = 2 * np.pi / pr.wl

@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--wavelengths", type=int, default=8)
     ap.add_argument("--elements", type=int, default=50_000)
     ap.add_argument("--nmax", type=int, default=10)
+    ap.add_argument("--lanes", type=int, default=0)
     a = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -51,7 +52,7 @@ def main():
     if world > 1:
         dist.barrier()
     t0 = time.perf_counter()
-    res = sweep.solve_sweep(meshes, probs, Nmax=a.nmax, kind="vector")
+    res = sweep.solve_sweep(meshes, probs, Nmax=a.nmax, kind="vector", lanes=a.lanes or None)
     torch.cuda.synchronize()
     dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
     if world > 1:

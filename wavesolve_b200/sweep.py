@@ -192,13 +192,22 @@ class _MeshContext:
 
 def solve_sweep(meshes: Sequence, problems: Sequence[SweepProblem], Nmax: int = 10, kind: str = "vector",
                 group=None, device=None, leaf_elems=None, with_vectors: bool = True, gather: bool = True,
-                dst: Optional[int] = None):
+                dst: Optional[int] = None, lanes: Optional[int] = None):
     """Solve every problem of the sweep, this rank taking its share (``partition``), and gather.
 
     ``meshes``: mesh objects (vector sweeps: already passed through ``get_unique_edges``), the same
     list on every rank.  Returns a list of ``SweepResult`` in problem order (on every rank, or on
-    ``dst`` only), or this rank's own results when ``gather=False``."""
+    ``dst`` only), or this rank's own results when ``gather=False``.
+
+    ``lanes``: problems solved concurrently on this GPU, each on its own CUDA stream with its own
+    solver storage, driven by its own host thread (the C calls release the GIL).  An eigensolve on a
+    mesh of ~50k triangles is a chain of ~3000 short dependent kernels that fills a fraction of a
+    B200, so several independent problems overlap almost for free; a 1M-triangle problem saturates
+    the GPU by itself.  Default 1: measured on a B200 with 32 problems of 100k unknowns, 2 lanes give
+    +15 % and 4 or 8 lanes are slower than one (the lanes contend for the stream-ordered memory pool
+    and the driver; tools/bench_sweep.py --lanes N) -- kept as an opt-in until that is resolved."""
     from . import device as _dev, fe_solver as fs
+    import threading
     assert kind in ("vector", "scalar")
     dist = _dist()
     multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
@@ -214,41 +223,77 @@ def solve_sweep(meshes: Sequence, problems: Sequence[SweepProblem], Nmax: int = 
     sizes = [n_unknowns(m) for m in meshes]
     table = partition([p.mesh_id for p in problems], [estimate_cost(sizes[p.mesh_id]) for p in problems], world)
     mine = table[rank]
+    if lanes is None:
+        lanes = 1
+    lanes = max(1, min(int(lanes), max(1, len(mine))))
     local, infos = {}, {}
     # one flat send buffer per rank: [w_0 | V_0 | w_1 | V_1 ...]; the eigensolver writes into its views
     # (sized for the largest rank payload so that it can be handed to all_gather unpadded)
     total = max(sum(Nmax * (1 + sizes[problems[i].mesh_id]) for i in r) for r in table)
     with torch.cuda.device(dev):
         sendbuf = torch.zeros(max(total, 1), dtype=torch.float64, device=dev)
-        off = 0
-        ctx, ctx_mesh = None, None
+        offsets, off = {}, 0
         for i in mine:
-            pr = problems[i]
-            k = 2 * np.pi / pr.wl
-            if ctx_mesh != pr.mesh_id:
-                if ctx is not None:
-                    ctx.close()
-                ctx = _MeshContext(meshes[pr.mesh_id], kind, pr.IOR_dict, k, dev, leaf_elems)
-                ctx_mesh = pr.mesh_id
-            else:
-                ctx.prob.set_materials(ctx.mesh, pr.IOR_dict, k)
-            N = ctx.prob.N
-            wv = sendbuf[off:off + Nmax]
-            Vv = sendbuf[off + Nmax:off + Nmax + Nmax * N].view(Nmax, N)
-            off += Nmax * (1 + N)
-            nmax_ior = max(pr.IOR_dict.values())
-            sigma = float(np.power(k * (nmax_ior if pr.target_neff is None else pr.target_neff), 2))
-            if kind == "vector":
-                _, _, info = fs.solve_vector_resident(ctx.prob, sigma, Nmax, solver=ctx.solver, out=(wv, Vv))
-            else:
-                _, _, info = fs.solve_scalar_resident(ctx.prob, sigma, Nmax, solver=ctx.solver, out=(wv, Vv))
-            w_host = wv.cpu().numpy()
-            cnt = fs._count_modes(w_host, k, pr.IOR_dict,
-                                  always=(kind == "vector" and pr.target_neff is not None))
-            local[i] = (wv, Vv, cnt)
-            infos[i] = info
-        if ctx is not None:
-            ctx.close()
+            offsets[i] = off
+            off += Nmax * (1 + sizes[problems[i].mesh_id])
+        # problems of one mesh are dealt round-robin to the lanes (consecutive in `mine`), so the lanes
+        # work on the same mesh at the same time and each keeps one resident context
+        lane_items = [mine[l::lanes] for l in range(lanes)]
+        main_stream = torch.cuda.current_stream(dev)
+        errors = []
+
+        def run_lane(items, stream):
+            try:
+                with torch.cuda.device(dev), torch.cuda.stream(stream):
+                    ctx, ctx_mesh = None, None
+                    for i in items:
+                        pr = problems[i]
+                        k = 2 * np.pi / pr.wl
+                        if ctx_mesh != pr.mesh_id:
+                            if ctx is not None:
+                                ctx.close()
+                            ctx = _MeshContext(meshes[pr.mesh_id], kind, pr.IOR_dict, k, dev, leaf_elems)
+                            ctx_mesh = pr.mesh_id
+                        else:
+                            ctx.prob.set_materials(ctx.mesh, pr.IOR_dict, k)
+                        N = ctx.prob.N
+                        o = offsets[i]
+                        wv = sendbuf[o:o + Nmax]
+                        Vv = sendbuf[o + Nmax:o + Nmax + Nmax * N].view(Nmax, N)
+                        nmax_ior = max(pr.IOR_dict.values())
+                        sigma = float(np.power(k * (nmax_ior if pr.target_neff is None else pr.target_neff), 2))
+                        if kind == "vector":
+                            _, _, info = fs.solve_vector_resident(ctx.prob, sigma, Nmax, solver=ctx.solver, out=(wv, Vv))
+                        else:
+                            _, _, info = fs.solve_scalar_resident(ctx.prob, sigma, Nmax, solver=ctx.solver, out=(wv, Vv))
+                        w_host = wv.cpu().numpy()
+                        cnt = fs._count_modes(w_host, k, pr.IOR_dict,
+                                              always=(kind == "vector" and pr.target_neff is not None))
+                        local[i] = (wv, Vv, cnt)
+                        infos[i] = info
+                    if ctx is not None:
+                        ctx.close()
+                    stream.synchronize()
+            except BaseException as e:      # re-raised on the calling thread
+                errors.append(e)
+
+        if lanes == 1:
+            run_lane(lane_items[0], main_stream)
+        else:
+            streams = [torch.cuda.Stream(device=dev) for _ in range(lanes)]
+            for st_ in streams:
+                st_.wait_stream(main_stream)          # sendbuf is zero-filled on the caller's stream
+            threads = [threading.Thread(target=run_lane, args=(lane_items[l], streams[l]), daemon=True)
+                       for l in range(lanes)]
+            for t in threads:
+                t.start()
+            for t in threads:
+                t.join()
+            for st_ in streams:
+                main_stream.wait_stream(st_)
+        if errors:
+            raise errors[0]
+        local = {i: local[i] for i in mine}      # send-buffer order (the lanes finish in any order)
         torch.cuda.synchronize(dev)
         if not gather:
             return [SweepResult(i, local[i][0].cpu().numpy(), local[i][1].cpu().numpy() if with_vectors else None,
