@@ -1024,6 +1024,7 @@ static FrontView view(const ws_solver* s) {
                      s->fr_woff.get(), s->fr_bndoff.get(), s->bnd.get(), s->rel.get()};
 }
 
+constexpr int OUTER_NB = 4 * NB;                  // outer block of the right-looking top levels
 constexpr int FUSED_MAX_M = 256;                  // one thread per front row
 constexpr size_t FUSED_MAX_SMEM = 72 * 1024;     // >= 3 resident CTAs per SM
 static bool fused_enabled() {
@@ -1149,14 +1150,19 @@ static void build_plan(ws_solver* s, cudaStream_t st) {
             LP.pan[kb].cnt = (int64_t)P.size() - LP.pan[kb].off;
             LP.trail[kb].off = (int64_t)G.size();
             if (LP.right_looking)
+                // two-level blocking: after block column kb only the rest of its OUTER block (OB columns)
+                // is updated (rank NB, cheap: m x <= OB-NB entries); the trailing matrix beyond the outer
+                // block gets one rank-OB update when the outer block is complete -- a quarter of the
+                // passes over the trailing matrix and four times the arithmetic intensity per pass.
                 for (int64_t t = f0; t < f1; ++t) {
                     const int p = Y.p[t], m = p + Y.q[t];
                     if (p <= k0) continue;
                     const int nbk = std::min(NB, p - k0);
                     const int c0 = k0 + nbk;           // first trailing row / column
+                    const int J0 = (k0 / OUTER_NB) * OUTER_NB, Jend = std::min(J0 + OUTER_NB, p);
                     double* Lt = Lb + Y.Loff[t];
                     for (int i0 = c0; i0 < m; i0 += GT)
-                        for (int j0 = c0; j0 <= i0 && j0 < p; j0 += GT) {
+                        for (int j0 = c0; j0 <= i0 && j0 < Jend; j0 += GT) {
                             GemmTask g{};
                             g.A = Lt + i0 + (size_t)k0 * m;
                             g.B = Lt + j0 + (size_t)k0 * m;
@@ -1164,11 +1170,26 @@ static void build_plan(ws_solver* s, cudaStream_t st) {
                             g.dscale = db + Y.start[t] + k0;
                             g.lda = g.ldb = g.ldc = m;
                             g.m = std::min(GT, m - i0);
-                            g.n = std::min(GT, p - j0);
+                            g.n = std::min(GT, Jend - j0);     // never beyond the outer block
                             g.k = nbk;
                             g.flags = GF_ACCUM | GF_NEG;
                             G.push_back(g);
                         }
+                    if (c0 >= Jend && Jend < p)
+                        for (int i0 = Jend; i0 < m; i0 += GT)
+                            for (int j0 = Jend; j0 <= i0 && j0 < p; j0 += GT) {
+                                GemmTask g{};
+                                g.A = Lt + i0 + (size_t)J0 * m;
+                                g.B = Lt + j0 + (size_t)J0 * m;
+                                g.C = Lt + i0 + (size_t)j0 * m;
+                                g.dscale = db + Y.start[t] + J0;
+                                g.lda = g.ldb = g.ldc = m;
+                                g.m = std::min(GT, m - i0);
+                                g.n = std::min(GT, p - j0);
+                                g.k = Jend - J0;
+                                g.flags = GF_ACCUM | GF_NEG;
+                                G.push_back(g);
+                            }
                 }
             LP.trail[kb].cnt = (int64_t)G.size() - LP.trail[kb].off;
         }
