@@ -520,6 +520,44 @@ __global__ void __launch_bounds__(128) k_rotate(double* __restrict__ V, int64_t 
     if (move_residual) V[(size_t)k * ldv + n] = res;
 }
 
+// the same rotation with the basis column held in REGISTERS (MM >= m, fully unrolled, statically
+// indexed): the generic kernel above indexes col[] dynamically, which puts it in local memory
+template <int MM>
+__global__ void __launch_bounds__(128) k_rotate_t(double* __restrict__ V, int64_t ldv, int m, int k,
+                                                  const double* __restrict__ Q, int64_t N, int move_residual,
+                                                  double* __restrict__ out, int64_t ldo) {
+    extern __shared__ double qs[];
+    for (int i = threadIdx.x; i < m * k; i += blockDim.x) qs[i] = Q[i];
+    __syncthreads();
+    const int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    double col[MM];
+#pragma unroll
+    for (int j = 0; j < MM; ++j) col[j] = j < m ? V[(size_t)j * ldv + n] : 0.0;
+    const double res = move_residual ? V[(size_t)m * ldv + n] : 0.0;
+    double* dst = out ? out : V;
+    const int64_t ldd = out ? ldo : ldv;
+    for (int i = 0; i < k; ++i) {
+        double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+        for (int j = 0; j < MM; j += 2) {
+            if (j < m) s0 += qs[j * k + i] * col[j];
+            if (j + 1 < m) s1 += qs[(j + 1) * k + i] * col[j + 1];
+        }
+        dst[(size_t)i * ldd + n] = s0 + s1;
+    }
+    if (move_residual) V[(size_t)k * ldv + n] = res;
+}
+
+static void launch_rotate(double* V, int64_t ldv, int m, int k, const double* Q, int64_t N, int move_residual, double* out,
+                          int64_t ldo, cudaStream_t st) {
+    const size_t sh = (size_t)m * k * sizeof(double);
+    const int grid = ceil_div(N, 128);
+    if (m <= 24) k_rotate_t<24><<<grid, 128, sh, st>>>(V, ldv, m, k, Q, N, move_residual, out, ldo);
+    else if (m <= 32) k_rotate_t<32><<<grid, 128, sh, st>>>(V, ldv, m, k, Q, N, move_residual, out, ldo);
+    else k_rotate<<<grid, 128, sh, st>>>(V, ldv, m, k, Q, N, move_residual, out, ldo);
+}
+
 __global__ void k_scale_rows(double* __restrict__ X, int64_t ld, int nrows, const double* __restrict__ nrm2, int64_t N) {
     const int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (n >= N) return;
@@ -863,9 +901,9 @@ int ws_eig_solve(const ws_pattern* p, ws_solver* s, const double* B_vals, double
         tr_host += th1 - th0;
         WS_CUDA(cudaMemcpyAsync(W.Hd.get(), Hh.data(), Hh.size() * sizeof(double), cudaMemcpyHostToDevice, st));
         WS_CUDA(cudaMemcpyAsync(W.Q.get(), Qc.data(), Qc.size() * sizeof(double), cudaMemcpyHostToDevice, st));
-        k_rotate<<<ceil_div(N, 128), 128, (size_t)m * kk * sizeof(double), st>>>(V, N, m, kk, W.Q.get(), N, 1, nullptr, 0);
+        launch_rotate(V, N, m, kk, W.Q.get(), N, 1, nullptr, 0, st);
         if (kind == 0)
-            k_rotate<<<ceil_div(N, 128), 128, (size_t)m * kk * sizeof(double), st>>>(Z, N, m, kk, W.Q.get(), N, 1, nullptr, 0);
+            launch_rotate(Z, N, m, kk, W.Q.get(), N, 1, nullptr, 0, st);
         count_launch(kind == 0 ? 2 : 1);
         WS_CUDA(cudaStreamSynchronize(st));     // Qc / Hh are host temporaries
         tr_rot += tick() - th1;
@@ -897,7 +935,7 @@ int ws_eig_solve(const ws_pattern* p, ws_solver* s, const double* B_vals, double
         for (int r = 0; r < m; ++r) Qx[(size_t)r * nev + i] = Y[(size_t)r * m + c0] / nn;
     }
     WS_CUDA(cudaMemcpyAsync(W.Q.get(), Qx.data(), Qx.size() * sizeof(double), cudaMemcpyHostToDevice, st));
-    k_rotate<<<ceil_div(N, 128), 128, (size_t)m * nev * sizeof(double), st>>>(V, N, m, nev, W.Q.get(), N, 0, V_out, N);
+    launch_rotate(V, N, m, nev, W.Q.get(), N, 0, V_out, N, st);
     count_launch(1);
     if (kind == 1) {
         // unit 2-norm rows (what ARPACK's dneupd returns)
