@@ -164,6 +164,8 @@ int ws_symbolic_destroy(ws_symbolic* s);
  *                    Synchronises the stream once to read the pivot statistics; returns
  *                    WS_ERR_NUMERIC on a zero / non-finite pivot.
  * ws_solver_solve  : x = M^-1 b, nrhs right-hand sides stored contiguously [nrhs*N]; asynchronous.
+ *                    Right-hand sides are swept in pairs that share every load of the inverted
+ *                    panels (1.26 ms for two vs 1.03 ms for one at 1M triangles).
  * ws_solver_stats  : h_info[8] = nnz(L), fronts, max front, bytes, negative pivots, positive
  *                    pivots, bad pivots, tree depth; h_dinfo[3] = factor flops, min |pivot|,
  *                    max |pivot|.  (negative / positive pivots = inertia of M: Sylvester's law
@@ -199,6 +201,10 @@ int ws_vector_T(const ws_pattern* p, const int32_t* edges, const double* xy, int
  *         eigs(spsolve(A - sigma B, B), k, which='SR'), fe_solver.py:398-400); `s` holds the
  *         factorisation of the quasi-definite M' (ws_assemble_vector_qd) and edges/xy/Ntt
  *         describe T; eigenvectors come back with unit 2-norm.
+ * kind 2: as kind 1 with block size 2: two basis vectors go through the operator per step and share
+ *         one pair of sweeps (ws_solver_solve with nrhs = 2 costs 1.22x one right-hand side).  On the
+ *         1M-triangle problem it needs 102-122 operator applications instead of 80, so it is not
+ *         faster end to end (measured); kept as an option for operators whose application dominates more.
  * ncv <= 0 -> max(2 nev + 4, 20) (scipy: 2 nev + 1; three more vectors save 1-2 restart cycles at
  * tol = eps on these problems); tol <= 0 -> machine epsilon (scipy's default).
  * w [nev] (device): lambda = sigma + 1/theta, descending.  V [nev*N] (device): row j =

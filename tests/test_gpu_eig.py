@@ -183,3 +183,30 @@ def test_scalar_p1_assembly_and_solve_vs_reference_golden(ws, name):
     check_fields(w, v, z["w"], z["v"], util.golden_matrix(z, "B"))
     with pytest.raises(AssertionError):
         ws.solve_waveguide(mesh, float(z["wl"]), ior, order=2)
+
+
+def test_block2_arnoldi_matches_single_vector(ws):
+    """kind 2 (block size 2: two basis vectors share one pair of sweeps) finds the same eigenpairs
+    as the single-vector iteration."""
+    from wavesolve_b200 import fe_solver as fs, solver as sv
+    mg = ws.meshgen
+    mesh = mg.fiber_disc(20000, order=1, seed=8)
+    ws.get_unique_edges(mesh)
+    k = 2 * np.pi / 1.55
+    sigma = (k * max(mg.FIBER_IOR.values())) ** 2
+    prob = fs.VectorProblem(mesh, mg.FIBER_IOR, k)
+    Mq, B = prob.assemble_qd(sigma, with_B=True, fast=True)
+    S = sv.Solver(prob.pattern, sv.Symbolic.on_device(prob.dofs, prob.xy, prob.N, prob.Ntt))
+    S.factor(Mq)
+    out = {}
+    for kind in (1, 2):
+        w, V, info = fs._eig_device(prob.pattern, S, B, sigma, kind, 8, prob.N, prob.dev, edges=prob.edges, xy=prob.xy,
+                                    Ntt=prob.Ntt)
+        out[kind] = (w.cpu().numpy(), V.cpu().numpy(), info)
+        assert info["nconv"] == 8
+    w1, V1, _ = out[1]
+    w2, V2, i2 = out[2]
+    assert i2["n_op"] % 2 == 0
+    assert np.max(np.abs(np.sqrt(w1) - np.sqrt(w2)) / np.sqrt(w1)) < 1e-10
+    for g in util.group_degenerate(w1, rtol=1e-7):
+        assert util.subspace_overlap(V1[g], V2[g]) >= 1 - 1e-8

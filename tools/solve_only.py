@@ -15,6 +15,7 @@ def main():
     ap.add_argument("--elements", type=int, default=1_000_000)
     ap.add_argument("--solves", type=int, default=3)
     ap.add_argument("--factors", type=int, default=1)
+    ap.add_argument("--nrhs", type=int, default=1)
     ap.add_argument("--leaf", type=int, default=0)
     a = ap.parse_args()
     import torch
@@ -33,7 +34,8 @@ def main():
     S = sv.Solver(prob.pattern, sym)
     for _ in range(a.factors):
         st = S.factor(Mq)
-    b = torch.randn(prob.N, dtype=torch.float64, device="cuda")
+    b = torch.randn(prob.N, dtype=torch.float64, device="cuda") if a.nrhs == 1 else \
+        torch.randn((a.nrhs, prob.N), dtype=torch.float64, device="cuda")
     x = torch.empty_like(b)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     S.solve(b, out=x)
@@ -42,7 +44,7 @@ def main():
         S.solve(b, out=x)
     e1.record()
     torch.cuda.synchronize()
-    y = prob.pattern.spmv(B, x)
+    y = prob.pattern.spmv(B, x if a.nrhs == 1 else x[0])
     print("N %d nnzL %d solve %.3f ms  (%.0f GB/s)  depth %d" % (prob.N, st["nnzL"], e0.elapsed_time(e1) / a.solves,
           16 * st["nnzL"] / (e0.elapsed_time(e1) / a.solves * 1e-3) / 1e9, st["depth"]))
 

@@ -604,12 +604,287 @@ int ws_host_eig_general(int n, const double* h_A, double* h_wr, double* h_wi, do
     WS_API_END
 }
 
+// ---------------------------------------------------------------------------------------------
+// Block (size 2) Arnoldi with thick restart for the vector problem (kind 1).  The operator
+// application is bound by the bytes of the inverted panels, which one sweep can share between two
+// right-hand sides (ws_solver_solve, nrhs = 2): a block step applies OP to two basis vectors for
+// little more than the price of one.  Basis column c is OP v_c orthogonalised against v_0..v_{c+1}
+// and normalised into slot c+2, so H is band-Hessenberg with two subdiagonals and the residual of
+// a Ritz pair is ||R y||, R = rows m, m+1 of the (m+2) x m projected matrix.
+// ---------------------------------------------------------------------------------------------
+static void eig_solve_block2(const ws_pattern* p, ws_solver* s, const double* B_vals, double sigma, int nev, int m,
+                             double tol, int maxit, uint64_t seed, const int32_t* edges, const double* xy, int64_t Ntt,
+                             double* w_out, double* V_out, int64_t* h_info, double* h_resid, int device, cudaStream_t st) {
+    const int64_t N = p->N;
+    const int LD = m + 2;
+    EigWork W;
+    W.N = N; W.ncv = m; W.st = st;
+    W.nchunks = ceil_div(N, DOT_CHUNK);
+    W.V.alloc((size_t)(m + 2) * N, st);
+    W.w.alloc(2 * N, st); W.t1.alloc(2 * N, st); W.t2.alloc(2 * N, st); W.t3.alloc(2 * N, st);
+    W.partial.alloc((size_t)W.nchunks * MAXV, st);
+    W.h.alloc(MAXV, st);
+    W.Hd.alloc((size_t)LD * m, st);
+    W.nrm.alloc(MAXV, st);
+    W.Q.alloc((size_t)MAXV * MAXV, st);
+    double* V = W.V.get();
+    const int T = 256;
+    const int nb = ceil_div(N, T);
+    auto vecT = [&](cudaStream_t q, int mode, const double* in, double* out) {
+        int rc = ws_vector_T(p, edges, xy, Ntt, mode, in, out, device, (void*)q);
+        if (rc) throw Error(rc, ws_last_error());
+    };
+    // OP applied to basis vectors j, j+1 (contiguous rows of V) -> W.w (two vectors)
+    auto apply_op2 = [&](cudaStream_t q, int j, int nrhs) {
+        for (int r = 0; r < nrhs; ++r) {
+            spmv_launch(p, B_vals, V + (size_t)(j + r) * N, W.t1.get() + (size_t)r * N, q);
+            vecT(q, 1, W.t1.get() + (size_t)r * N, W.t2.get() + (size_t)r * N);
+        }
+        int rc = ws_solver_solve(s, W.t2.get(), W.t3.get(), nrhs, device, (void*)q);
+        if (rc) throw Error(rc, ws_last_error());
+        for (int r = 0; r < nrhs; ++r) vecT(q, 0, W.t3.get() + (size_t)r * N, W.w.get() + (size_t)r * N);
+    };
+    // orthogonalise wv against rows 0..nvec-1 (CGS2), normalise into slot `slot`
+    auto orth_into = [&](cudaStream_t q, double* wv, int nvec, int slot, double* Hcol) {
+        for (int pass = 0; pass < 2 && nvec > 0; ++pass) {
+            dots(W, q, V, nvec, wv, W.h.get(), Hcol);
+            k_update<<<nb, T, 0, q>>>(wv, V, N, nvec, W.h.get(), N);
+            count_launch(1);
+        }
+        dots(W, q, wv, 1, wv, W.nrm.get(), nullptr);
+        k_normalize<<<nb, T, 0, q>>>(wv, nullptr, W.nrm.get(), Hcol ? Hcol + slot : nullptr, V + (size_t)slot * N, nullptr, N);
+        count_launch(1);
+    };
+    auto block_step = [&](cudaStream_t q, int j) {
+        apply_op2(q, j, 2);
+        orth_into(q, W.w.get(), j + 2, j + 2, W.Hd.get() + (size_t)j * LD);
+        orth_into(q, W.w.get() + N, j + 3, j + 3, W.Hd.get() + (size_t)(j + 1) * LD);
+    };
+    struct GraphSet {
+        std::vector<cudaGraphExec_t> exec;
+        cudaStream_t cap = nullptr;
+        ~GraphSet() {
+            for (auto e : exec)
+                if (e) cudaGraphExecDestroy(e);
+            if (cap) cudaStreamDestroy(cap);
+        }
+    } graphs;
+    graphs.exec.assign(m, nullptr);
+    const char* nog = getenv("WS_NO_GRAPH");
+    const bool use_graphs = !(nog && atoi(nog));
+    if (use_graphs) WS_CUDA(cudaStreamCreateWithFlags(&graphs.cap, cudaStreamNonBlocking));
+    auto run_step = [&](int j) {
+        if (!use_graphs) {
+            block_step(st, j);
+            return;
+        }
+        if (!graphs.exec[j]) {
+            cudaGraph_t g = nullptr;
+            WS_CUDA(cudaStreamBeginCapture(graphs.cap, cudaStreamCaptureModeThreadLocal));
+            try {
+                block_step(graphs.cap, j);
+            } catch (...) {
+                cudaStreamEndCapture(graphs.cap, &g);
+                if (g) cudaGraphDestroy(g);
+                throw;
+            }
+            WS_CUDA(cudaStreamEndCapture(graphs.cap, &g));
+            cudaError_t e = cudaGraphInstantiate(&graphs.exec[j], g, 0);
+            cudaGraphDestroy(g);
+            if (e != cudaSuccess) throw Error(WS_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e));
+        }
+        WS_CUDA(cudaGraphLaunch(graphs.exec[j], st));
+        count_launch(1);
+    };
+    // ---- start block: two random vectors pushed once through OP (uncaptured: loads every kernel)
+    k_random<<<nb, T, 0, st>>>(V, N, seed ? seed : 0x5DEECE66Dull);
+    k_random<<<nb, T, 0, st>>>(V + N, N, (seed ? seed : 0x5DEECE66Dull) ^ 0x9E3779B97F4A7C15ull);
+    count_launch(2);
+    apply_op2(st, 0, 2);
+    orth_into(st, W.w.get(), 0, 0, nullptr);
+    orth_into(st, W.w.get() + N, 1, 1, nullptr);
+    WS_CUDA(cudaMemsetAsync(W.Hd.get(), 0, W.Hd.bytes(), st));
+
+    std::vector<double> Hh((size_t)LD * m, 0.0);
+    std::vector<double> theta_r(m), theta_i(m), Y, resid(m, 0.0);
+    std::vector<int> order(m);
+    int j0 = 0, nconv = 0, restarts = 0, kkeep = 0;
+    int64_t nops = 2;
+    const double eps23 = std::pow(2.220446049250313e-16, 2.0 / 3.0);
+    std::vector<double> Hm((size_t)m * m);
+    while (true) {
+        for (int j = j0; j < m; j += 2) {
+            run_step(j);
+            nops += 2;
+        }
+        WS_CUDA(cudaMemcpyAsync(Hh.data(), W.Hd.get(), Hh.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
+        WS_CUDA(cudaStreamSynchronize(st));
+        WS_CUDA(cudaGetLastError());
+        bool finite = true;
+        for (double v : Hh) finite = finite && std::isfinite(v);
+        if (!finite) throw Error(WS_ERR_NUMERIC, "non-finite projected matrix in the block Krylov iteration");
+        for (int i = 0; i < m; ++i)
+            for (int j = 0; j < m; ++j) Hm[(size_t)i * m + j] = Hh[(size_t)j * LD + i];
+        std::vector<double> A = Hm;
+        if (!eig_general(m, A, theta_r, theta_i, Y)) throw Error(WS_ERR_NOCONV, "dense QR iteration did not converge");
+        std::iota(order.begin(), order.end(), 0);
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return theta_r[a] < theta_r[b]; });
+        // residual of a Ritz pair: || R y || / || y ||,  R = rows m, m+1 of the projected matrix
+        auto rdot = [&](int row, int c) {
+            double sacc = 0.0;
+            for (int j = 0; j < m; ++j) sacc += Hh[(size_t)j * LD + row] * Y[(size_t)j * m + c];
+            return sacc;
+        };
+        auto colnorm2 = [&](int c) {
+            double sacc = 0.0;
+            for (int i = 0; i < m; ++i) sacc += Y[(size_t)i * m + c] * Y[(size_t)i * m + c];
+            return sacc;
+        };
+        auto ritz_res = [&](int c) {
+            if (theta_i[c] == 0.0) return std::sqrt((rdot(m, c) * rdot(m, c) + rdot(m + 1, c) * rdot(m + 1, c)) / colnorm2(c));
+            const int c0 = theta_i[c] > 0 ? c : c - 1;
+            const double a0 = rdot(m, c0), a1 = rdot(m, c0 + 1), b0 = rdot(m + 1, c0), b1 = rdot(m + 1, c0 + 1);
+            return std::sqrt((a0 * a0 + a1 * a1 + b0 * b0 + b1 * b1) / (colnorm2(c0) + colnorm2(c0 + 1)));
+        };
+        nconv = 0;
+        for (int i = 0; i < nev; ++i) {
+            const int c = order[i];
+            resid[i] = ritz_res(c);
+            const double mag = std::hypot(theta_r[c], theta_i[c]);
+            if (resid[i] <= tol * std::max(eps23, mag)) ++nconv;
+        }
+        ++restarts;
+        if (nconv >= nev || restarts >= maxit) break;
+        // ---- thick restart: keep an even number of Ritz directions
+        int k = nev + std::min(nconv, (m - nev) / 2);
+        k += k & 1;
+        if (k > m - 2) k = m - 2;
+        std::vector<int> keep;
+        {
+            std::vector<char> used(m, 0);
+            for (int i = 0; i < m && (int)keep.size() < k; ++i) {
+                const int c = order[i];
+                if (used[c]) continue;
+                if (theta_i[c] == 0.0) {
+                    keep.push_back(c);
+                    used[c] = 1;
+                } else {
+                    const int c0 = theta_i[c] > 0.0 ? c : c - 1;
+                    if ((int)keep.size() + 2 > m - 2) break;
+                    keep.push_back(c0);
+                    keep.push_back(c0 + 1);
+                    used[c0] = used[c0 + 1] = 1;
+                }
+            }
+            k = (int)keep.size();
+        }
+        std::vector<double> Qh((size_t)m * k, 0.0);
+        for (int i = 0; i < k; ++i)
+            for (int r = 0; r < m; ++r) Qh[(size_t)r * k + i] = Y[(size_t)r * m + keep[i]];
+        int kk = 0;
+        for (int i = 0; i < k; ++i) {
+            for (int pass = 0; pass < 2; ++pass)
+                for (int jq = 0; jq < kk; ++jq) {
+                    double d = 0.0;
+                    for (int r = 0; r < m; ++r) d += Qh[(size_t)r * k + jq] * Qh[(size_t)r * k + i];
+                    for (int r = 0; r < m; ++r) Qh[(size_t)r * k + i] -= d * Qh[(size_t)r * k + jq];
+                }
+            double nn = 0.0;
+            for (int r = 0; r < m; ++r) nn += Qh[(size_t)r * k + i] * Qh[(size_t)r * k + i];
+            nn = std::sqrt(nn);
+            if (nn < 1e-10) continue;
+            for (int r = 0; r < m; ++r) Qh[(size_t)r * k + kk] = Qh[(size_t)r * k + i] / nn;
+            ++kk;
+        }
+        kk -= kk & 1;                      // the remaining columns are processed in pairs
+        if (kk < 2) throw Error(WS_ERR_NOCONV, "block Krylov restart lost its basis");
+        std::vector<double> Qc((size_t)m * kk);
+        for (int r = 0; r < m; ++r)
+            for (int i = 0; i < kk; ++i) Qc[(size_t)r * kk + i] = Qh[(size_t)r * k + i];
+        kkeep = kk;
+        std::vector<double> HQ((size_t)m * kk, 0.0);
+        for (int r = 0; r < m; ++r)
+            for (int c = 0; c < kk; ++c) {
+                double sacc = 0.0;
+                for (int q2 = 0; q2 < m; ++q2) sacc += Hm[(size_t)r * m + q2] * Qc[(size_t)q2 * kk + c];
+                HQ[(size_t)r * kk + c] = sacc;
+            }
+        std::vector<double> Hn((size_t)LD * m, 0.0);
+        for (int c = 0; c < kk; ++c) {
+            for (int r = 0; r < kk; ++r) {
+                double sacc = 0.0;
+                for (int q2 = 0; q2 < m; ++q2) sacc += Qc[(size_t)q2 * kk + r] * HQ[(size_t)q2 * kk + c];
+                Hn[(size_t)c * LD + r] = sacc;
+            }
+            for (int rr = 0; rr < 2; ++rr) {
+                double sacc = 0.0;
+                for (int q2 = 0; q2 < m; ++q2) sacc += Hh[(size_t)q2 * LD + m + rr] * Qc[(size_t)q2 * kk + c];
+                Hn[(size_t)c * LD + kk + rr] = sacc;
+            }
+        }
+        Hh = Hn;
+        WS_CUDA(cudaMemcpyAsync(W.Hd.get(), Hh.data(), Hh.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+        WS_CUDA(cudaMemcpyAsync(W.Q.get(), Qc.data(), Qc.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+        launch_rotate(V, N, m, kk, W.Q.get(), N, 1, nullptr, 0, st);                 // rows 0..kk-1, row m -> row kk
+        WS_CUDA(cudaMemcpyAsync(V + (size_t)(kk + 1) * N, V + (size_t)(m + 1) * N, N * sizeof(double), cudaMemcpyDeviceToDevice, st));
+        count_launch(1);
+        WS_CUDA(cudaStreamSynchronize(st));     // Qc / Hh are host temporaries
+        j0 = kk;
+    }
+    // ---- Ritz vectors, ordered by descending lambda = sigma + 1/theta
+    std::vector<int> sel(order.begin(), order.begin() + nev);
+    std::vector<double> lam(nev), lam_i(nev);
+    for (int i = 0; i < nev; ++i) {
+        const std::complex<double> th(theta_r[sel[i]], theta_i[sel[i]]);
+        const std::complex<double> l = sigma + 1.0 / th;
+        lam[i] = l.real();
+        lam_i[i] = l.imag();
+    }
+    std::vector<int> ord2(nev);
+    std::iota(ord2.begin(), ord2.end(), 0);
+    std::stable_sort(ord2.begin(), ord2.end(), [&](int a, int b) { return lam[a] > lam[b]; });
+    std::vector<double> Qx((size_t)m * nev), wh(nev), rh(nev);
+    int ncomplex = 0;
+    for (int i = 0; i < nev; ++i) {
+        const int c = sel[ord2[i]];
+        wh[i] = lam[ord2[i]];
+        rh[i] = resid[ord2[i]];
+        if (lam_i[ord2[i]] != 0.0) ++ncomplex;
+        const int c0 = theta_i[c] < 0 ? c - 1 : c;
+        double nn = 0.0;
+        for (int r = 0; r < m; ++r) nn += Y[(size_t)r * m + c0] * Y[(size_t)r * m + c0];
+        nn = std::sqrt(nn);
+        for (int r = 0; r < m; ++r) Qx[(size_t)r * nev + i] = Y[(size_t)r * m + c0] / nn;
+    }
+    WS_CUDA(cudaMemcpyAsync(W.Q.get(), Qx.data(), Qx.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+    launch_rotate(V, N, m, nev, W.Q.get(), N, 0, V_out, N, st);
+    count_launch(1);
+    for (int i = 0; i < nev; ++i) dots(W, st, V_out + (size_t)i * N, 1, V_out + (size_t)i * N, W.nrm.get() + i, nullptr);
+    k_scale_rows<<<nb, T, 0, st>>>(V_out, N, nev, W.nrm.get(), N);
+    count_launch(1);
+    WS_CUDA(cudaMemcpyAsync(w_out, wh.data(), nev * sizeof(double), cudaMemcpyHostToDevice, st));
+    WS_CUDA(cudaStreamSynchronize(st));
+    WS_CUDA(cudaGetLastError());
+    if (getenv("WS_TRACE"))
+        fprintf(stderr, "[ws_eig block2] N=%lld ops=%lld (%lld sweeps) restarts=%d nconv=%d\n", (long long)N, (long long)nops,
+                (long long)(nops / 2), restarts, nconv);
+    if (h_info) {
+        h_info[0] = nconv; h_info[1] = nops; h_info[2] = restarts; h_info[3] = ncomplex; h_info[4] = kkeep;
+    }
+    if (h_resid) std::copy(rh.begin(), rh.end(), h_resid);
+    if (nconv < nev) throw Error(WS_ERR_NOCONV, "eigensolver: " + std::to_string(nconv) + " of " + std::to_string(nev) +
+                                                    " eigenpairs converged in " + std::to_string(restarts) + " restarts");
+}
+
 int ws_eig_solve(const ws_pattern* p, ws_solver* s, const double* B_vals, double sigma, int kind, int nev, int ncv,
                  double tol, int maxit, uint64_t seed, const int32_t* edges, const double* xy, int64_t Ntt,
                  double* w_out, double* V_out, int64_t* h_info, double* h_resid, int device, void* stream) {
     WS_API_BEGIN
     WS_REQUIRE(p && s && B_vals && w_out && V_out, "null pointer");
-    WS_REQUIRE(kind == 0 || kind == 1, "kind must be 0 (B-orthogonal, symmetric) or 1 (Euclidean, non-symmetric)");
+    WS_REQUIRE(kind == 0 || kind == 1 || kind == 2,
+               "kind must be 0 (B-orthogonal, symmetric), 1 (Euclidean, non-symmetric) or 2 (as 1, block size 2)");
+    const bool want_block = kind == 2;
+    if (kind == 2) kind = 1;
     const int64_t N = p->N;
     WS_REQUIRE(nev >= 1 && nev < N - 1, "1 <= nev < N-1");
     // scipy's default is ncv = max(2k+1, 20) (arpack.py); with the convergence test at tol = eps that
@@ -623,6 +898,16 @@ int ws_eig_solve(const ws_pattern* p, ws_solver* s, const double* B_vals, double
     if (maxit <= 0) maxit = 300;
     DeviceGuard g(device);
     cudaStream_t st = (cudaStream_t)stream;
+    {
+        static const int block = getenv("WS_EIG_BLOCK") ? atoi(getenv("WS_EIG_BLOCK")) : 1;
+        if (kind == 1 && (block == 2 || want_block) && N > 4 * ncv) {
+            int mb = ncv + (ncv & 1);
+            if (mb + 2 >= MAXV) mb -= 2;
+            eig_solve_block2(p, s, B_vals, sigma, nev, mb, tol, maxit, seed, edges, xy, Ntt, w_out, V_out, h_info, h_resid,
+                             device, st);
+            return WS_OK;
+        }
+    }
     const int m = ncv;
     EigWork W;
     W.N = N; W.ncv = m; W.st = st;

@@ -719,27 +719,38 @@ struct SolveCtx {
     double* W;      // boundary remainders of every front (forward)
     double* yd;     // D^-1 y, permuted order
     double* x;      // solution, permuted order
+    int64_t sW;     // stride between right-hand sides in W
+    int64_t sN;     // stride between right-hand sides in yd / x / b / xout (= N)
 };
 
-__device__ __forceinline__ double fwd_gather(const SolveCtx& cx, const FrontRec& R, int i, int has_children,
-                                             const double* __restrict__ b) {
-    double v = (i < R.p) ? b[cx.perm[R.start + i]] : 0.0;
+// NR right-hand sides share every load of the inverted panels: a sweep is bound by the panel bytes,
+// so a second vector costs its own (small) vector traffic and arithmetic only.
+template <int NR>
+__device__ __forceinline__ void fwd_gather(const SolveCtx& cx, const FrontRec& R, int i, int has_children,
+                                           const double* __restrict__ b, double (&v)[NR]) {
+    const int32_t pi = (i < R.p) ? cx.perm[R.start + i] : -1;
+    int s0 = -1, s1 = -1;
     if (has_children) {
-        const int s0 = cx.wsrc0[R.woff + i], s1 = cx.wsrc1[R.woff + i];
-        if (s0 >= 0) v += cx.W[s0];
-        if (s1 >= 0) v += cx.W[s1];
+        s0 = cx.wsrc0[R.woff + i];
+        s1 = cx.wsrc1[R.woff + i];
     }
-    return v;
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+        double t = pi >= 0 ? b[pi + r * cx.sN] : 0.0;
+        if (s0 >= 0) t += cx.W[s0 + r * cx.sW];
+        if (s1 >= 0) t += cx.W[s1 + r * cx.sW];
+        v[r] = t;
+    }
 }
 
 // one CTA per front, one thread per front row (blockDim.x >= m, multiple of 32, <= MAXT).
 // The k loop is double-buffered: KB loads of the next batch are in flight while the current
 // batch is multiplied.  (MAXT only sets the register budget: with a 1024-thread bound ptxas has
 // 64 registers and serialises the batch, so small fronts get their own instantiation.)
-template <int MAXT, int KB>
+template <int MAXT, int KB, int NR>
 __global__ void __launch_bounds__(MAXT) k_fwd_front(int64_t first, int has_children, SolveCtx cx,
-                                                    const double* __restrict__ b) {
-    extern __shared__ double sw[];
+                                                    const double* __restrict__ b, int pstride) {
+    extern __shared__ double sw[];          // [NR][pstride]
     pdl_launch_dependents();
     const FrontRec R = cx.recs[first + blockIdx.x];
     const int p = R.p, m = p + R.q, r = threadIdx.x;
@@ -752,34 +763,51 @@ __global__ void __launch_bounds__(MAXT) k_fwd_front(int64_t first, int has_child
     for (int j = 0; j < KB; ++j) a[j] = (j < kend) ? __ldg(Sr + (size_t)j * ld) : 0.0;
 #pragma unroll
     for (int j = 0; j < KB; ++j) c[j] = (KB + j < kend) ? __ldg(Sr + (size_t)(KB + j) * ld) : 0.0;
-    double wv = 0.0;
+    double wv[NR];
+#pragma unroll
+    for (int q = 0; q < NR; ++q) wv[q] = 0.0;
     pdl_wait();
     if (act) {
-        wv = fwd_gather(cx, R, r, has_children, b);
-        if (r < p) sw[r] = wv;
+        fwd_gather<NR>(cx, R, r, has_children, b, wv);
+        if (r < p) {
+#pragma unroll
+            for (int q = 0; q < NR; ++q) sw[q * pstride + r] = wv[q];
+        }
     }
     __syncthreads();
-    double acc0 = 0.0, acc1 = 0.0;
+    double acc0[NR], acc1[NR];
+#pragma unroll
+    for (int q = 0; q < NR; ++q) acc0[q] = acc1[q] = 0.0;
     for (int k0 = 0; k0 < kend; k0 += 2 * KB) {
 #pragma unroll
         for (int j = 0; j < KB; j += 2) {
-            if (k0 + j < kend) acc0 += a[j] * sw[k0 + j];
-            if (k0 + j + 1 < kend) acc1 += a[j + 1] * sw[k0 + j + 1];
+#pragma unroll
+            for (int q = 0; q < NR; ++q) {
+                if (k0 + j < kend) acc0[q] += a[j] * sw[q * pstride + k0 + j];
+                if (k0 + j + 1 < kend) acc1[q] += a[j + 1] * sw[q * pstride + k0 + j + 1];
+            }
         }
 #pragma unroll
         for (int j = 0; j < KB; ++j) a[j] = (k0 + 2 * KB + j < kend) ? __ldg(Sr + (size_t)(k0 + 2 * KB + j) * ld) : 0.0;
 #pragma unroll
         for (int j = 0; j < KB; j += 2) {
-            if (k0 + KB + j < kend) acc0 += c[j] * sw[k0 + KB + j];
-            if (k0 + KB + j + 1 < kend) acc1 += c[j + 1] * sw[k0 + KB + j + 1];
+#pragma unroll
+            for (int q = 0; q < NR; ++q) {
+                if (k0 + KB + j < kend) acc0[q] += c[j] * sw[q * pstride + k0 + KB + j];
+                if (k0 + KB + j + 1 < kend) acc1[q] += c[j + 1] * sw[q * pstride + k0 + KB + j + 1];
+            }
         }
 #pragma unroll
         for (int j = 0; j < KB; ++j) c[j] = (k0 + 3 * KB + j < kend) ? __ldg(Sr + (size_t)(k0 + 3 * KB + j) * ld) : 0.0;
     }
     if (act) {
-        const double acc = acc0 + acc1;
-        if (r < p) cx.yd[R.start + r] = acc * cx.dinv[R.start + r];
-        else cx.W[R.woff + r] = wv - acc;
+        const double di = r < p ? cx.dinv[R.start + r] : 0.0;
+#pragma unroll
+        for (int q = 0; q < NR; ++q) {
+            const double acc = acc0[q] + acc1[q];
+            if (r < p) cx.yd[R.start + r + q * cx.sN] = acc * di;
+            else cx.W[R.woff + r + q * cx.sW] = wv[q] - acc;
+        }
     }
 }
 
@@ -787,20 +815,20 @@ __global__ void __launch_bounds__(MAXT) k_fwd_front(int64_t first, int has_child
 struct FwdTile {
     int32_t front, r0, nr, pad;
 };
-template <int KL>
+template <int KL, int NR>
 __global__ void __launch_bounds__(32 * KL) k_fwd_tile(const FwdTile* __restrict__ tasks, int has_children, SolveCtx cx,
-                                                      const double* __restrict__ b) {
+                                                      const double* __restrict__ b, int pstride) {
     extern __shared__ double sm[];
     pdl_launch_dependents();
     const FwdTile t = tasks[blockIdx.x];
     const FrontRec R = cx.recs[t.front];
     const int p = R.p, m = p + R.q;
-    double* sw = sm;                       // [kend_tile]
+    double* sw = sm;                       // [NR][pstride]
     const int lr = threadIdx.x & 31, kl = threadIdx.x >> 5;
     const int r = t.r0 + lr;
     const bool valid = lr < t.nr;
     const int kend_tile = min(p, (t.r0 < p) ? t.r0 + t.nr : p);
-    double* red = sm + ((kend_tile + 1) & ~1);     // [KL][33]
+    double* red = sm + (size_t)NR * pstride;        // [NR][KL][33]
     const int kend = valid ? ((r < p) ? min(kend_tile, r + 1) : p) : 0;
     const double* Sr = cx.S + R.Loff + r;
     const size_t ld = (size_t)m;
@@ -809,11 +837,20 @@ __global__ void __launch_bounds__(32 * KL) k_fwd_tile(const FwdTile* __restrict_
 #pragma unroll
     for (int j = 0; j < NL; ++j) a[j] = (kl + j * KL < kend) ? __ldg(Sr + (size_t)(kl + j * KL) * ld) : 0.0;
     pdl_wait();
-    for (int k = threadIdx.x; k < kend_tile; k += 32 * KL) sw[k] = fwd_gather(cx, R, k, has_children, b);
-    double wv = 0.0;
-    if (kl == 0 && valid && r >= p) wv = fwd_gather(cx, R, r, has_children, b);
+    for (int k = threadIdx.x; k < kend_tile; k += 32 * KL) {
+        double g[NR];
+        fwd_gather<NR>(cx, R, k, has_children, b, g);
+#pragma unroll
+        for (int q = 0; q < NR; ++q) sw[q * pstride + k] = g[q];
+    }
+    double wv[NR];
+#pragma unroll
+    for (int q = 0; q < NR; ++q) wv[q] = 0.0;
+    if (kl == 0 && valid && r >= p) fwd_gather<NR>(cx, R, r, has_children, b, wv);
     __syncthreads();
-    double acc = 0.0, acc1 = 0.0;
+    double acc[NR], acc1[NR];
+#pragma unroll
+    for (int q = 0; q < NR; ++q) acc[q] = acc1[q] = 0.0;
     for (int k = kl; k < kend; k += NL * KL) {
         double c[NL];
 #pragma unroll
@@ -823,27 +860,34 @@ __global__ void __launch_bounds__(32 * KL) k_fwd_tile(const FwdTile* __restrict_
             a[j] = (k + (NL + j) * KL < kend) ? __ldg(Sr + (size_t)(k + (NL + j) * KL) * ld) : 0.0;
 #pragma unroll
         for (int j = 0; j < NL; j += 2) {
-            if (k + j * KL < kend) acc += c[j] * sw[k + j * KL];
-            if (k + (j + 1) * KL < kend) acc1 += c[j + 1] * sw[k + (j + 1) * KL];
+#pragma unroll
+            for (int q = 0; q < NR; ++q) {
+                if (k + j * KL < kend) acc[q] += c[j] * sw[q * pstride + k + j * KL];
+                if (k + (j + 1) * KL < kend) acc1[q] += c[j + 1] * sw[q * pstride + k + (j + 1) * KL];
+            }
         }
     }
-    acc += acc1;
-    red[kl * 33 + lr] = acc;
+#pragma unroll
+    for (int q = 0; q < NR; ++q) red[(q * KL + kl) * 33 + lr] = acc[q] + acc1[q];
     __syncthreads();
     if (kl == 0 && valid) {
-        double sacc = 0.0;
+        const double di = r < p ? cx.dinv[R.start + r] : 0.0;
 #pragma unroll
-        for (int j = 0; j < KL; ++j) sacc += red[j * 33 + lr];
-        if (r < p) cx.yd[R.start + r] = sacc * cx.dinv[R.start + r];
-        else cx.W[R.woff + r] = wv - sacc;
+        for (int q = 0; q < NR; ++q) {
+            double sacc = 0.0;
+#pragma unroll
+            for (int j = 0; j < KL; ++j) sacc += red[(q * KL + j) * 33 + lr];
+            if (r < p) cx.yd[R.start + r + q * cx.sN] = sacc * di;
+            else cx.W[R.woff + r + q * cx.sW] = wv[q] - sacc;
+        }
     }
 }
 
 // backward, one CTA per front: warp w owns columns w, w+NW, ...; BWD_CB columns x BWD_RJ row groups
 // of loads in flight per lane; g = [D^-1 y_own ; -x_bnd] is staged in shared memory.
-template <int MAXT, int BWD_CB, int BWD_RJ>
-__global__ void __launch_bounds__(MAXT) k_bwd_front(int64_t first, SolveCtx cx, double* __restrict__ xout) {
-    extern __shared__ double sg[];
+template <int MAXT, int BWD_CB, int BWD_RJ, int NR>
+__global__ void __launch_bounds__(MAXT) k_bwd_front(int64_t first, SolveCtx cx, double* __restrict__ xout, int mstride) {
+    extern __shared__ double sg[];          // [NR][mstride]
     pdl_launch_dependents();
     const FrontRec R = cx.recs[first + blockIdx.x];
     const int p = R.p, m = p + R.q;
@@ -860,21 +904,27 @@ __global__ void __launch_bounds__(MAXT) k_bwd_front(int64_t first, SolveCtx cx, 
         }
     }
     pdl_wait();
-    for (int i = threadIdx.x; i < m; i += blockDim.x)
-        sg[i] = (i < p) ? cx.yd[R.start + i] : -cx.x[cx.bnd[R.bndoff + i - p]];
+    for (int i = threadIdx.x; i < m; i += blockDim.x) {
+        const int64_t src = (i < p) ? R.start + i : (int64_t)cx.bnd[R.bndoff + i - p];
+#pragma unroll
+        for (int q = 0; q < NR; ++q) sg[q * mstride + i] = (i < p) ? cx.yd[src + q * cx.sN] : -cx.x[src + q * cx.sN];
+    }
     __syncthreads();
     for (int cb = warp; cb < p; cb += NW * BWD_CB) {
-        double acc[BWD_CB];
+        double acc[BWD_CB][NR];
 #pragma unroll
         for (int i = 0; i < BWD_CB; ++i) {
             const int c = cb + NW * i;
-            double s = 0.0;
+#pragma unroll
+            for (int q = 0; q < NR; ++q) acc[i][q] = 0.0;
 #pragma unroll
             for (int j = 0; j < BWD_RJ; ++j) {
                 const int r = c + lane + 32 * j;
-                if (c < p && r < m) s += a[i][j] * sg[r];
+                if (c < p && r < m) {
+#pragma unroll
+                    for (int q = 0; q < NR; ++q) acc[i][q] += a[i][j] * sg[q * mstride + r];
+                }
             }
-            acc[i] = s;
         }
         // remaining row groups of this batch
         const int rmax = m - cb;                    // rows below the first column of the batch
@@ -894,7 +944,10 @@ __global__ void __launch_bounds__(MAXT) k_bwd_front(int64_t first, SolveCtx cx, 
 #pragma unroll
                 for (int j = 0; j < BWD_RJ; ++j) {
                     const int r = c + lane + 32 * (j0 + j);
-                    if (c < p && r < m) acc[i] += a[i][j] * sg[r];
+                    if (c < p && r < m) {
+#pragma unroll
+                        for (int q = 0; q < NR; ++q) acc[i][q] += a[i][j] * sg[q * mstride + r];
+                    }
                 }
             }
         }
@@ -911,13 +964,16 @@ __global__ void __launch_bounds__(MAXT) k_bwd_front(int64_t first, SolveCtx cx, 
         }
 #pragma unroll
         for (int i = 0; i < BWD_CB; ++i) {
-            double s = acc[i];
-#pragma unroll
-            for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
             const int c = cb + NW * i;
-            if (lane == 0 && c < p) {
-                cx.x[R.start + c] = s;
-                xout[cx.perm[R.start + c]] = s;
+#pragma unroll
+            for (int q = 0; q < NR; ++q) {
+                double s = acc[i][q];
+#pragma unroll
+                for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+                if (lane == 0 && c < p) {
+                    cx.x[R.start + c + q * cx.sN] = s;
+                    xout[cx.perm[R.start + c] + q * cx.sN] = s;
+                }
             }
         }
     }
@@ -927,16 +983,16 @@ __global__ void __launch_bounds__(MAXT) k_bwd_front(int64_t first, SolveCtx cx, 
 struct BwdTile {
     int32_t front, c0, nc, pad;
 };
-template <int WPC>
+template <int WPC, int NR>
 __global__ void __launch_bounds__(32 * GEMVT_COLS * WPC) k_bwd_tile(const BwdTile* __restrict__ tasks, SolveCtx cx,
-                                                                    double* __restrict__ xout) {
+                                                                    double* __restrict__ xout, int mstride) {
     extern __shared__ double sm[];
     pdl_launch_dependents();
     const BwdTile t = tasks[blockIdx.x];
     const FrontRec R = cx.recs[t.front];
     const int p = R.p, m = p + R.q;
-    double* sg = sm;                                   // g[c0 .. m)
-    double* red = sm + ((m - t.c0 + 1) & ~1);          // [GEMVT_COLS][WPC]
+    double* sg = sm;                                   // [NR][mstride]: g[c0 .. m)
+    double* red = sm + (size_t)NR * mstride;           // [NR][GEMVT_COLS][WPC]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int wc = warp / WPC, part = warp % WPC;
     const int c = t.c0 + wc;
@@ -949,12 +1005,19 @@ __global__ void __launch_bounds__(32 * GEMVT_COLS * WPC) k_bwd_tile(const BwdTil
 #pragma unroll
     for (int j = 0; j < NL; ++j) a[j] = (on && rb + j * step < m) ? __ldg(Sc + rb + j * step) : 0.0;
     pdl_wait();
-    for (int i = t.c0 + threadIdx.x; i < m; i += blockDim.x)
-        sg[i - t.c0] = (i < p) ? cx.yd[R.start + i] : -cx.x[cx.bnd[R.bndoff + i - p]];
+    for (int i = t.c0 + threadIdx.x; i < m; i += blockDim.x) {
+        const int64_t src = (i < p) ? R.start + i : (int64_t)cx.bnd[R.bndoff + i - p];
+#pragma unroll
+        for (int q = 0; q < NR; ++q) sg[q * mstride + i - t.c0] = (i < p) ? cx.yd[src + q * cx.sN] : -cx.x[src + q * cx.sN];
+    }
     __syncthreads();
-    double acc = 0.0;
+    double acc[NR];
+#pragma unroll
+    for (int q = 0; q < NR; ++q) acc[q] = 0.0;
     if (on) {
-        double a0 = 0.0, a1 = 0.0;
+        double a0[NR], a1[NR];
+#pragma unroll
+        for (int q = 0; q < NR; ++q) a0[q] = a1[q] = 0.0;
         for (int r = rb; r < m; r += NL * step) {
             double cbuf[NL];
 #pragma unroll
@@ -963,23 +1026,36 @@ __global__ void __launch_bounds__(32 * GEMVT_COLS * WPC) k_bwd_tile(const BwdTil
             for (int j = 0; j < NL; ++j) a[j] = (r + (NL + j) * step < m) ? __ldg(Sc + r + (NL + j) * step) : 0.0;
 #pragma unroll
             for (int j = 0; j < NL; j += 2) {
-                if (r + j * step < m) a0 += cbuf[j] * sg[r + j * step - t.c0];
-                if (r + (j + 1) * step < m) a1 += cbuf[j + 1] * sg[r + (j + 1) * step - t.c0];
+#pragma unroll
+                for (int q = 0; q < NR; ++q) {
+                    if (r + j * step < m) a0[q] += cbuf[j] * sg[q * mstride + r + j * step - t.c0];
+                    if (r + (j + 1) * step < m) a1[q] += cbuf[j + 1] * sg[q * mstride + r + (j + 1) * step - t.c0];
+                }
             }
         }
-        acc = a0 + a1;
 #pragma unroll
-        for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        for (int q = 0; q < NR; ++q) {
+            double s = a0[q] + a1[q];
+#pragma unroll
+            for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            acc[q] = s;
+        }
     }
-    if (lane == 0) red[wc * WPC + part] = acc;
+    if (lane == 0) {
+#pragma unroll
+        for (int q = 0; q < NR; ++q) red[(q * GEMVT_COLS + wc) * WPC + part] = acc[q];
+    }
     __syncthreads();
     if (threadIdx.x < t.nc) {
-        double sacc = 0.0;
-#pragma unroll
-        for (int j = 0; j < WPC; ++j) sacc += red[threadIdx.x * WPC + j];
         const int cc = t.c0 + threadIdx.x;
-        cx.x[R.start + cc] = sacc;
-        xout[cx.perm[R.start + cc]] = sacc;
+#pragma unroll
+        for (int q = 0; q < NR; ++q) {
+            double sacc = 0.0;
+#pragma unroll
+            for (int j = 0; j < WPC; ++j) sacc += red[(q * GEMVT_COLS + threadIdx.x) * WPC + j];
+            cx.x[R.start + cc + q * cx.sN] = sacc;
+            xout[cx.perm[R.start + cc] + q * cx.sN] = sacc;
+        }
     }
 }
 
@@ -1401,40 +1477,104 @@ static const SweepTuning& sweep_tuning() {
     return t;
 }
 
-template <int MAXT>
-static void launch_fwd_front_t(int kb, unsigned nf, int nt, size_t sh, cudaStream_t st, int64_t first, int hc,
+// NR = 1: every (KB | CB, RJ) variant (experiments); NR = 2: the tuned defaults only (compile time)
+template <int MAXT, int NR>
+static void launch_fwd_front_t(int kb, unsigned nf, int nt, int pstride, cudaStream_t st, int64_t first, int hc,
                                const SolveCtx& cx, const double* b) {
-    if (kb <= 2) launch_pdl(k_fwd_front<MAXT, 2>, nf, nt, sh, st, first, hc, cx, b);
-    else if (kb <= 4) launch_pdl(k_fwd_front<MAXT, 4>, nf, nt, sh, st, first, hc, cx, b);
-    else if (kb <= 8 || MAXT > 512) launch_pdl(k_fwd_front<MAXT, 8>, nf, nt, sh, st, first, hc, cx, b);
-    else launch_pdl(k_fwd_front<(MAXT > 512 ? 512 : MAXT), 16>, nf, nt, sh, st, first, hc, cx, b);
+    const size_t sh = (size_t)NR * pstride * sizeof(double);
+    if constexpr (NR == 1) {
+        if (kb <= 2) launch_pdl(k_fwd_front<MAXT, 2, 1>, nf, nt, sh, st, first, hc, cx, b, pstride);
+        else if (kb <= 4) launch_pdl(k_fwd_front<MAXT, 4, 1>, nf, nt, sh, st, first, hc, cx, b, pstride);
+        else if (kb <= 8 || MAXT > 512) launch_pdl(k_fwd_front<MAXT, 8, 1>, nf, nt, sh, st, first, hc, cx, b, pstride);
+        else launch_pdl(k_fwd_front<(MAXT > 512 ? 512 : MAXT), 16, 1>, nf, nt, sh, st, first, hc, cx, b, pstride);
+    } else {
+        if (kb <= 4) launch_pdl(k_fwd_front<MAXT, 4, NR>, nf, nt, sh, st, first, hc, cx, b, pstride);
+        else launch_pdl(k_fwd_front<MAXT, 8, NR>, nf, nt, sh, st, first, hc, cx, b, pstride);
+    }
 }
-static void launch_fwd_front(int nt, int kb, unsigned nf, size_t sh, cudaStream_t st, int64_t first, int hc,
+template <int NR>
+static void launch_fwd_front(int nt, int kb, unsigned nf, int pstride, cudaStream_t st, int64_t first, int hc,
                              const SolveCtx& cx, const double* b) {
-    if (nt <= 256) launch_fwd_front_t<256>(kb, nf, nt, sh, st, first, hc, cx, b);
-    else if (nt <= 512) launch_fwd_front_t<512>(kb, nf, nt, sh, st, first, hc, cx, b);
-    else launch_fwd_front_t<1024>(kb, nf, nt, sh, st, first, hc, cx, b);
+    if (nt <= 256) launch_fwd_front_t<256, NR>(kb, nf, nt, pstride, st, first, hc, cx, b);
+    else if (nt <= 512) launch_fwd_front_t<512, NR>(kb, nf, nt, pstride, st, first, hc, cx, b);
+    else launch_fwd_front_t<1024, NR>(kb, nf, nt, pstride, st, first, hc, cx, b);
 }
 
-template <int MAXT, int RJ>
-static void launch_bwd_front_t(int cb, unsigned nf, int nt, size_t sh, cudaStream_t st, int64_t first, const SolveCtx& cx,
+template <int MAXT, int RJ, int NR>
+static void launch_bwd_front_t(int cb, unsigned nf, int nt, int mstride, cudaStream_t st, int64_t first, const SolveCtx& cx,
                                double* x) {
-    if (cb <= 1) launch_pdl(k_bwd_front<MAXT, 1, RJ>, nf, nt, sh, st, first, cx, x);
-    else if (cb <= 2) launch_pdl(k_bwd_front<MAXT, 2, RJ>, nf, nt, sh, st, first, cx, x);
-    else if (cb <= 4 || MAXT > 512) launch_pdl(k_bwd_front<MAXT, (MAXT > 512 && RJ > 2 ? 2 : 4), RJ>, nf, nt, sh, st, first, cx, x);
-    else launch_pdl(k_bwd_front<(MAXT > 512 ? 512 : MAXT), 8, RJ>, nf, nt, sh, st, first, cx, x);
+    const size_t sh = (size_t)NR * mstride * sizeof(double);
+    if constexpr (NR == 1) {
+        if (cb <= 1) launch_pdl(k_bwd_front<MAXT, 1, RJ, 1>, nf, nt, sh, st, first, cx, x, mstride);
+        else if (cb <= 2) launch_pdl(k_bwd_front<MAXT, 2, RJ, 1>, nf, nt, sh, st, first, cx, x, mstride);
+        else if (cb <= 4 || MAXT > 512)
+            launch_pdl(k_bwd_front<MAXT, (MAXT > 512 && RJ > 2 ? 2 : 4), RJ, 1>, nf, nt, sh, st, first, cx, x, mstride);
+        else launch_pdl(k_bwd_front<(MAXT > 512 ? 512 : MAXT), 8, RJ, 1>, nf, nt, sh, st, first, cx, x, mstride);
+    } else {
+        if (cb <= 1) launch_pdl(k_bwd_front<MAXT, 1, RJ, NR>, nf, nt, sh, st, first, cx, x, mstride);
+        else launch_pdl(k_bwd_front<MAXT, 2, RJ, NR>, nf, nt, sh, st, first, cx, x, mstride);
+    }
 }
-static void launch_bwd_front(int nt, int cb, int rj, unsigned nf, size_t sh, cudaStream_t st, int64_t first,
+template <int NR>
+static void launch_bwd_front(int nt, int cb, int rj, unsigned nf, int mstride, cudaStream_t st, int64_t first,
                              const SolveCtx& cx, double* x) {
     if (rj <= 2) {
-        if (nt <= 256) launch_bwd_front_t<256, 2>(cb, nf, nt, sh, st, first, cx, x);
-        else if (nt <= 512) launch_bwd_front_t<512, 2>(cb, nf, nt, sh, st, first, cx, x);
-        else launch_bwd_front_t<1024, 2>(cb, nf, nt, sh, st, first, cx, x);
+        if (nt <= 256) launch_bwd_front_t<256, 2, NR>(cb, nf, nt, mstride, st, first, cx, x);
+        else if (nt <= 512) launch_bwd_front_t<512, 2, NR>(cb, nf, nt, mstride, st, first, cx, x);
+        else launch_bwd_front_t<1024, 2, NR>(cb, nf, nt, mstride, st, first, cx, x);
     } else {
-        if (nt <= 256) launch_bwd_front_t<256, 4>(cb, nf, nt, sh, st, first, cx, x);
-        else if (nt <= 512) launch_bwd_front_t<512, 4>(cb, nf, nt, sh, st, first, cx, x);
-        else launch_bwd_front_t<1024, 4>(cb, nf, nt, sh, st, first, cx, x);
+        if (nt <= 256) launch_bwd_front_t<256, 4, NR>(cb, nf, nt, mstride, st, first, cx, x);
+        else if (nt <= 512) launch_bwd_front_t<512, 4, NR>(cb, nf, nt, mstride, st, first, cx, x);
+        else launch_bwd_front_t<1024, 4, NR>(cb, nf, nt, mstride, st, first, cx, x);
     }
+}
+
+constexpr int MAX_NRHS = 2;     // right-hand sides one sweep can carry
+
+// both sweeps for NR right-hand sides stored contiguously in b / x (stride N)
+template <int NR>
+static void sweep_launches(ws_solver* s, const double* bi, double* xi, cudaStream_t st) {
+    const Symbolic& Y = s->sym;
+    SolveCtx cx{s->recs.get(), s->S.get(), s->perm.get(), s->wsrc0.get(), s->wsrc1.get(), s->bnd.get(),
+                s->dinv.get(), s->W.get(), s->yd.get(), s->x.get(), (int64_t)((Y.Wtotal + 1) & ~(int64_t)1), s->N};
+    const SweepTuning& tune = sweep_tuning();
+    int nl = 0;
+    for (int l = Y.depth; l >= 0; --l) {
+        const LevelPlan& LP = s->levels[l];
+        const int hc = l < Y.depth ? 1 : 0;
+        if (LP.small) {
+            launch_fwd_front<NR>(LP.nt, l == Y.depth ? tune.kb_leaf : tune.kb, (unsigned)LP.nfronts, std::max(LP.maxp, 2), st,
+                                 LP.first_front, hc, cx, bi);
+            ++nl;
+        } else if (LP.fwd.cnt) {
+            const int base = (LP.maxp + 1) & ~1;
+            if (LP.fwd.cnt >= 500)
+                launch_pdl(k_fwd_tile<8, NR>, (unsigned)LP.fwd.cnt, 32 * 8, (size_t)NR * (base + 8 * 33) * sizeof(double), st,
+                           s->fwd_tiles.get() + LP.fwd.off, hc, cx, bi, base);
+            else
+                launch_pdl(k_fwd_tile<32, NR>, (unsigned)LP.fwd.cnt, 32 * 32, (size_t)NR * (base + 32 * 33) * sizeof(double), st,
+                           s->fwd_tiles.get() + LP.fwd.off, hc, cx, bi, base);
+            ++nl;
+        }
+    }
+    for (int l = 0; l <= Y.depth; ++l) {
+        const LevelPlan& LP = s->levels[l];
+        if (LP.small) {
+            launch_bwd_front<NR>(LP.nt, l == Y.depth ? tune.cb_leaf : tune.cb, l == Y.depth ? tune.rj_leaf : tune.rj,
+                                 (unsigned)LP.nfronts, std::max(LP.maxm, 2), st, LP.first_front, cx, xi);
+            ++nl;
+        } else if (LP.bwd.cnt) {
+            const int base = (LP.maxm + 1) & ~1;
+            if (LP.bwd.cnt >= 430)
+                launch_pdl(k_bwd_tile<1, NR>, (unsigned)LP.bwd.cnt, 32 * GEMVT_COLS, (size_t)NR * (base + GEMVT_COLS) * sizeof(double),
+                           st, s->bwd_tiles.get() + LP.bwd.off, cx, xi, base);
+            else
+                launch_pdl(k_bwd_tile<4, NR>, (unsigned)LP.bwd.cnt, 32 * GEMVT_COLS * 4,
+                           (size_t)NR * (base + GEMVT_COLS * 4) * sizeof(double), st, s->bwd_tiles.get() + LP.bwd.off, cx, xi, base);
+            ++nl;
+        }
+    }
+    count_launch(nl);
 }
 
 }  // namespace ws
@@ -1492,11 +1632,11 @@ int ws_solver_create(const ws_pattern* p, const ws_symbolic* sym, ws_solver** ou
         s->S.alloc(Y.Ltotal, st);
         s->T.alloc(Y.Ltotal, st);
         s->U.alloc(std::max<int64_t>(Y.Utotal, 2), st);
-        s->W.alloc(Y.Wtotal, st);
+        s->W.alloc((size_t)MAX_NRHS * ((Y.Wtotal + 1) & ~(int64_t)1), st);
         s->d.alloc(Y.N, st);
         s->dinv.alloc(Y.N, st);
-        s->yd.alloc(Y.N, st);
-        s->x.alloc(Y.N, st);
+        s->yd.alloc((size_t)MAX_NRHS * Y.N, st);
+        s->x.alloc((size_t)MAX_NRHS * Y.N, st);
         {
             std::vector<FrontRec> recs((size_t)Y.nfronts);
             for (int64_t t = 1; t < Y.nfronts; ++t)
@@ -1636,56 +1776,20 @@ int ws_solver_solve(ws_solver* s, const double* b, double* x, int nrhs, int devi
     // (b may alias x: b is read by the forward sweep only, x is written by the backward sweep only)
     static bool configured = false;
     if (!configured) {
-        const int big = 160 * 1024;
-        WS_CUDA(cudaFuncSetAttribute(k_fwd_tile<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-        WS_CUDA(cudaFuncSetAttribute(k_fwd_tile<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-        WS_CUDA(cudaFuncSetAttribute(k_bwd_tile<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-        WS_CUDA(cudaFuncSetAttribute(k_bwd_tile<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+        const int big = 200 * 1024;
+        WS_CUDA(cudaFuncSetAttribute(k_fwd_tile<8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+        WS_CUDA(cudaFuncSetAttribute(k_fwd_tile<32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+        WS_CUDA(cudaFuncSetAttribute(k_bwd_tile<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+        WS_CUDA(cudaFuncSetAttribute(k_bwd_tile<4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+        WS_CUDA(cudaFuncSetAttribute(k_fwd_tile<8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+        WS_CUDA(cudaFuncSetAttribute(k_fwd_tile<32, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+        WS_CUDA(cudaFuncSetAttribute(k_bwd_tile<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+        WS_CUDA(cudaFuncSetAttribute(k_bwd_tile<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
         configured = true;
     }
-    SolveCtx cx{s->recs.get(), s->S.get(), s->perm.get(), s->wsrc0.get(), s->wsrc1.get(), s->bnd.get(),
-                s->dinv.get(), s->W.get(), s->yd.get(), s->x.get()};
-    const SweepTuning& tune = sweep_tuning();
-    for (int rhs = 0; rhs < nrhs; ++rhs) {
-        const double* bi = b + (size_t)rhs * s->N;
-        double* xi = x + (size_t)rhs * s->N;
-        int nl = 0;
-        for (int l = Y.depth; l >= 0; --l) {
-            const LevelPlan& LP = s->levels[l];
-            const int hc = l < Y.depth ? 1 : 0;
-            if (LP.small) {
-                const size_t sh = (size_t)std::max(LP.maxp, 2) * sizeof(double);
-                const unsigned nf = (unsigned)LP.nfronts;
-                launch_fwd_front(LP.nt, l == Y.depth ? tune.kb_leaf : tune.kb, nf, sh, st, LP.first_front, hc, cx, bi);
-                ++nl;
-            } else if (LP.fwd.cnt) {
-                const size_t base = (size_t)((LP.maxp + 1) & ~1);
-                if (LP.fwd.cnt >= 500)
-                    launch_pdl(k_fwd_tile<8>, (unsigned)LP.fwd.cnt, 32 * 8, (base + 8 * 33) * sizeof(double), st, s->fwd_tiles.get() + LP.fwd.off, hc, cx, bi);
-                else
-                    launch_pdl(k_fwd_tile<32>, (unsigned)LP.fwd.cnt, 32 * 32, (base + 32 * 33) * sizeof(double), st, s->fwd_tiles.get() + LP.fwd.off, hc, cx, bi);
-                ++nl;
-            }
-        }
-        for (int l = 0; l <= Y.depth; ++l) {
-            const LevelPlan& LP = s->levels[l];
-            if (LP.small) {
-                const size_t sh = (size_t)std::max(LP.maxm, 2) * sizeof(double);
-                const unsigned nf = (unsigned)LP.nfronts;
-                launch_bwd_front(LP.nt, l == Y.depth ? tune.cb_leaf : tune.cb, l == Y.depth ? tune.rj_leaf : tune.rj, nf, sh, st,
-                                 LP.first_front, cx, xi);
-                ++nl;
-            } else if (LP.bwd.cnt) {
-                const size_t base = (size_t)((LP.maxm + 1) & ~1);
-                if (LP.bwd.cnt >= 430)
-                    launch_pdl(k_bwd_tile<1>, (unsigned)LP.bwd.cnt, 32 * GEMVT_COLS, (base + GEMVT_COLS) * sizeof(double), st, s->bwd_tiles.get() + LP.bwd.off, cx, xi);
-                else
-                    launch_pdl(k_bwd_tile<4>, (unsigned)LP.bwd.cnt, 32 * GEMVT_COLS * 4, (base + GEMVT_COLS * 4) * sizeof(double), st, s->bwd_tiles.get() + LP.bwd.off, cx, xi);
-                ++nl;
-            }
-        }
-        count_launch(nl);
-    }
+    int rhs = 0;
+    for (; rhs + 2 <= nrhs; rhs += 2) sweep_launches<2>(s, b + (size_t)rhs * s->N, x + (size_t)rhs * s->N, st);
+    for (; rhs < nrhs; ++rhs) sweep_launches<1>(s, b + (size_t)rhs * s->N, x + (size_t)rhs * s->N, st);
     WS_CUDA(cudaGetLastError());
     WS_API_END
 }
