@@ -26,6 +26,7 @@
 namespace ws {
 
 void spmv_launch(const ws_pattern* p, const double* vals, const double* x, double* y, cudaStream_t st);
+void spmv_launch2(const ws_pattern* p, const double* vals, const double* x, double* y, cudaStream_t st);
 
 // =============================================================================================
 // host dense eigen-solvers (n <= ~64)
@@ -473,6 +474,82 @@ __global__ void __launch_bounds__(256) k_update(double* __restrict__ w, const do
     w[n] = acc;
 }
 
+// two vectors against the same basis in one pass over it (block Arnoldi):
+// partial[c*2*nvec + 2*i + r] = sum over chunk c of Z_i[n] * u_r[n]
+__global__ void __launch_bounds__(256) k_dots_partial2(const double* __restrict__ Z, int64_t ldz, int nvec,
+                                                       const double* __restrict__ u0, const double* __restrict__ u1, int64_t N,
+                                                       double* __restrict__ partial) {
+    __shared__ double us[2][DOT_CHUNK];
+    const int64_t n0 = (int64_t)blockIdx.x * DOT_CHUNK;
+    const int len = (int)min((int64_t)DOT_CHUNK, N - n0);
+    for (int i = threadIdx.x; i < DOT_CHUNK; i += 256) {
+        us[0][i] = (i < len) ? u0[n0 + i] : 0.0;
+        us[1][i] = (i < len) ? u1[n0 + i] : 0.0;
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int v = warp; v < nvec; v += 8) {
+        const double* z = Z + (size_t)v * ldz + n0;
+        double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
+        int i = lane;
+        for (; i + 32 < len; i += 64) {
+            const double z0 = z[i], z1 = z[i + 32];
+            a0 += z0 * us[0][i];
+            b0 += z0 * us[1][i];
+            a1 += z1 * us[0][i + 32];
+            b1 += z1 * us[1][i + 32];
+        }
+        for (; i < len; i += 32) {
+            const double z0 = z[i];
+            a0 += z0 * us[0][i];
+            b0 += z0 * us[1][i];
+        }
+        double sa = a0 + a1, sb = b0 + b1;
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            sa += __shfl_xor_sync(0xffffffffu, sa, o);
+            sb += __shfl_xor_sync(0xffffffffu, sb, o);
+        }
+        if (lane == 0) {
+            partial[((size_t)blockIdx.x * nvec + v) * 2] = sa;
+            partial[((size_t)blockIdx.x * nvec + v) * 2 + 1] = sb;
+        }
+    }
+}
+
+// h[2*i + r] = sum_c partial[c][i][r];  hacc_r[i] += h[2*i + r]
+__global__ void __launch_bounds__(32) k_dots_reduce2(const double* __restrict__ partial, int nchunks, int nvec,
+                                                     double* __restrict__ h, double* __restrict__ hacc0, double* __restrict__ hacc1) {
+    const int i = blockIdx.x >> 1, r = blockIdx.x & 1, lane = threadIdx.x;
+    double s = 0.0;
+    for (int c = lane; c < nchunks; c += 32) s += partial[((size_t)c * nvec + i) * 2 + r];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) {
+        h[2 * i + r] = s;
+        double* hacc = r ? hacc1 : hacc0;
+        if (hacc) hacc[i] += s;
+    }
+}
+
+// w_r -= sum_i h[2*i + r] V_i, r = 0, 1: one pass over the basis for both
+__global__ void __launch_bounds__(256) k_update2(double* __restrict__ w0, double* __restrict__ w1, const double* __restrict__ V,
+                                                 int64_t ldv, int nvec, const double* __restrict__ h, int64_t N) {
+    __shared__ double hs[2 * MAXV];
+    if (threadIdx.x < 2 * nvec) hs[threadIdx.x] = h[threadIdx.x];
+    __syncthreads();
+    const int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    double a0 = w0[n], a1 = w1[n];
+    for (int i = 0; i < nvec; ++i) {
+        const double v = V[(size_t)i * ldv + n];
+        a0 -= hs[2 * i] * v;
+        a1 -= hs[2 * i + 1] * v;
+    }
+    w0[n] = a0;
+    w1[n] = a1;
+}
+
 // beta = sqrt(nrm2[0]); Hcol[j+1] = beta; v_next = w / beta; z_next = bw / beta (optional)
 __global__ void k_normalize(const double* __restrict__ w, const double* __restrict__ bw, const double* __restrict__ nrm2,
                             double* __restrict__ hslot, double* __restrict__ vnext, double* __restrict__ znext,
@@ -622,8 +699,8 @@ static void eig_solve_block2(const ws_pattern* p, ws_solver* s, const double* B_
     W.nchunks = ceil_div(N, DOT_CHUNK);
     W.V.alloc((size_t)(m + 2) * N, st);
     W.w.alloc(2 * N, st); W.t1.alloc(2 * N, st); W.t2.alloc(2 * N, st); W.t3.alloc(2 * N, st);
-    W.partial.alloc((size_t)W.nchunks * MAXV, st);
-    W.h.alloc(MAXV, st);
+    W.partial.alloc((size_t)W.nchunks * 2 * MAXV, st);
+    W.h.alloc(2 * MAXV, st);
     W.Hd.alloc((size_t)LD * m, st);
     W.nrm.alloc(MAXV, st);
     W.Q.alloc((size_t)MAXV * MAXV, st);
@@ -636,10 +713,9 @@ static void eig_solve_block2(const ws_pattern* p, ws_solver* s, const double* B_
     };
     // OP applied to basis vectors j, j+1 (contiguous rows of V) -> W.w (two vectors)
     auto apply_op2 = [&](cudaStream_t q, int j, int nrhs) {
-        for (int r = 0; r < nrhs; ++r) {
-            spmv_launch(p, B_vals, V + (size_t)(j + r) * N, W.t1.get() + (size_t)r * N, q);
-            vecT(q, 1, W.t1.get() + (size_t)r * N, W.t2.get() + (size_t)r * N);
-        }
+        if (nrhs == 2) spmv_launch2(p, B_vals, V + (size_t)j * N, W.t1.get(), q);      // B read once for both
+        else spmv_launch(p, B_vals, V + (size_t)j * N, W.t1.get(), q);
+        for (int r = 0; r < nrhs; ++r) vecT(q, 1, W.t1.get() + (size_t)r * N, W.t2.get() + (size_t)r * N);
         int rc = ws_solver_solve(s, W.t2.get(), W.t3.get(), nrhs, device, (void*)q);
         if (rc) throw Error(rc, ws_last_error());
         for (int r = 0; r < nrhs; ++r) vecT(q, 0, W.t3.get() + (size_t)r * N, W.w.get() + (size_t)r * N);
@@ -655,10 +731,32 @@ static void eig_solve_block2(const ws_pattern* p, ws_solver* s, const double* B_
         k_normalize<<<nb, T, 0, q>>>(wv, nullptr, W.nrm.get(), Hcol ? Hcol + slot : nullptr, V + (size_t)slot * N, nullptr, N);
         count_launch(1);
     };
+    // block step: both new vectors against v_0..v_{j+1} in ONE pass over the basis per CGS pass, then the
+    // second against the (normalised) first
     auto block_step = [&](cudaStream_t q, int j) {
         apply_op2(q, j, 2);
-        orth_into(q, W.w.get(), j + 2, j + 2, W.Hd.get() + (size_t)j * LD);
-        orth_into(q, W.w.get() + N, j + 3, j + 3, W.Hd.get() + (size_t)(j + 1) * LD);
+        double* w0 = W.w.get();
+        double* w1 = W.w.get() + N;
+        double* H0 = W.Hd.get() + (size_t)j * LD;
+        double* H1 = W.Hd.get() + (size_t)(j + 1) * LD;
+        const int nv = j + 2;
+        for (int pass = 0; pass < 2; ++pass) {
+            k_dots_partial2<<<W.nchunks, 256, 0, q>>>(V, N, nv, w0, w1, N, W.partial.get());
+            k_dots_reduce2<<<2 * nv, 32, 0, q>>>(W.partial.get(), W.nchunks, nv, W.h.get(), H0, H1);
+            k_update2<<<nb, T, 0, q>>>(w0, w1, V, N, nv, W.h.get(), N);
+            count_launch(3);
+        }
+        dots(W, q, w0, 1, w0, W.nrm.get(), nullptr);
+        k_normalize<<<nb, T, 0, q>>>(w0, nullptr, W.nrm.get(), H0 + (j + 2), V + (size_t)(j + 2) * N, nullptr, N);
+        count_launch(1);
+        for (int pass = 0; pass < 2; ++pass) {
+            dots(W, q, V + (size_t)(j + 2) * N, 1, w1, W.h.get(), H1 + (j + 2));
+            k_update<<<nb, T, 0, q>>>(w1, V + (size_t)(j + 2) * N, N, 1, W.h.get(), N);
+            count_launch(1);
+        }
+        dots(W, q, w1, 1, w1, W.nrm.get(), nullptr);
+        k_normalize<<<nb, T, 0, q>>>(w1, nullptr, W.nrm.get(), H1 + (j + 3), V + (size_t)(j + 3) * N, nullptr, N);
+        count_launch(1);
     };
     struct GraphSet {
         std::vector<cudaGraphExec_t> exec;

@@ -25,10 +25,13 @@ constexpr int SPMV_MAX_SMEM = 64 * 1024;
 // gathers of x, then parks the products: the dependent chain of a CTA is
 // rowptr -> (col, val) -> x -> shared memory, once for a block of edge / mid-side rows (~9
 // entries per row) and twice for a block of vertex / node rows (~19 per row).
+// NV vectors (x, y with stride ldv) share the (value, column) stream: a second vector costs its own
+// gathers and products only.
+template <int NV>
 __global__ void __launch_bounds__(SPMV_ROWS)
 k_spmv_stream(int64_t N, int64_t nnz, int cap, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
-              const double* __restrict__ vals, const double* __restrict__ x, double* __restrict__ y) {
-    extern __shared__ double prod[];
+              const double* __restrict__ vals, const double* __restrict__ x, double* __restrict__ y, int64_t ldv) {
+    extern __shared__ double prod[];          // [NV][cap]
     __shared__ int rp[SPMV_ROWS + 1];
     const int64_t r0 = (int64_t)blockIdx.x * SPMV_ROWS;
     const int nr = (int)min((int64_t)SPMV_ROWS, N - r0);
@@ -67,55 +70,72 @@ k_spmv_stream(int64_t N, int64_t nnz, int cap, const int32_t* __restrict__ rowpt
                 }
             }
 #pragma unroll
-            for (int i = 0; i < SPMV_CHUNKS; ++i) {
-                // entries outside [p0, p1) belong to neighbouring blocks: their columns are valid
-                // indices, the products are simply not stored
-                va[i].x *= __ldg(x + c[i].x);
-                va[i].y *= __ldg(x + c[i].y);
-                vb[i].x *= __ldg(x + c[i].z);
-                vb[i].y *= __ldg(x + c[i].w);
-            }
+            for (int v = 0; v < NV; ++v) {
+                const double* xv = x + (size_t)v * ldv;
+                double* pv = prod + (size_t)v * cap;
 #pragma unroll
-            for (int i = 0; i < SPMV_CHUNKS; ++i) {
-                const int s = (a0 - p0) + 4 * (cb + tid + i * SPMV_ROWS);   // slot of the chunk's first entry
-                if (s >= 0 && s + 3 < cnt) {
-                    prod[s] = va[i].x; prod[s + 1] = va[i].y; prod[s + 2] = vb[i].x; prod[s + 3] = vb[i].y;
-                } else {
-                    if (s >= 0 && s < cnt) prod[s] = va[i].x;
-                    if (s + 1 >= 0 && s + 1 < cnt) prod[s + 1] = va[i].y;
-                    if (s + 2 >= 0 && s + 2 < cnt) prod[s + 2] = vb[i].x;
-                    if (s + 3 >= 0 && s + 3 < cnt) prod[s + 3] = vb[i].y;
+                for (int i = 0; i < SPMV_CHUNKS; ++i) {
+                    // entries outside [p0, p1) belong to neighbouring blocks: their columns are valid
+                    // indices, the products are simply not stored
+                    const double q0 = va[i].x * __ldg(xv + c[i].x), q1 = va[i].y * __ldg(xv + c[i].y);
+                    const double q2 = vb[i].x * __ldg(xv + c[i].z), q3 = vb[i].y * __ldg(xv + c[i].w);
+                    const int s = (a0 - p0) + 4 * (cb + tid + i * SPMV_ROWS);   // slot of the chunk's first entry
+                    if (s >= 0 && s + 3 < cnt) {
+                        pv[s] = q0; pv[s + 1] = q1; pv[s + 2] = q2; pv[s + 3] = q3;
+                    } else {
+                        if (s >= 0 && s < cnt) pv[s] = q0;
+                        if (s + 1 >= 0 && s + 1 < cnt) pv[s + 1] = q1;
+                        if (s + 2 >= 0 && s + 2 < cnt) pv[s + 2] = q2;
+                        if (s + 3 >= 0 && s + 3 < cnt) pv[s + 3] = q3;
+                    }
                 }
             }
         }
         __syncthreads();
         if (tid < nr) {
-            double acc = 0.0;
             const int a = rp[tid] - p0, b = rp[tid + 1] - p0;
-            for (int i = a; i < b; ++i) acc += prod[i];
-            y[r0 + tid] = acc;
+#pragma unroll
+            for (int v = 0; v < NV; ++v) {
+                const double* pv = prod + (size_t)v * cap;
+                double acc = 0.0;
+                for (int i = a; i < b; ++i) acc += pv[i];
+                y[r0 + tid + (size_t)v * ldv] = acc;
+            }
         }
     } else if (tid < nr) {      // unusually dense block: plain row loop
-        double acc = 0.0;
-        for (int i = rp[tid]; i < rp[tid + 1]; ++i) acc += vals[i] * x[colidx[i]];
-        y[r0 + tid] = acc;
+        for (int v = 0; v < NV; ++v) {
+            double acc = 0.0;
+            for (int i = rp[tid]; i < rp[tid + 1]; ++i) acc += vals[i] * x[colidx[i] + (size_t)v * ldv];
+            y[r0 + tid + (size_t)v * ldv] = acc;
+        }
     }
 }
 
-void spmv_launch(const ws_pattern* p, const double* vals, const double* x, double* y, cudaStream_t st) {
+template <int NV>
+static void spmv_launch_nv(const ws_pattern* p, const double* vals, const double* x, double* y, int64_t ldv, cudaStream_t st) {
     if (p->N == 0) return;
     static bool configured = false;
     if (!configured) {
-        WS_CUDA(cudaFuncSetAttribute(k_spmv_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, SPMV_MAX_SMEM));
+        WS_CUDA(cudaFuncSetAttribute(k_spmv_stream<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, SPMV_MAX_SMEM));
         configured = true;
     }
     // shared-memory tile sized for this pattern's densest 128-row block (known from K2)
-    int cap = std::min(std::max(p->max_block_slots, 256), SPMV_MAX_SMEM / 8);
+    int cap = std::min(std::max(p->max_block_slots, 256), SPMV_MAX_SMEM / 8 / NV);
     cap = (cap + 63) & ~63;
-    k_spmv_stream<<<ceil_div(p->N, SPMV_ROWS), SPMV_ROWS, (size_t)cap * sizeof(double), st>>>(
-        p->N, p->nnz, cap, p->rowptr.get(), p->colidx.get(), vals, x, y);
+    if ((size_t)cap * NV * sizeof(double) > (size_t)SPMV_MAX_SMEM) cap = (SPMV_MAX_SMEM / 8 / NV) & ~63;
+    k_spmv_stream<NV><<<ceil_div(p->N, SPMV_ROWS), SPMV_ROWS, (size_t)cap * NV * sizeof(double), st>>>(
+        p->N, p->nnz, cap, p->rowptr.get(), p->colidx.get(), vals, x, y, ldv);
     WS_CUDA(cudaGetLastError());
     count_launch(1);
+}
+
+void spmv_launch(const ws_pattern* p, const double* vals, const double* x, double* y, cudaStream_t st) {
+    spmv_launch_nv<1>(p, vals, x, y, p->N, st);
+}
+
+// two vectors stored with stride N
+void spmv_launch2(const ws_pattern* p, const double* vals, const double* x, double* y, cudaStream_t st) {
+    spmv_launch_nv<2>(p, vals, x, y, p->N, st);
 }
 
 }  // namespace ws
