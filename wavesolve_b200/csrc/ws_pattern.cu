@@ -25,6 +25,10 @@ void configure_mempool(int device) {
     if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
         unsigned long long thr = ~0ull;
         cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+        // never make one stream wait for another just to recycle a freed block (concurrent sweep lanes
+        // allocate and free solver storage on their own streams): take fresh memory instead
+        int off = 0;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolReuseAllowInternalDependencies, &off);
     }
     done[device] = true;
 }
