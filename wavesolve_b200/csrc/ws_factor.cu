@@ -66,6 +66,7 @@ struct ws_solver {
     ws::DevBuf<double> L, S, T, U, W, d, dinv, yd, x;
     ws::DevBuf<ws::FrontRec> recs;
     ws::DevBuf<int32_t> wsrc0, wsrc1;       // gather maps of the forward sweep
+    ws::DevBuf<int32_t> sflags;             // per-front completion counters of the two sweeps [2 * nfronts]
     ws::DevBuf<unsigned long long> stats;   // [0] negative pivots [1] zero/NaN pivots [2] min |pivot| bits [3] max |pivot| bits
     // tasks
     ws::DevBuf<ws::GemmTask> gemm_tasks;
@@ -701,6 +702,34 @@ __global__ void k_front_fused(int64_t first, int has_children, FusedCtx cx) {
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
+// Per-front completion flags replace the level-wide wait between consecutive sweep kernels: a front
+// starts as soon as ITS OWN inputs are complete (forward: its two children; backward: its parent and
+// its own forward pass), so the ramp and tail of a level overlap with its neighbours instead of
+// adding up.  Safe against deadlock because a programmatically launched grid only becomes resident
+// once every CTA of its predecessor has started (each kernel triggers at its first instruction): a
+// spinning CTA always waits for CTAs that are already running.  The spin is bounded so that a logic
+// error can never hang the GPU (the result is then wrong and the parity tests say so).
+__device__ __forceinline__ int ld_acquire_gpu(const int32_t* p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void flag_wait(const int32_t* f, int need, int32_t* abort_flag) {
+    for (int it = 0; it < (1 << 21); ++it) {
+        if (ld_acquire_gpu(f) >= need) return;
+        if ((it & 1023) == 1023 && ld_acquire_gpu(abort_flag)) return;
+    }
+    atomicExch(abort_flag, 1);      // every later wait returns at once; ws_solver_solve's caller sees wrong numbers
+}
+// every thread of the CTA has issued its global writes; publish them and count this CTA in
+__device__ __forceinline__ void flag_signal(int32_t* f) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(f, 1);
+    }
+}
+
 struct FrontRec {
     int64_t Loff, start, woff, bndoff;
     int32_t p, q, pad0, pad1;
@@ -721,7 +750,26 @@ struct SolveCtx {
     double* x;      // solution, permuted order
     int64_t sW;     // stride between right-hand sides in W
     int64_t sN;     // stride between right-hand sides in yd / x / b / xout (= N)
+    int32_t* ffl;   // per front: CTAs of the forward sweep that have finished (nullptr: level-wide waits)
+    int32_t* bfl;   // the same for the backward sweep
 };
+
+// forward: wait for the two children of front t (their CTA counts are in their records)
+__device__ __forceinline__ void fwd_wait_children(const SolveCtx& cx, int64_t t) {
+    if (threadIdx.x == 0) {
+        flag_wait(cx.ffl + 2 * t, cx.recs[2 * t].pad0, cx.ffl);          // slot 0 (front ids start at 1) = abort flag
+        flag_wait(cx.ffl + 2 * t + 1, cx.recs[2 * t + 1].pad0, cx.ffl);
+    }
+    __syncthreads();
+}
+// backward: wait for the front's own forward pass and for its parent's backward pass
+__device__ __forceinline__ void bwd_wait_parent(const SolveCtx& cx, int64_t t, int own_fwd_ctas) {
+    if (threadIdx.x == 0) {
+        flag_wait(cx.ffl + t, own_fwd_ctas, cx.ffl);
+        if (t > 1) flag_wait(cx.bfl + (t >> 1), cx.recs[t >> 1].pad1, cx.ffl);
+    }
+    __syncthreads();
+}
 
 // NR right-hand sides share every load of the inverted panels: a sweep is bound by the panel bytes,
 // so a second vector costs its own (small) vector traffic and arithmetic only.
@@ -766,7 +814,8 @@ __global__ void __launch_bounds__(MAXT) k_fwd_front(int64_t first, int has_child
     double wv[NR];
 #pragma unroll
     for (int q = 0; q < NR; ++q) wv[q] = 0.0;
-    pdl_wait();
+    if (cx.ffl && has_children) fwd_wait_children(cx, first + blockIdx.x);
+    else pdl_wait();
     if (act) {
         fwd_gather<NR>(cx, R, r, has_children, b, wv);
         if (r < p) {
@@ -809,6 +858,7 @@ __global__ void __launch_bounds__(MAXT) k_fwd_front(int64_t first, int has_child
             else cx.W[R.woff + r + q * cx.sW] = wv[q] - acc;
         }
     }
+    if (cx.ffl) flag_signal(cx.ffl + first + blockIdx.x);
 }
 
 // large fronts: 32 rows x KL k-lanes per CTA (task = row tile of one front)
@@ -836,7 +886,8 @@ __global__ void __launch_bounds__(32 * KL) k_fwd_tile(const FwdTile* __restrict_
     double a[NL];
 #pragma unroll
     for (int j = 0; j < NL; ++j) a[j] = (kl + j * KL < kend) ? __ldg(Sr + (size_t)(kl + j * KL) * ld) : 0.0;
-    pdl_wait();
+    if (cx.ffl && has_children) fwd_wait_children(cx, t.front);
+    else pdl_wait();
     for (int k = threadIdx.x; k < kend_tile; k += 32 * KL) {
         double g[NR];
         fwd_gather<NR>(cx, R, k, has_children, b, g);
@@ -881,6 +932,7 @@ __global__ void __launch_bounds__(32 * KL) k_fwd_tile(const FwdTile* __restrict_
             else cx.W[R.woff + r + q * cx.sW] = wv[q] - sacc;
         }
     }
+    if (cx.ffl) flag_signal(cx.ffl + t.front);
 }
 
 // backward, one CTA per front: warp w owns columns w, w+NW, ...; BWD_CB columns x BWD_RJ row groups
@@ -903,7 +955,8 @@ __global__ void __launch_bounds__(MAXT) k_bwd_front(int64_t first, SolveCtx cx, 
             a[i][j] = (c < p && r < m) ? __ldg(Sf + r + (size_t)c * m) : 0.0;
         }
     }
-    pdl_wait();
+    if (cx.bfl) bwd_wait_parent(cx, first + blockIdx.x, R.pad0);
+    else pdl_wait();
     for (int i = threadIdx.x; i < m; i += blockDim.x) {
         const int64_t src = (i < p) ? R.start + i : (int64_t)cx.bnd[R.bndoff + i - p];
 #pragma unroll
@@ -977,6 +1030,7 @@ __global__ void __launch_bounds__(MAXT) k_bwd_front(int64_t first, SolveCtx cx, 
             }
         }
     }
+    if (cx.bfl) flag_signal(cx.bfl + first + blockIdx.x);
 }
 
 // large fronts: GEMVT_COLS columns per CTA, WPC warps share a column (task = column tile)
@@ -1004,7 +1058,8 @@ __global__ void __launch_bounds__(32 * GEMVT_COLS * WPC) k_bwd_tile(const BwdTil
     double a[NL];
 #pragma unroll
     for (int j = 0; j < NL; ++j) a[j] = (on && rb + j * step < m) ? __ldg(Sc + rb + j * step) : 0.0;
-    pdl_wait();
+    if (cx.bfl) bwd_wait_parent(cx, t.front, R.pad0);
+    else pdl_wait();
     for (int i = t.c0 + threadIdx.x; i < m; i += blockDim.x) {
         const int64_t src = (i < p) ? R.start + i : (int64_t)cx.bnd[R.bndoff + i - p];
 #pragma unroll
@@ -1057,6 +1112,7 @@ __global__ void __launch_bounds__(32 * GEMVT_COLS * WPC) k_bwd_tile(const BwdTil
             xout[cx.perm[R.start + cc] + q * cx.sN] = sacc;
         }
     }
+    if (cx.bfl) flag_signal(cx.bfl + t.front);
 }
 
 // gather maps: for child c of front t = c/2 and boundary entry j of c:
@@ -1535,8 +1591,12 @@ constexpr int MAX_NRHS = 2;     // right-hand sides one sweep can carry
 template <int NR>
 static void sweep_launches(ws_solver* s, const double* bi, double* xi, cudaStream_t st) {
     const Symbolic& Y = s->sym;
+    static const bool flagsync = !(getenv("WS_NO_FLAGSYNC") && atoi(getenv("WS_NO_FLAGSYNC"))) &&
+                                 !(getenv("WS_NO_PDL") && atoi(getenv("WS_NO_PDL")));
     SolveCtx cx{s->recs.get(), s->S.get(), s->perm.get(), s->wsrc0.get(), s->wsrc1.get(), s->bnd.get(),
-                s->dinv.get(), s->W.get(), s->yd.get(), s->x.get(), (int64_t)((Y.Wtotal + 1) & ~(int64_t)1), s->N};
+                s->dinv.get(), s->W.get(), s->yd.get(), s->x.get(), (int64_t)((Y.Wtotal + 1) & ~(int64_t)1), s->N,
+                flagsync ? s->sflags.get() : nullptr, flagsync ? s->sflags.get() + Y.nfronts : nullptr};
+    if (flagsync) WS_CUDA(cudaMemsetAsync(s->sflags.get(), 0, s->sflags.bytes(), st));
     const SweepTuning& tune = sweep_tuning();
     int nl = 0;
     for (int l = Y.depth; l >= 0; --l) {
@@ -1637,10 +1697,27 @@ int ws_solver_create(const ws_pattern* p, const ws_symbolic* sym, ws_solver** ou
         s->dinv.alloc(Y.N, st);
         s->yd.alloc((size_t)MAX_NRHS * Y.N, st);
         s->x.alloc((size_t)MAX_NRHS * Y.N, st);
+        classify_levels(s);
+        s->sflags.alloc((size_t)2 * Y.nfronts, st);
         {
+            // per front: how many CTAs the forward / backward sweep spends on it (1 for the one-CTA-per-front
+            // kernels, the number of row / column tiles for the large fronts): what a waiter compares with
             std::vector<FrontRec> recs((size_t)Y.nfronts);
-            for (int64_t t = 1; t < Y.nfronts; ++t)
-                recs[t] = FrontRec{Y.Loff[t], Y.start[t], Y.woff[t], Y.bndoff[t], Y.p[t], Y.q[t], 0, 0};
+            for (int64_t t = 1; t < Y.nfronts; ++t) {
+                const int p_ = Y.p[t], m_ = p_ + Y.q[t];
+                int nf = 1, nbk = 1;
+                if (!s->levels[63 - __builtin_clzll((unsigned long long)t)].small) {
+                    nf = 0;
+                    for (int r0 = 0; r0 < m_; r0 += GEMV_ROWS) {
+                        int nr = std::min(GEMV_ROWS, m_ - r0);
+                        if (r0 < p_ && r0 + nr > p_) nr = p_ - r0;
+                        ++nf;
+                        if (nr < GEMV_ROWS && r0 + nr < m_) ++nf;
+                    }
+                    nbk = (p_ + GEMVT_COLS - 1) / GEMVT_COLS;
+                }
+                recs[t] = FrontRec{Y.Loff[t], Y.start[t], Y.woff[t], Y.bndoff[t], Y.p[t], Y.q[t], nf, nbk};
+            }
             upload(s->recs, recs, st);
             WS_CUDA(cudaStreamSynchronize(st));   // recs dies here
             WS_REQUIRE(Y.Wtotal < ((int64_t)1 << 31), "work-vector storage exceeds 32-bit indexing");
@@ -1667,7 +1744,6 @@ int ws_solver_create(const ws_pattern* p, const ws_symbolic* sym, ws_solver** ou
         WS_CUDA(cudaMemcpyAsync(&bad, s->stats.get(), sizeof bad, cudaMemcpyDeviceToHost, st));
         count_launch(2);
         const double tc2 = tnow();
-        classify_levels(s);
         WS_CUDA(cudaStreamSynchronize(st));
         if (trace)
             fprintf(stderr, "[ws_solver_create] copy+upload+alloc %.1f ms, dest map %.1f ms, plan %.1f ms\n",
