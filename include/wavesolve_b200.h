@@ -175,6 +175,9 @@ int ws_solver_create(const ws_pattern* p, const ws_symbolic* sym, ws_solver** ou
 int ws_solver_factor(ws_solver* s, const double* A_vals, const double* B_vals, double sigma,
                      int device, void* stream);
 int ws_solver_solve(ws_solver* s, const double* b, double* x, int nrhs, int device, void* stream);
+/* ws_solver_check : synchronises the stream and returns WS_ERR_STATE if a flag-synchronised sweep
+ *                    gave up waiting for a front since the last solve (internal error guard).    */
+int ws_solver_check(const ws_solver* s, int device, void* stream);
 int ws_solver_stats(const ws_solver* s, int64_t* h_info, double* h_dinfo);
 int ws_solver_destroy(ws_solver* s);
 

@@ -46,6 +46,7 @@ _SIGNATURES = {
     "ws_solver_create": (c_int, [c_vp, c_vp, C.POINTER(c_vp), c_int, c_vp]),
     "ws_solver_factor": (c_int, [c_vp, c_vp, c_vp, C.c_double, c_int, c_vp]),
     "ws_solver_solve": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_vp]),
+    "ws_solver_check": (c_int, [c_vp, c_int, c_vp]),
     "ws_solver_stats": (c_int, [c_vp, c_vp, c_vp]),
     "ws_solver_destroy": (c_int, [c_vp]),
     "ws_assemble_vector_qd": (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, C.c_double, c_vp, c_vp, c_int, c_int, c_vp]),

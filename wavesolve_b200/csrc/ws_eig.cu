@@ -963,6 +963,10 @@ static void eig_solve_block2(const ws_pattern* p, ws_solver* s, const double* B_
     WS_CUDA(cudaMemcpyAsync(w_out, wh.data(), nev * sizeof(double), cudaMemcpyHostToDevice, st));
     WS_CUDA(cudaStreamSynchronize(st));
     WS_CUDA(cudaGetLastError());
+    {
+        int rc = ws_solver_check(s, device, (void*)st);
+        if (rc) throw Error(rc, ws_last_error());
+    }
     if (getenv("WS_TRACE"))
         fprintf(stderr, "[ws_eig block2] N=%lld ops=%lld (%lld sweeps) restarts=%d nconv=%d\n", (long long)N, (long long)nops,
                 (long long)(nops / 2), restarts, nconv);
@@ -1331,6 +1335,10 @@ int ws_eig_solve(const ws_pattern* p, ws_solver* s, const double* B_vals, double
     WS_CUDA(cudaMemcpyAsync(w_out, wh.data(), nev * sizeof(double), cudaMemcpyHostToDevice, st));
     WS_CUDA(cudaStreamSynchronize(st));
     WS_CUDA(cudaGetLastError());
+    {
+        int rc = ws_solver_check(s, device, (void*)st);
+        if (rc) throw Error(rc, ws_last_error());
+    }
     if (etrace) {
         cudaStreamSynchronize(st);
         const double wall1 = std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();

@@ -1596,7 +1596,8 @@ static void sweep_launches(ws_solver* s, const double* bi, double* xi, cudaStrea
     SolveCtx cx{s->recs.get(), s->S.get(), s->perm.get(), s->wsrc0.get(), s->wsrc1.get(), s->bnd.get(),
                 s->dinv.get(), s->W.get(), s->yd.get(), s->x.get(), (int64_t)((Y.Wtotal + 1) & ~(int64_t)1), s->N,
                 flagsync ? s->sflags.get() : nullptr, flagsync ? s->sflags.get() + Y.nfronts : nullptr};
-    if (flagsync) WS_CUDA(cudaMemsetAsync(s->sflags.get(), 0, s->sflags.bytes(), st));
+    // (slot 0 is the sticky abort flag: front ids start at 1)
+    if (flagsync) WS_CUDA(cudaMemsetAsync(s->sflags.get() + 1, 0, s->sflags.bytes() - sizeof(int32_t), st));
     const SweepTuning& tune = sweep_tuning();
     int nl = 0;
     for (int l = Y.depth; l >= 0; --l) {
@@ -1699,6 +1700,7 @@ int ws_solver_create(const ws_pattern* p, const ws_symbolic* sym, ws_solver** ou
         s->x.alloc((size_t)MAX_NRHS * Y.N, st);
         classify_levels(s);
         s->sflags.alloc((size_t)2 * Y.nfronts, st);
+        WS_CUDA(cudaMemsetAsync(s->sflags.get(), 0, s->sflags.bytes(), st));
         {
             // per front: how many CTAs the forward / backward sweep spends on it (1 for the one-CTA-per-front
             // kernels, the number of row / column tiles for the large fronts): what a waiter compares with
@@ -1867,6 +1869,24 @@ int ws_solver_solve(ws_solver* s, const double* b, double* x, int nrhs, int devi
     for (; rhs + 2 <= nrhs; rhs += 2) sweep_launches<2>(s, b + (size_t)rhs * s->N, x + (size_t)rhs * s->N, st);
     for (; rhs < nrhs; ++rhs) sweep_launches<1>(s, b + (size_t)rhs * s->N, x + (size_t)rhs * s->N, st);
     WS_CUDA(cudaGetLastError());
+    WS_API_END
+}
+
+// Host check of the abort flag of the flag-synchronised sweeps (set when a wait ran into its bound:
+// a logic error, never expected).  Synchronises the stream.
+int ws_solver_check(const ws_solver* s, int device, void* stream) {
+    WS_API_BEGIN
+    WS_REQUIRE(s, "solver == NULL");
+    DeviceGuard g(device);
+    int32_t flag = 0;
+    if (s->sflags.get()) {
+        WS_CUDA(cudaMemcpyAsync(&flag, s->sflags.get(), sizeof flag, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+        WS_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    }
+    if (flag) {
+        WS_CUDA(cudaMemsetAsync(s->sflags.get(), 0, sizeof(int32_t), (cudaStream_t)stream));
+        throw Error(WS_ERR_STATE, "internal: a solve sweep timed out waiting for a front (results are invalid)");
+    }
     WS_API_END
 }
 

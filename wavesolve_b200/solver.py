@@ -141,6 +141,10 @@ class Solver:
                                               self.dev.index, d.stream_ptr(self.dev)))
         return out
 
+    def check(self):
+        """Synchronise and raise if a solve sweep reported an internal synchronisation error."""
+        _lib.check(_lib.lib().ws_solver_check(self.handle, self.dev.index, self._dev.stream_ptr(self.dev)))
+
     def stats(self):
         info = np.zeros(8, dtype=np.int64)
         dinfo = np.zeros(3, dtype=np.float64)
