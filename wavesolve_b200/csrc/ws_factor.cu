@@ -50,6 +50,7 @@ struct LevelPlan {
     int maxp = 0, maxm = 0;
     bool right_looking = false;
     bool fused = false;                   // factorised by k_front_fused (one CTA per front, no tile tasks)
+    int64_t fwd_mid = 0, bwd_mid = 0;     // tile tasks of the left half of the level's fronts (sweep pipelining)
 };
 
 }  // namespace ws
@@ -1368,6 +1369,13 @@ static void build_plan(ws_solver* s, cudaStream_t st) {
         }
         LP.fwd.cnt = (int64_t)F.size() - LP.fwd.off;
         LP.bwd.cnt = (int64_t)Bk.size() - LP.bwd.off;
+        {
+            const int64_t mid = f0 + (f1 - f0) / 2;
+            LP.fwd_mid = 0;
+            LP.bwd_mid = 0;
+            for (int64_t i = LP.fwd.off; i < (int64_t)F.size() && F[i].front < mid; ++i) ++LP.fwd_mid;
+            for (int64_t i = LP.bwd.off; i < (int64_t)Bk.size() && Bk[i].front < mid; ++i) ++LP.bwd_mid;
+        }
     }
     // ---- selective inversion (all fronts that are not handled by k_front_fused, independent of the tree)
     auto tiled = [&](int64_t t) { return !s->levels[63 - __builtin_clzll((unsigned long long)t)].fused; };
@@ -1600,39 +1608,61 @@ static void sweep_launches(ws_solver* s, const double* bi, double* xi, cudaStrea
     if (flagsync) WS_CUDA(cudaMemsetAsync(s->sflags.get() + 1, 0, s->sflags.bytes() - sizeof(int32_t), st));
     const SweepTuning& tune = sweep_tuning();
     int nl = 0;
+    // Optional (WS_SPLIT=1): every level launched in two halves (left / right subtree of the root).  With the
+    // per-front flags the left half of level l-1 depends on the left half of level l only, so it can run while the
+    // right half of level l drains.  Measured: 0.977 ms against 0.970 ms per solve -- the tails are not what is
+    // left to gain -- so it is off by default.
+    static const bool halves = flagsync && getenv("WS_SPLIT") && atoi(getenv("WS_SPLIT"));
     for (int l = Y.depth; l >= 0; --l) {
         const LevelPlan& LP = s->levels[l];
         const int hc = l < Y.depth ? 1 : 0;
-        if (LP.small) {
-            launch_fwd_front<NR>(LP.nt, l == Y.depth ? tune.kb_leaf : tune.kb, (unsigned)LP.nfronts, std::max(LP.maxp, 2), st,
-                                 LP.first_front, hc, cx, bi);
-            ++nl;
-        } else if (LP.fwd.cnt) {
-            const int base = (LP.maxp + 1) & ~1;
-            if (LP.fwd.cnt >= 500)
-                launch_pdl(k_fwd_tile<8, NR>, (unsigned)LP.fwd.cnt, 32 * 8, (size_t)NR * (base + 8 * 33) * sizeof(double), st,
-                           s->fwd_tiles.get() + LP.fwd.off, hc, cx, bi, base);
-            else
-                launch_pdl(k_fwd_tile<32, NR>, (unsigned)LP.fwd.cnt, 32 * 32, (size_t)NR * (base + 32 * 33) * sizeof(double), st,
-                           s->fwd_tiles.get() + LP.fwd.off, hc, cx, bi, base);
-            ++nl;
+        const int nparts = (halves && LP.nfronts >= 2) ? 2 : 1;
+        for (int part = 0; part < nparts; ++part) {
+            if (LP.small) {
+                const int64_t h = nparts == 2 ? LP.nfronts / 2 : LP.nfronts;
+                const int64_t f = LP.first_front + (part ? h : 0);
+                const int64_t n = nparts == 2 ? (part ? LP.nfronts - h : h) : LP.nfronts;
+                launch_fwd_front<NR>(LP.nt, l == Y.depth ? tune.kb_leaf : tune.kb, (unsigned)n, std::max(LP.maxp, 2), st, f, hc, cx, bi);
+                ++nl;
+            } else if (LP.fwd.cnt) {
+                const int64_t o = LP.fwd.off + (nparts == 2 && part ? LP.fwd_mid : 0);
+                const int64_t n = nparts == 2 ? (part ? LP.fwd.cnt - LP.fwd_mid : LP.fwd_mid) : LP.fwd.cnt;
+                if (n <= 0) continue;
+                const int base = (LP.maxp + 1) & ~1;
+                if (LP.fwd.cnt >= 500)
+                    launch_pdl(k_fwd_tile<8, NR>, (unsigned)n, 32 * 8, (size_t)NR * (base + 8 * 33) * sizeof(double), st,
+                               s->fwd_tiles.get() + o, hc, cx, bi, base);
+                else
+                    launch_pdl(k_fwd_tile<32, NR>, (unsigned)n, 32 * 32, (size_t)NR * (base + 32 * 33) * sizeof(double), st,
+                               s->fwd_tiles.get() + o, hc, cx, bi, base);
+                ++nl;
+            }
         }
     }
     for (int l = 0; l <= Y.depth; ++l) {
         const LevelPlan& LP = s->levels[l];
-        if (LP.small) {
-            launch_bwd_front<NR>(LP.nt, l == Y.depth ? tune.cb_leaf : tune.cb, l == Y.depth ? tune.rj_leaf : tune.rj,
-                                 (unsigned)LP.nfronts, std::max(LP.maxm, 2), st, LP.first_front, cx, xi);
-            ++nl;
-        } else if (LP.bwd.cnt) {
-            const int base = (LP.maxm + 1) & ~1;
-            if (LP.bwd.cnt >= 430)
-                launch_pdl(k_bwd_tile<1, NR>, (unsigned)LP.bwd.cnt, 32 * GEMVT_COLS, (size_t)NR * (base + GEMVT_COLS) * sizeof(double),
-                           st, s->bwd_tiles.get() + LP.bwd.off, cx, xi, base);
-            else
-                launch_pdl(k_bwd_tile<4, NR>, (unsigned)LP.bwd.cnt, 32 * GEMVT_COLS * 4,
-                           (size_t)NR * (base + GEMVT_COLS * 4) * sizeof(double), st, s->bwd_tiles.get() + LP.bwd.off, cx, xi, base);
-            ++nl;
+        const int nparts = (halves && LP.nfronts >= 2) ? 2 : 1;
+        for (int part = 0; part < nparts; ++part) {
+            if (LP.small) {
+                const int64_t h = nparts == 2 ? LP.nfronts / 2 : LP.nfronts;
+                const int64_t f = LP.first_front + (part ? h : 0);
+                const int64_t n = nparts == 2 ? (part ? LP.nfronts - h : h) : LP.nfronts;
+                launch_bwd_front<NR>(LP.nt, l == Y.depth ? tune.cb_leaf : tune.cb, l == Y.depth ? tune.rj_leaf : tune.rj,
+                                     (unsigned)n, std::max(LP.maxm, 2), st, f, cx, xi);
+                ++nl;
+            } else if (LP.bwd.cnt) {
+                const int64_t o = LP.bwd.off + (nparts == 2 && part ? LP.bwd_mid : 0);
+                const int64_t n = nparts == 2 ? (part ? LP.bwd.cnt - LP.bwd_mid : LP.bwd_mid) : LP.bwd.cnt;
+                if (n <= 0) continue;
+                const int base = (LP.maxm + 1) & ~1;
+                if (LP.bwd.cnt >= 430)
+                    launch_pdl(k_bwd_tile<1, NR>, (unsigned)n, 32 * GEMVT_COLS, (size_t)NR * (base + GEMVT_COLS) * sizeof(double),
+                               st, s->bwd_tiles.get() + o, cx, xi, base);
+                else
+                    launch_pdl(k_bwd_tile<4, NR>, (unsigned)n, 32 * GEMVT_COLS * 4,
+                               (size_t)NR * (base + GEMVT_COLS * 4) * sizeof(double), st, s->bwd_tiles.get() + o, cx, xi, base);
+                ++nl;
+            }
         }
     }
     count_launch(nl);
