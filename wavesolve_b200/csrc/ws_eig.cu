@@ -474,6 +474,62 @@ __global__ void __launch_bounds__(256) k_update(double* __restrict__ w, const do
     w[n] = acc;
 }
 
+// CGS2, middle of the step: w -= V h (update of pass 1) and the partial inner products V^T w of pass 2
+// in ONE pass over the basis.  A CTA owns DOT_CHUNK rows and walks them in tiles of 256: the tile of
+// every basis vector is staged in shared memory once, used to update the 256 entries of w and then,
+// with the updated entries, for the partial dots.  partial has the layout of k_dots_partial.
+constexpr int UD_TILE = 256;
+__global__ void __launch_bounds__(256) k_update_dots(double* __restrict__ w, const double* __restrict__ V, int64_t ldv, int nvec,
+                                                     const double* __restrict__ h, int64_t N, double* __restrict__ partial) {
+    extern __shared__ double uds[];            // [nvec][UD_TILE] basis tile, then [UD_TILE] updated w
+    __shared__ double hs[MAXV];
+    double* Vs = uds;
+    double* ws_ = uds + (size_t)nvec * UD_TILE;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid < nvec) hs[tid] = h[tid];
+    const int64_t c0 = (int64_t)blockIdx.x * DOT_CHUNK;
+    double dsum[MAXV / 8];
+#pragma unroll
+    for (int i = 0; i < MAXV / 8; ++i) dsum[i] = 0.0;
+    for (int t0 = 0; t0 < DOT_CHUNK; t0 += UD_TILE) {
+        const int64_t n0 = c0 + t0;
+        if (n0 >= N) break;
+        const int len = (int)min((int64_t)UD_TILE, N - n0);
+        __syncthreads();                       // previous tile fully consumed (and hs visible)
+        for (int v = warp; v < nvec; v += 8) {
+            const double* src = V + (size_t)v * ldv + n0;
+#pragma unroll
+            for (int k = 0; k < UD_TILE / 32; ++k) {
+                const int i = lane + 32 * k;
+                Vs[v * UD_TILE + i] = i < len ? src[i] : 0.0;
+            }
+        }
+        __syncthreads();
+        double acc = 0.0;
+        if (tid < len) {
+            acc = w[n0 + tid];
+            for (int v = 0; v < nvec; ++v) acc -= hs[v] * Vs[v * UD_TILE + tid];
+            w[n0 + tid] = acc;
+        }
+        ws_[tid] = acc;
+        __syncthreads();
+        int slot = 0;
+        for (int v = warp; v < nvec; v += 8, ++slot) {
+            double a = 0.0;
+#pragma unroll
+            for (int k = 0; k < UD_TILE / 32; ++k) a += Vs[v * UD_TILE + lane + 32 * k] * ws_[lane + 32 * k];
+            dsum[slot] += a;
+        }
+    }
+    int slot = 0;
+    for (int v = warp; v < nvec; v += 8, ++slot) {
+        double a = dsum[slot];
+#pragma unroll
+        for (int o = 16; o; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+        if (lane == 0) partial[(size_t)blockIdx.x * nvec + v] = a;
+    }
+}
+
 // two vectors against the same basis in one pass over it (block Arnoldi):
 // partial[c*2*nvec + 2*i + r] = sum over chunk c of Z_i[n] * u_r[n]
 __global__ void __launch_bounds__(256) k_dots_partial2(const double* __restrict__ Z, int64_t ldz, int nvec,
@@ -1001,6 +1057,13 @@ int ws_eig_solve(const ws_pattern* p, ws_solver* s, const double* B_vals, double
     DeviceGuard g(device);
     cudaStream_t st = (cudaStream_t)stream;
     {
+        static bool ud_configured = false;
+        if (!ud_configured) {
+            WS_CUDA(cudaFuncSetAttribute(k_update_dots, cudaFuncAttributeMaxDynamicSharedMemorySize, (MAXV + 1) * UD_TILE * (int)sizeof(double)));
+            ud_configured = true;
+        }
+    }
+    {
         static const int block = getenv("WS_EIG_BLOCK") ? atoi(getenv("WS_EIG_BLOCK")) : 1;
         if (kind == 1 && (block == 2 || want_block) && N > 4 * ncv) {
             int mb = ncv + (ncv & 1);
@@ -1062,13 +1125,26 @@ int ws_eig_solve(const ws_pattern* p, ws_solver* s, const double* B_vals, double
     };
     // one Arnoldi step: w = OP v_j, CGS2 against rows 0..j (coefficients with the dual basis,
     // update with the primal one), normalise into slot j+1
+    static const bool fuse_cgs = !(getenv("WS_NO_CGS_FUSE") && atoi(getenv("WS_NO_CGS_FUSE")));
     auto arnoldi_step = [&](cudaStream_t q, int j) {
         apply_op(q, j);
         double* Hcol = W.Hd.get() + (size_t)j * (m + 1);
-        for (int pass = 0; pass < 2; ++pass) {
-            dots(W, q, Z, j + 1, W.w.get(), W.h.get(), Hcol);
-            k_update<<<nb, T, 0, q>>>(W.w.get(), V, N, j + 1, W.h.get(), N);
-            count_launch(1);
+        const int nv = j + 1;
+        if (kind == 1 && fuse_cgs) {
+            // Euclidean inner product (dual basis = basis): the update of pass 1 and the inner products
+            // of pass 2 share one pass over the basis -- three basis reads per step instead of four
+            dots(W, q, V, nv, W.w.get(), W.h.get(), Hcol);
+            k_update_dots<<<W.nchunks, 256, (size_t)(nv + 1) * UD_TILE * sizeof(double), q>>>(W.w.get(), V, N, nv, W.h.get(), N,
+                                                                                         W.partial.get());
+            k_dots_reduce<<<nv, 32, 0, q>>>(W.partial.get(), W.nchunks, nv, W.h.get(), Hcol);
+            k_update<<<nb, T, 0, q>>>(W.w.get(), V, N, nv, W.h.get(), N);
+            count_launch(3);
+        } else {
+            for (int pass = 0; pass < 2; ++pass) {
+                dots(W, q, Z, nv, W.w.get(), W.h.get(), Hcol);
+                k_update<<<nb, T, 0, q>>>(W.w.get(), V, N, nv, W.h.get(), N);
+                count_launch(1);
+            }
         }
         normalize_into(q, j + 1, Hcol + (j + 1));
     };
