@@ -245,7 +245,13 @@ def run_ours(args):
         t0e, t1e = ev(), ev()
         t0e.record()
         for _ in range(args.steps):
+            if os.environ.get("WS_BENCH_TRACE"):
+                torch.cuda.synchronize()
+                _t = time.perf_counter()
             wd, Vd = device_step()
+            if os.environ.get("WS_BENCH_TRACE"):
+                torch.cuda.synchronize()
+                print("[bench step] rank %d: %.1f ms" % (rank, (time.perf_counter() - _t) * 1e3), file=sys.stderr, flush=True)
         t1e.record()
         barrier()
         dev_ms = t0e.elapsed_time(t1e) / args.steps
