@@ -16,6 +16,8 @@
  *                                   behind fe_solver.py:196-199, 212-213
  *   ws_spmv                      <- ARPACK reverse communication ido=2 (M_matvec) inside
  *                                   eigsh (fe_solver.py:328)
+ *   ws_overlap / ws_bnormalize   <- `u.T @ B @ v` with B = construct_B(mesh) (fe_solver.py:71-101,
+ *                                   notes eq. 38) and the B-normalisation eigsh applies to its output
  *   ws_solver_*                  <- SuperLU splu/gssv inside eigsh sigma-mode and spsolve
  *                                   (fe_solver.py:328, fe_solver.py:398)
  *   ws_eig_*                     <- eigsh(A, M=B, k, which='SA', sigma)   (fe_solver.py:328) and
@@ -253,6 +255,19 @@ int ws_interp_weights(const double* xy, const int32_t* conn, int64_t Ne, int str
                       void* stream);
 int ws_interp_apply(const int64_t* tri_idx, int64_t npts, int64_t Ne, const int32_t* dof, int stride, int nd, int wdim,
                     const double* weights, const double* field, int ncomp, double* out, int device, void* stream);
+
+/* ---- K16/K17: overlaps in the mass-matrix inner product (second widening step) ---------------
+ * The reference gives the user construct_B (fe_solver.py:71-101) and leaves `u.T @ B @ v` (notes eq. 38)
+ * to scipy, one pair of host vectors at a time.  Modes are rows: U [nu x ldu], V [nv x ldv] (device,
+ * ldu, ldv >= N); vals are values on the pattern (B from ws_assemble_mass_p2 / ws_assemble_*).
+ * ws_overlap    : G[i*nv + j] = U_i^T B V_j   (device, row-major nu x nv; B V_j is read once per
+ *                 pair of columns, the reduction order is fixed -> bitwise reproducible)
+ * ws_bnormalize : d[i] = U_i^T B U_i (device); scale != 0 also divides row i by sqrt(d[i]) where
+ *                 d[i] > 0 (rows with d <= 0 or NaN are left as they are).                          */
+int ws_overlap(const ws_pattern* p, const double* vals, const double* U, int64_t ldu, int nu, const double* V,
+               int64_t ldv, int nv, double* G, int device, void* stream);
+int ws_bnormalize(const ws_pattern* p, const double* vals, double* U, int64_t ldu, int nu, double* d, int scale,
+                  int device, void* stream);
 
 #ifdef __cplusplus
 }

@@ -174,8 +174,44 @@ def interp_cases(fe, wg):
     print("interp_vec_disc500", "inside", int((out["tri_idxs"] >= 0).sum()), "of", out["tri_idxs"].size)
 
 
+def fake_meshio_mesh():
+    """What meshio.read returns for a gmsh .msh with two triangle6 blocks: one index array per cell block
+    in every cell set, the last set being gmsh's bounding entities (waveguide.py:91-93)."""
+    rng = np.random.default_rng(12)
+    pts = rng.standard_normal((40, 3))
+    blocks = [mg.CellBlock("line", rng.integers(0, 40, (7, 2)).astype(np.uint64)),
+              mg.CellBlock("triangle6", rng.integers(0, 40, (5, 6)).astype(np.uint64)),
+              mg.CellBlock("triangle6", rng.integers(0, 40, (4, 6)).astype(np.uint64)),
+              mg.CellBlock("vertex", rng.integers(0, 40, (3, 1)).astype(np.uint64))]
+    e = np.zeros(0, dtype=np.int64)
+    sets = {"core": [e, np.array([0, 2]), np.array([1]), e],
+            "cladding": [e, np.array([1, 3, 4]), np.array([0, 2, 3]), e],
+            "jacket": [e, e, e, e],
+            "ring": [e, e, np.array([3]), e],
+            "gmsh:bounding_entities": [np.array([0, 1]), e, e, np.array([0])]}
+    m = mg.Mesh(pts, blocks[1].data, sets)
+    m.cells = blocks
+    return m
+
+
+def meshio_case(wg):
+    """load_meshio_mesh (waveguide.py:91-126) run literally, with meshio.read returning the fake above."""
+    wg.meshio.read = lambda name: fake_meshio_mesh()
+    out = wg.load_meshio_mesh("whatever")
+    d = {"tris": np.asarray(out.cells[1].data), "labels": np.array(list(out.cell_sets.keys())),
+         "others_none": np.array([out.cells[i] is None for i in range(len(out.cells)) if i != 1])}
+    for i, (k, v) in enumerate(out.cell_sets.items()):
+        assert v[0] is None and v[2] is None and len(v) == 3
+        d["set_%d" % i] = np.asarray(v[1], dtype=np.int64)
+    np.savez_compressed(os.path.join(GOLD, "meshio_regroup.npz"), **d)
+    print("meshio_regroup", d["tris"].shape, [len(d["set_%d" % i]) for i in range(len(d["labels"]))])
+
+
 def main():
     fe, sf, wg = refshim.load()
+    if "--meshio-only" in sys.argv:      # added later; leaves the earlier fixtures untouched
+        meshio_case(wg)
+        return
     os.makedirs(GOLD, exist_ok=True)
     ior = mg.FIBER_IOR
     if "--interp-only" in sys.argv:      # added later; leaves the earlier fixtures untouched

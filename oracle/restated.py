@@ -526,3 +526,20 @@ def interpolate_kdtree_loop(v, mesh, xa, ya, maxr=0):
                     out[i, j] = np.sum(np.asarray(v)[tris[e]] * N)
                     break
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# overlaps in the mass-matrix inner product
+# ---------------------------------------------------------------------------------------------
+def overlap_matrix(U, V, B, conj=False):
+    """`u.T @ B @ v` (notes eq. 38) for stacks of modes stored as rows -- the expression a reference
+    user writes with B = construct_B(mesh, sparse=True) (fe_solver.py:71-101)."""
+    U, V = np.asarray(U), np.asarray(V)
+    return (U.conj() if conj else U) @ (B @ V.T)
+
+
+def normalize_modes(U, B):
+    """u / sqrt(u^H B u) per row: the normalisation eigsh applies to the vectors it returns (fe_solver.py:328)."""
+    U = np.atleast_2d(np.asarray(U))
+    d = np.einsum("in,ni->i", U.conj(), B @ U.T).real
+    return U / np.sqrt(d)[:, None]

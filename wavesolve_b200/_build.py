@@ -25,6 +25,7 @@ SOURCES = {
     "ws_factor.cu": [],
     "ws_eig.cu": [],
     "ws_interp.cu": ["-fmad=false"],
+    "ws_overlap.cu": [],
 }
 
 

@@ -59,6 +59,8 @@ _SIGNATURES = {
     "ws_locate": (c_int, [c_vp, c_vp, c_vp, c_int, c_vp, c_vp, c_i64, c_i64, C.c_double, c_int, c_vp, c_int, c_vp]),
     "ws_interp_weights": (c_int, [c_vp, c_vp, c_i64, c_int, c_int, c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_int, c_vp]),
     "ws_interp_apply": (c_int, [c_vp, c_i64, c_i64, c_vp, c_int, c_int, c_int, c_vp, c_vp, c_int, c_vp, c_int, c_vp]),
+    "ws_overlap": (c_int, [c_vp, c_vp, c_vp, c_i64, c_int, c_vp, c_i64, c_int, c_vp, c_int, c_vp]),
+    "ws_bnormalize": (c_int, [c_vp, c_vp, c_vp, c_i64, c_int, c_vp, c_int, c_int, c_vp]),
     "ws_vector_T": (c_int, [c_vp, c_vp, c_vp, c_i64, c_int, c_vp, c_vp, c_int, c_vp]),
 }
 

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
 #include <cstdio>
 #include <cstring>
 #include <stdexcept>
@@ -99,6 +100,21 @@ struct DeviceGuard {
     }
     ~DeviceGuard() {
         if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+// cudaFuncSetAttribute is a per-device setting: run a (idempotent) configuration once per device
+// the calling thread is bound to.  Two threads racing on the first use both run it -- harmless.
+struct PerDeviceOnce {
+    std::atomic<uint64_t> done{0};
+    template <class F>
+    void operator()(F&& f) {
+        int dev = 0;
+        WS_CUDA(cudaGetDevice(&dev));
+        const uint64_t bit = 1ull << (dev & 63);
+        if (done.load(std::memory_order_acquire) & bit) return;
+        f();
+        done.fetch_or(bit, std::memory_order_release);
     }
 };
 

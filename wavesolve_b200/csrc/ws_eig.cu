@@ -1057,11 +1057,8 @@ int ws_eig_solve(const ws_pattern* p, ws_solver* s, const double* B_vals, double
     DeviceGuard g(device);
     cudaStream_t st = (cudaStream_t)stream;
     {
-        static bool ud_configured = false;
-        if (!ud_configured) {
-            WS_CUDA(cudaFuncSetAttribute(k_update_dots, cudaFuncAttributeMaxDynamicSharedMemorySize, (MAXV + 1) * UD_TILE * (int)sizeof(double)));
-            ud_configured = true;
-        }
+        static PerDeviceOnce configure;
+        configure([] { WS_CUDA(cudaFuncSetAttribute(k_update_dots, cudaFuncAttributeMaxDynamicSharedMemorySize, (MAXV + 1) * UD_TILE * (int)sizeof(double))); });
     }
     {
         static const int block = getenv("WS_EIG_BLOCK") ? atoi(getenv("WS_EIG_BLOCK")) : 1;

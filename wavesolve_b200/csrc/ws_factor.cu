@@ -1488,12 +1488,11 @@ static void build_plan(ws_solver* s, cudaStream_t st) {
 
 static void launch_gemm(const ws_solver* s, const Range& r, bool narrow, cudaStream_t st) {
     if (!r.cnt) return;
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceOnce configure;
+    configure([] {
         WS_CUDA(cudaFuncSetAttribute(k_gemm_tiles<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem_bytes<32>()));
         WS_CUDA(cudaFuncSetAttribute(k_gemm_tiles<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem_bytes<64>()));
-        configured = true;
-    }
+    });
     if (narrow) k_gemm_tiles<32><<<(unsigned)r.cnt, 128, gemm_smem_bytes<32>(), st>>>(s->gemm_tasks.get() + r.off);
     else k_gemm_tiles<64><<<(unsigned)r.cnt, 128, gemm_smem_bytes<64>(), st>>>(s->gemm_tasks.get() + r.off);
     count_launch(1);
@@ -1809,12 +1808,11 @@ int ws_solver_factor(ws_solver* s, const double* A_vals, const double* B_vals, d
         count_launch(1);
     }
     FrontView fv = view(s);
-    static bool fused_configured = false;
-    if (!fused_configured) {
+    static PerDeviceOnce configure_fused;
+    configure_fused([] {
         WS_CUDA(cudaFuncSetAttribute(k_front_fused<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FUSED_MAX_SMEM));
         WS_CUDA(cudaFuncSetAttribute(k_front_fused<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FUSED_MAX_SMEM));
-        fused_configured = true;
-    }
+    });
     for (int l = Y.depth; l >= 0; --l) {
         const LevelPlan& LP = s->levels[l];
         if (LP.fused) {
@@ -1882,8 +1880,8 @@ int ws_solver_solve(ws_solver* s, const double* b, double* x, int nrhs, int devi
     cudaStream_t st = (cudaStream_t)stream;
     const Symbolic& Y = s->sym;
     // (b may alias x: b is read by the forward sweep only, x is written by the backward sweep only)
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceOnce configure;
+    configure([] {
         const int big = 200 * 1024;
         WS_CUDA(cudaFuncSetAttribute(k_fwd_tile<8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
         WS_CUDA(cudaFuncSetAttribute(k_fwd_tile<32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
@@ -1893,8 +1891,7 @@ int ws_solver_solve(ws_solver* s, const double* b, double* x, int nrhs, int devi
         WS_CUDA(cudaFuncSetAttribute(k_fwd_tile<32, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
         WS_CUDA(cudaFuncSetAttribute(k_bwd_tile<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
         WS_CUDA(cudaFuncSetAttribute(k_bwd_tile<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-        configured = true;
-    }
+    });
     int rhs = 0;
     for (; rhs + 2 <= nrhs; rhs += 2) sweep_launches<2>(s, b + (size_t)rhs * s->N, x + (size_t)rhs * s->N, st);
     for (; rhs < nrhs; ++rhs) sweep_launches<1>(s, b + (size_t)rhs * s->N, x + (size_t)rhs * s->N, st);

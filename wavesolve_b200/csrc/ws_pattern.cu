@@ -15,12 +15,12 @@ namespace ws {
 
 static thread_local std::string g_last_error;
 void set_last_error(const std::string& s) { g_last_error = s; }
-static long long g_launches = 0;
-void count_launch(int n) { g_launches += n; }
+static std::atomic<long long> g_launches{0};
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 void configure_mempool(int device) {
-    static bool done[64] = {false};
-    if (device < 0 || device >= 64 || done[device]) return;
+    static std::atomic<bool> done[64];
+    if (device < 0 || device >= 64 || done[device].load()) return;
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
         unsigned long long thr = ~0ull;
@@ -30,7 +30,7 @@ void configure_mempool(int device) {
         int off = 0;
         cudaMemPoolSetAttribute(pool, cudaMemPoolReuseAllowInternalDependencies, &off);
     }
-    done[device] = true;
+    done[device].store(true);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -249,7 +249,7 @@ extern "C" {
 
 int ws_version(void) { return 100; }
 const char* ws_last_error(void) { return ws::g_last_error.c_str(); }
-long long ws_launch_count(void) { return ws::g_launches; }
+long long ws_launch_count(void) { return ws::g_launches.load(std::memory_order_relaxed); }
 
 int ws_edges_first_appearance(const int32_t* tris, int64_t Ne, int64_t Np, int32_t* edges,
                               int32_t* edge_idx, int64_t* h_Ntt, int device, void* stream) {

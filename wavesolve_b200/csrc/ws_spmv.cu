@@ -25,12 +25,12 @@ constexpr int SPMV_MAX_SMEM = 64 * 1024;
 // gathers of x, then parks the products: the dependent chain of a CTA is
 // rowptr -> (col, val) -> x -> shared memory, once for a block of edge / mid-side rows (~9
 // entries per row) and twice for a block of vertex / node rows (~19 per row).
-// NV vectors (x, y with stride ldv) share the (value, column) stream: a second vector costs its own
+// NV vectors (x with stride ldx, y with stride ldy) share the (value, column) stream: a second vector costs its own
 // gathers and products only.
 template <int NV>
 __global__ void __launch_bounds__(SPMV_ROWS)
 k_spmv_stream(int64_t N, int64_t nnz, int cap, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
-              const double* __restrict__ vals, const double* __restrict__ x, double* __restrict__ y, int64_t ldv) {
+              const double* __restrict__ vals, const double* __restrict__ x, int64_t ldx, double* __restrict__ y, int64_t ldy) {
     extern __shared__ double prod[];          // [NV][cap]
     __shared__ int rp[SPMV_ROWS + 1];
     const int64_t r0 = (int64_t)blockIdx.x * SPMV_ROWS;
@@ -71,7 +71,7 @@ k_spmv_stream(int64_t N, int64_t nnz, int cap, const int32_t* __restrict__ rowpt
             }
 #pragma unroll
             for (int v = 0; v < NV; ++v) {
-                const double* xv = x + (size_t)v * ldv;
+                const double* xv = x + (size_t)v * ldx;
                 double* pv = prod + (size_t)v * cap;
 #pragma unroll
                 for (int i = 0; i < SPMV_CHUNKS; ++i) {
@@ -99,43 +99,47 @@ k_spmv_stream(int64_t N, int64_t nnz, int cap, const int32_t* __restrict__ rowpt
                 const double* pv = prod + (size_t)v * cap;
                 double acc = 0.0;
                 for (int i = a; i < b; ++i) acc += pv[i];
-                y[r0 + tid + (size_t)v * ldv] = acc;
+                y[r0 + tid + (size_t)v * ldy] = acc;
             }
         }
     } else if (tid < nr) {      // unusually dense block: plain row loop
         for (int v = 0; v < NV; ++v) {
             double acc = 0.0;
-            for (int i = rp[tid]; i < rp[tid + 1]; ++i) acc += vals[i] * x[colidx[i] + (size_t)v * ldv];
-            y[r0 + tid + (size_t)v * ldv] = acc;
+            for (int i = rp[tid]; i < rp[tid + 1]; ++i) acc += vals[i] * x[colidx[i] + (size_t)v * ldx];
+            y[r0 + tid + (size_t)v * ldy] = acc;
         }
     }
 }
 
 template <int NV>
-static void spmv_launch_nv(const ws_pattern* p, const double* vals, const double* x, double* y, int64_t ldv, cudaStream_t st) {
+static void spmv_launch_nv(const ws_pattern* p, const double* vals, const double* x, int64_t ldx, double* y, int64_t ldy, cudaStream_t st) {
     if (p->N == 0) return;
-    static bool configured = false;
-    if (!configured) {
-        WS_CUDA(cudaFuncSetAttribute(k_spmv_stream<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, SPMV_MAX_SMEM));
-        configured = true;
-    }
+    static PerDeviceOnce configure;
+    configure([] { WS_CUDA(cudaFuncSetAttribute(k_spmv_stream<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, SPMV_MAX_SMEM)); });
     // shared-memory tile sized for this pattern's densest 128-row block (known from K2)
     int cap = std::min(std::max(p->max_block_slots, 256), SPMV_MAX_SMEM / 8 / NV);
     cap = (cap + 63) & ~63;
     if ((size_t)cap * NV * sizeof(double) > (size_t)SPMV_MAX_SMEM) cap = (SPMV_MAX_SMEM / 8 / NV) & ~63;
     k_spmv_stream<NV><<<ceil_div(p->N, SPMV_ROWS), SPMV_ROWS, (size_t)cap * NV * sizeof(double), st>>>(
-        p->N, p->nnz, cap, p->rowptr.get(), p->colidx.get(), vals, x, y, ldv);
+        p->N, p->nnz, cap, p->rowptr.get(), p->colidx.get(), vals, x, ldx, y, ldy);
     WS_CUDA(cudaGetLastError());
     count_launch(1);
 }
 
 void spmv_launch(const ws_pattern* p, const double* vals, const double* x, double* y, cudaStream_t st) {
-    spmv_launch_nv<1>(p, vals, x, y, p->N, st);
+    spmv_launch_nv<1>(p, vals, x, p->N, y, p->N, st);
 }
 
 // two vectors stored with stride N
 void spmv_launch2(const ws_pattern* p, const double* vals, const double* x, double* y, cudaStream_t st) {
-    spmv_launch_nv<2>(p, vals, x, y, p->N, st);
+    spmv_launch_nv<2>(p, vals, x, p->N, y, p->N, st);
+}
+
+// nv = 1 or 2 vectors with independent strides (rows of a mode matrix in, scratch columns out)
+void spmv_launch_strided(const ws_pattern* p, const double* vals, const double* x, int64_t ldx, double* y, int64_t ldy,
+                         int nv, cudaStream_t st) {
+    if (nv == 2) spmv_launch_nv<2>(p, vals, x, ldx, y, ldy, st);
+    else spmv_launch_nv<1>(p, vals, x, ldx, y, ldy, st);
 }
 
 }  // namespace ws

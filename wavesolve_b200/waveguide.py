@@ -7,6 +7,7 @@ import numpy as np
 import torch
 
 from . import _lib, device as _dev
+from .mesh_io import load_meshio_mesh  # noqa: F401  (waveguide.py:91 lives in this module in the reference)
 
 
 def _torch_dtype(dt):
