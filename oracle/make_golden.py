@@ -207,8 +207,32 @@ def meshio_case(wg):
     print("meshio_regroup", d["tris"].shape, [len(d["set_%d" % i]) for i in range(len(d["labels"]))])
 
 
+def solve_sparse_case(fe):
+    """solve_sparse (fe_solver.py:262-290) with its default num_modes=6 on the matrices of two
+    existing fixtures (P2 disc, P1 disc: lil -> csr of construct_AB_order1), and compute_IOR_arr
+    (fe_solver.py:446-452) on the ragged material sets.  Only results are stored: the meshes and
+    matrices are the ones already in scalar_disc600 / scalar_p1_disc800 / scalar_sq6_ragged."""
+    k = 2 * np.pi / WL
+    ior = mg.FIBER_IOR
+    out = {}
+    for tag, mesh, order in (("p2", mg.fiber_disc(600, seed=1), 2), ("p1", mg.fiber_disc(800, order=1, seed=6), 1)):
+        A, B = fe.construct_AB(mesh, ior, k, sparse=True, order=order)
+        w, v, cnt = fe.solve_sparse(A, B, mesh, k, ior)
+        out[tag + "_w"], out[tag + "_v"], out[tag + "_count"] = np.array(w), np.ascontiguousarray(v), np.array(cnt)
+        print("solve_sparse", tag, "neff", np.sqrt(np.array(w)) / k, "count", cnt)
+    m = mg.structured_square(6)
+    core, clad = m.cell_sets["core"][1], m.cell_sets["cladding"][1]
+    m.cell_sets = {"core": [None, core, None], "void": [None, np.zeros(0, dtype=np.int64), None],
+                   "cladding": [None, np.concatenate([clad[:-5], core[:1]]), None]}
+    out["ior_arr_ragged"] = fe.compute_IOR_arr(m, {"core": 1.46, "void": 1.0, "cladding": 1.444})
+    np.savez_compressed(os.path.join(GOLD, "solve_sparse.npz"), **out)
+
+
 def main():
     fe, sf, wg = refshim.load()
+    if "--solve-sparse-only" in sys.argv:   # added later; leaves the earlier fixtures untouched
+        solve_sparse_case(fe)
+        return
     if "--meshio-only" in sys.argv:      # added later; leaves the earlier fixtures untouched
         meshio_case(wg)
         return

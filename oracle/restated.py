@@ -345,6 +345,23 @@ def solve_waveguide(mesh, wl, IOR_dict, Nmax=10, target_neff=None, AB=None, orde
     return w[::-1], v.T[::-1], count_modes_scalar(w[::-1], k, IOR_dict)
 
 
+def solve_sparse(A, B, mesh, k, IOR_dict, num_modes=6):
+    """fe_solver.py:262-290: the eigsh call of solve_waveguide on matrices the caller brings,
+    sigma always (k n_max)^2, default 6 modes; results reversed to descending order."""
+    sigma = np.power(k * max(IOR_dict.values()), 2)
+    w, v = spla.eigsh(A.tocsr(), M=B.tocsr(), k=num_modes, which="SA", sigma=sigma)
+    return w[::-1], v.T[::-1], count_modes_scalar(w[::-1], k, IOR_dict)
+
+
+def compute_IOR_arr(mesh, IOR_dict):
+    """fe_solver.py:446-452: index per element in cells[1].data order; unassigned elements stay 0,
+    later material sets overwrite earlier ones."""
+    out = np.zeros(len(mesh.cells[1].data))
+    for material, sel in mesh.cell_sets.items():
+        out[np.asarray(sel[1], dtype=np.int64)] = IOR_dict[material]
+    return out
+
+
 def solve_waveguide_vec(mesh, wl, IOR_dict, Nmax=10, target_neff=None, AB=None, return_info=False):
     """Vector solve, 'transform' semantics (fe_solver.py:397-400) applied matrix-free:
     the reference forms the dense C = (A - sigma B)^-1 B with spsolve and calls

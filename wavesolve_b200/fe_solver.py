@@ -483,6 +483,93 @@ def solve_waveguide(mesh, wl, IOR_dict, plot=False, ignore_warning=False, sparse
     return w, v, mode_count
 
 
+def _values_on_pattern(M, pattern, what):
+    """Values of a scipy sparse matrix laid out on the slots of a device pattern.  A matrix with
+    exactly the pattern's structure (what ``construct_AB`` returns, explicit zeros included) is
+    uploaded as it is; any other matrix whose entries all lie inside the pattern (pruned zeros,
+    lil -> csr of ``construct_AB_order1``) is scattered into place by a sorted-key lookup on the
+    device; an entry outside the mesh's pattern is refused."""
+    import scipy.sparse as sp
+    if not sp.issparse(M):
+        raise TypeError("%s: a scipy sparse matrix is expected (the dense `solve` of fe_solver.py:220 "
+                        "is not part of the device path)" % what)
+    M = M.tocsr()                                                  # fe_solver.py:266
+    N, dev = pattern.N, pattern.dev
+    if M.shape != (N, N):
+        raise ValueError("%s has shape %s, the mesh gives %d unknowns" % (what, M.shape, N))
+    if not M.has_canonical_format:
+        M = M.copy()                                               # never touch the caller's matrix
+        M.sum_duplicates()
+    if np.iscomplexobj(M.data):
+        raise TypeError("%s: real matrices only" % what)
+    indptr = _dev.h2d(np.ascontiguousarray(M.indptr, dtype=np.int32), dev)
+    indices = _dev.h2d(np.ascontiguousarray(M.indices, dtype=np.int32), dev)
+    data = _dev.h2d(np.ascontiguousarray(M.data, dtype=np.float64), dev)
+    p_indptr, p_indices = pattern.export()
+    return _place_on_pattern(p_indptr, p_indices, indptr, indices, data, N, what)
+
+
+def _place_on_pattern(p_indptr, p_indices, indptr, indices, data, N, what="matrix"):
+    """CSR arrays (canonical: sorted, no duplicates) -> value array on the slots of the CSR pattern
+    (p_indptr, p_indices).  Tensors of one device; index marshalling only (sorted (row, column) keys,
+    one binary search per stored entry)."""
+    nnz_p = p_indices.numel()
+    if indices.numel() == nnz_p and torch.equal(indptr, p_indptr) and torch.equal(indices, p_indices):
+        return data
+    dev = p_indptr.device
+    rows = torch.arange(N, dtype=torch.int64, device=dev)
+    key_p = torch.repeat_interleave(rows, torch.diff(p_indptr).to(torch.int64)) * N + p_indices.to(torch.int64)
+    key_m = torch.repeat_interleave(rows, torch.diff(indptr).to(torch.int64)) * N + indices.to(torch.int64)
+    slot = torch.searchsorted(key_p, key_m)
+    ok = slot < nnz_p
+    if nnz_p:
+        ok &= key_p[slot.clamp(max=nnz_p - 1)] == key_m
+    if not bool(ok.all()):
+        raise ValueError("%s has %d stored entries outside the sparsity pattern of the mesh"
+                         % (what, int((~ok).sum())))
+    vals = torch.zeros(nnz_p, dtype=torch.float64, device=dev)
+    vals[slot] = data
+    return vals
+
+
+def solve_sparse(A, B, mesh, k, IOR_dict, plot=False, num_modes=6, device=None, leaf_elems=None):
+    """The eigen-solve on matrices the caller already holds (fe_solver.py:262-290):
+    ``eigsh(A.tocsr(), M=B.tocsr(), k=num_modes, which="SA", sigma=(k max n)^2)``, returned as
+    ``(w descending, v rows, mode_count)``.  ``A`` / ``B``: scipy sparse matrices on the unknowns of
+    ``mesh`` (``construct_AB(mesh, IOR_dict, k, sparse=True)`` of the reference or of this package, any
+    format).  The values are placed on the mesh's device pattern and go through the same
+    factorisation + Lanczos iteration as ``solve_waveguide``; the mesh supplies the coordinates the
+    nested-dissection ordering works on (SuperLU orders the bare matrix with COLAMD)."""
+    ncol = np.asarray(mesh.cells[1].data).shape[1]
+    if ncol not in (3, 6):
+        raise NotImplementedError("triangles with %d nodes" % ncol)
+    order = 2 if ncol == 6 else 1
+    est_eigval = np.power(k * max(IOR_dict.values()), 2)
+    prob = ScalarProblem(mesh, IOR_dict, k, device, order=order)
+    with torch.cuda.device(prob.dev):
+        Av = _values_on_pattern(A, prob.pattern, "A")
+        Bv = _values_on_pattern(B, prob.pattern, "B")
+        wd, Vd, info = solve_scalar_resident(prob, est_eigval, num_modes, leaf_elems, values=(Av, Bv))
+        w = _dev.d2h(wd)
+        v = _dev.d2h_pinned(Vd)
+    prob.pattern.close()
+    last_info.clear()
+    last_info.update(info)
+    mode_count = _count_modes(w, k, IOR_dict)
+    if plot:
+        _report_modes(2 * np.pi / k, w, k, IOR_dict, warn_always=True)
+    return w, v, mode_count
+
+
+def compute_IOR_arr(mesh, IOR_dict):
+    """Refractive index per element in ``cells[1].data`` order (fe_solver.py:446-452); elements
+    in no material set stay 0, a later set overwrites an earlier one."""
+    IORs = np.zeros(len(mesh.cells[1].data))
+    for material in mesh.cell_sets.keys():
+        IORs[tuple(mesh.cell_sets[material])] = IOR_dict[material]
+    return IORs
+
+
 def solve_vector_resident(prob, sigma, Nmax, leaf_elems=None, symbolic=None, solver=None, out=None):
     """Device part of the vector solve on a resident VectorProblem: assembly of B and of the
     quasi-definite M', symbolic analysis (host), factorisation, Krylov iteration.  Returns
@@ -509,11 +596,13 @@ def solve_vector_resident(prob, sigma, Nmax, leaf_elems=None, symbolic=None, sol
     return wd, Vd, info
 
 
-def solve_scalar_resident(prob, sigma, Nmax, leaf_elems=None, symbolic=None, solver=None, out=None):
-    """Device part of the scalar solve on a resident ScalarProblem (see solve_vector_resident)."""
+def solve_scalar_resident(prob, sigma, Nmax, leaf_elems=None, symbolic=None, solver=None, out=None, values=None):
+    """Device part of the scalar solve on a resident ScalarProblem (see solve_vector_resident).
+    ``values=(A, B)``: device value arrays on the problem's pattern to use instead of assembling
+    (``solve_sparse``: the caller brings the matrices)."""
     from . import solver as _sv
     prob.build_pattern()
-    A, B = prob.assemble(fast=True)
+    A, B = values if values is not None else prob.assemble(fast=True)
     if solver is not None:
         S = solver
     else:
