@@ -38,6 +38,29 @@ def test_partition_splits_a_single_mesh_across_ranks():
     assert sorted(len(r) for r in t) == [0] * 5 + [1] * 3
 
 
+def test_problem_grid_is_mesh_major_and_carries_tags():
+    from wavesolve_b200 import sweep
+    ior = {"core": 1.45, "cladding": 1.44}
+    wls = np.linspace(1.0, 1.8, 4)
+    g = sweep.problem_grid(3, wls, ior, tags=[9.0, 12.5, 16.0])
+    assert [p.mesh_id for p in g] == [0] * 4 + [1] * 4 + [2] * 4
+    assert [p.wl for p in g[:4]] == [float(w) for w in wls] and g[5].tag == (12.5, float(wls[1]))
+    assert all(p.IOR_dict == ior and p.IOR_dict is not ior for p in g)
+    per_mesh = [{"core": 1.45 + 0.01 * m, "cladding": 1.44} for m in range(3)]
+    g = sweep.problem_grid(3, [1.55], per_mesh, target_neff=1.444)
+    assert [p.IOR_dict["core"] for p in g] == [1.45, 1.46, 1.47] and g[0].target_neff == 1.444 and g[2].tag == (2, 1.55)
+    g = sweep.problem_grid(2, [1.0, 2.0], lambda m, wl: {"core": 1.45 - 0.01 * wl, "cladding": 1.44})
+    assert [round(p.IOR_dict["core"], 6) for p in g] == [1.44, 1.43, 1.44, 1.43]
+    assert sweep.problem_grid(0, wls, ior) == [] and sweep.problem_grid(2, [], ior) == []
+    with pytest.raises(ValueError):
+        sweep.problem_grid(2, wls, per_mesh)
+    with pytest.raises(ValueError):
+        sweep.problem_grid(2, wls, ior, tags=[1.0])
+    # the grid feeds partition: the wavelengths of one mesh stay together on a rank
+    table = sweep.partition([p.mesh_id for p in sweep.problem_grid(4, wls, ior)], [1.0] * 16, 2)
+    assert sorted(len(t) for t in table) == [8, 8]
+
+
 def test_partition_edge_cases():
     assert sweep.partition([], [], 4) == [[], [], [], []]
     assert sweep.partition([3], [2.0], 1) == [[0]]

@@ -5,6 +5,7 @@ The reference runs sweeps as a serial notebook loop that re-meshes per z-slice, 
 per wavelength and pickles per radius (lantern-demo.ipynb cell 4).  Here a sweep is a list of
 independent ``SweepProblem``s:
 
+* ``problem_grid``   meshes x wavelengths (x index sets) -> the flat problem list;
 * ``partition``      cost-sorted, mesh-grouped longest-first assignment of problems to ranks
                      (pure host logic; identical on every rank, no communication);
 * ``solve_sweep``    each rank keeps one resident context per mesh (pattern, incidence lists,
@@ -44,6 +45,31 @@ class SweepResult:
     mode_count: int
     rank: int
     info: dict = field(default_factory=dict)
+
+
+def problem_grid(n_meshes: int, wavelengths: Sequence[float], IOR_dicts, target_neff: Optional[float] = None,
+                 tags: Optional[Sequence] = None) -> List[SweepProblem]:
+    """The problem list of the reference's sweep loop (lantern-demo.ipynb cell 4: for each z-slice
+    mesh, for each wavelength, solve) as a flat list, mesh-major so that the problems of one mesh are
+    adjacent.  ``IOR_dicts``: one dict for all problems, one per mesh (sequence of length ``n_meshes``),
+    or a callable ``(mesh_id, wl) -> dict`` for dispersive materials.  ``tags[m]`` labels mesh ``m``
+    (e.g. the taper radius); each problem carries ``tag = (tags[m], wl)``."""
+    if tags is not None and len(tags) != n_meshes:
+        raise ValueError("tags: one per mesh")
+    if not callable(IOR_dicts) and not isinstance(IOR_dicts, dict) and len(IOR_dicts) != n_meshes:
+        raise ValueError("IOR_dicts: one dict, one dict per mesh, or a callable")
+    out = []
+    for m in range(n_meshes):
+        for wl in wavelengths:
+            wl = float(wl)
+            if callable(IOR_dicts):
+                ior = IOR_dicts(m, wl)
+            elif isinstance(IOR_dicts, dict):
+                ior = IOR_dicts
+            else:
+                ior = IOR_dicts[m]
+            out.append(SweepProblem(m, wl, dict(ior), target_neff, (tags[m] if tags is not None else m, wl)))
+    return out
 
 
 def estimate_cost(n_unknowns: int) -> float:
