@@ -546,13 +546,15 @@ def solve_sparse(A, B, mesh, k, IOR_dict, plot=False, num_modes=6, device=None, 
     order = 2 if ncol == 6 else 1
     est_eigval = np.power(k * max(IOR_dict.values()), 2)
     prob = ScalarProblem(mesh, IOR_dict, k, device, order=order)
-    with torch.cuda.device(prob.dev):
-        Av = _values_on_pattern(A, prob.pattern, "A")
-        Bv = _values_on_pattern(B, prob.pattern, "B")
-        wd, Vd, info = solve_scalar_resident(prob, est_eigval, num_modes, leaf_elems, values=(Av, Bv))
-        w = _dev.d2h(wd)
-        v = _dev.d2h_pinned(Vd)
-    prob.pattern.close()
+    try:
+        with torch.cuda.device(prob.dev):
+            Av = _values_on_pattern(A, prob.pattern, "A")
+            Bv = _values_on_pattern(B, prob.pattern, "B")
+            wd, Vd, info = solve_scalar_resident(prob, est_eigval, num_modes, leaf_elems, values=(Av, Bv))
+            w = _dev.d2h(wd)
+            v = _dev.d2h_pinned(Vd)
+    finally:
+        prob.pattern.close()
     last_info.clear()
     last_info.update(info)
     mode_count = _count_modes(w, k, IOR_dict)
