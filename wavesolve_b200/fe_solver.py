@@ -49,14 +49,14 @@ def _material_order(mesh, IOR_dict, k):
         k2.append(np.full(len(idx), k ** 2 * IOR_dict[material] ** 2, dtype=np.float64))
     if not idxs:
         return np.zeros(0, dtype=np.int64), np.zeros(0)
-    order = np.concatenate(idxs)
+    order = idxs[0] if len(idxs) == 1 else np.concatenate(idxs)
+    if len(order) == ne and ne and order[0] == 0 and order[-1] == ne - 1 and np.array_equal(order, np.arange(ne)):
+        return None, np.concatenate(k2)          # identity: nothing to gather, no bounds check needed
     if order.size and (int(order.min()) < 0 or int(order.max()) >= ne):
         # numpy fancy indexing semantics of the reference: negative ids wrap, too large ids raise
         if int(order.max()) >= ne or int(order.min()) < -ne:
             raise IndexError("cell_sets index out of bounds for cells[1].data")
         order = np.where(order < 0, order + ne, order)
-    if len(order) == ne and np.array_equal(order, np.arange(ne)):
-        return None, np.concatenate(k2)
     return order, np.concatenate(k2)
 
 
@@ -241,9 +241,13 @@ class VectorProblem:
         tris32 = _as_i32(tris_all[:, :3], "vertex ids")
         eidx32 = _as_i32(eidx_all, "edge ids")
         edges32 = _as_i32(np.asarray(mesh.cells[0].data), "edge table")
-        xy = np.ascontiguousarray(np.asarray(mesh.points, dtype=np.float64)[:, :2])
+        pts = np.asarray(mesh.points)
+        whole = pts.dtype == np.float64 and pts.ndim == 2 and pts.shape[1] > 2 and pts.flags.c_contiguous
+        # (Np, 3) float64 as pygmsh delivers it: the z column is dropped on the device (a strided host copy of
+        # the first two columns costs more than moving the third one)
+        xy = pts if whole else np.ascontiguousarray(np.asarray(pts, dtype=np.float64)[:, :2])
         with torch.cuda.device(dev):
-            self.xy = _dev.h2d(xy, dev)
+            self.xy = _dev.h2d(xy, dev)[:, :2].contiguous() if whole else _dev.h2d(xy, dev)
             self.edges = _dev.h2d(edges32, dev)
             self.k2n2 = _dev.h2d(k2, dev)
             t_d, e_d = _dev.h2d(tris32, dev), _dev.h2d(eidx32, dev)
