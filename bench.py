@@ -96,7 +96,13 @@ class ClockSampler:
                                              stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
                 self.th = threading.Thread(target=self._run, daemon=True)
                 self.th.start()
-                time.sleep(0.3)          # NVML initialisation of the sampler happens before the timed region
+                # NVML initialisation of the sampler must be over before the timed region starts (it stalls
+                # the driver calls of the step under test): wait for its first sample, not for a fixed time --
+                # on a fresh box nvidia-smi and libnvidia-ml are still being paged in
+                t0 = time.time()
+                while not self.samples and time.time() - t0 < 10.0 and self.proc.poll() is None:
+                    time.sleep(0.02)
+                time.sleep(0.1)
             except Exception:
                 self.proc = None
         return self
