@@ -36,10 +36,9 @@ def get_unique_edges(mesh, mutate=True, device=None):
     ``edge_indices`` (uint), ``edge_flips``, ``num_edges`` and ``num_points``.
     The O(E^2) list scan is replaced by a device sort/unique/rank (csrc/ws_pattern.cu)."""
     dev = _dev.require_cuda(device)
+    from .fe_solver import _as_i32
     tris = np.asarray(mesh.cells[1].data)
-    if tris.size and int(tris[:, :3].max()) >= 2 ** 31:
-        raise ValueError("vertex ids must fit in int32")
-    t32 = np.ascontiguousarray(tris[:, :3].astype(np.int32))
+    t32 = _as_i32(tris[:, :3], "vertex ids")
     with torch.cuda.device(dev):
         td = _dev.h2d(t32, dev)
         npts = int(t32.max()) + 1 if t32.size else 0
