@@ -20,7 +20,7 @@
  *                                   notes eq. 38) and the B-normalisation eigsh applies to its output
  *   ws_solver_*                  <- SuperLU splu/gssv inside eigsh sigma-mode and spsolve
  *                                   (fe_solver.py:328, fe_solver.py:398)
- *   ws_eig_*                     <- eigsh(A, M=B, k, which='SA', sigma)   (fe_solver.py:328) and
+ *   ws_eig_*                     <- eigsh(A, M=B, k, which='SA', sigma)   (fe_solver.py:328, :266) and
  *                                   eigs((A - sigma B)^-1 B, k, which='SR') (fe_solver.py:398-400)
  *
  * Conventions
