@@ -162,9 +162,19 @@ int ws_symbolic_destroy(ws_symbolic* s);
  * ws_solver_create : binds a pattern to a symbolic analysis, allocates all fronts (they stay
  *                    resident; ~6 kB per unknown at 1M elements) and uploads the task plan.
  * ws_solver_factor : M = A_vals - sigma*B_vals (values on the pattern; B_vals may be NULL for
- *                    M = A_vals), multifrontal LDL^T without pivoting + selective inversion.
- *                    Synchronises the stream once to read the pivot statistics; returns
- *                    WS_ERR_NUMERIC on a zero / non-finite pivot.
+ *                    M = A_vals), multifrontal LDL^T with STATIC pivoting (|pivot| < 1e-10 max|M_ij| is
+ *                    replaced by +-that) + selective inversion, followed by an accuracy probe: one system
+ *                    M x = b is solved with the new factors and its normwise backward error decides how many
+ *                    steps of iterative refinement every later ws_solver_solve performs (0 when the factors
+ *                    pass as they are: definite / quasi-definite matrices at the default shift).  This is what
+ *                    SuperLU's partial pivoting buys the reference for interior shifts (target_neff,
+ *                    fe_solver.py:313-316, :375-378).  Synchronises the stream to read the statistics; returns
+ *                    WS_ERR_NUMERIC on non-finite pivots or when refinement cannot reach a backward error of
+ *                    1e-11 (never a silently inaccurate factorisation).  While refine steps > 0 the value
+ *                    arrays must stay alive until the last solve (the residual b - M x is formed from them).
+ * ws_solver_quality: h_info[4] = perturbed pivots, refinement steps per solve, refinement steps the probe
+ *                    needed, 0;  h_dinfo[4] = probe backward error before / after refinement, max|M_ij|,
+ *                    pivot threshold.
  * ws_solver_solve  : x = M^-1 b, nrhs right-hand sides stored contiguously [nrhs*N]; asynchronous.
  *                    Right-hand sides are swept in pairs that share every load of the inverted
  *                    panels (1.26 ms for two vs 1.03 ms for one at 1M triangles).
@@ -181,6 +191,7 @@ int ws_solver_solve(ws_solver* s, const double* b, double* x, int nrhs, int devi
  *                    gave up waiting for a front since the last solve (internal error guard).    */
 int ws_solver_check(const ws_solver* s, int device, void* stream);
 int ws_solver_stats(const ws_solver* s, int64_t* h_info, double* h_dinfo);
+int ws_solver_quality(const ws_solver* s, int64_t* h_info, double* h_dinfo);
 int ws_solver_destroy(ws_solver* s);
 
 /* ---- vector problem: quasi-definite form ---------------------------------------------------

@@ -48,6 +48,7 @@ _SIGNATURES = {
     "ws_solver_solve": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_vp]),
     "ws_solver_check": (c_int, [c_vp, c_int, c_vp]),
     "ws_solver_stats": (c_int, [c_vp, c_vp, c_vp]),
+    "ws_solver_quality": (c_int, [c_vp, c_vp, c_vp]),
     "ws_solver_destroy": (c_int, [c_vp]),
     "ws_assemble_vector_qd": (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, C.c_double, c_vp, c_vp, c_int, c_int, c_vp]),
     "ws_eig_solve": (c_int, [c_vp, c_vp, c_vp, C.c_double, c_int, c_int, c_int, C.c_double, c_int, C.c_uint64,

@@ -128,6 +128,16 @@ void configure_mempool(int device);
 // global launch counter (bench.py reports how many of OUR kernels ran in the timed region)
 void count_launch(int n = 1);
 
+#ifdef __CUDACC__
+// fp64 tensor-core MMA (DMMA m8n8k4; tcgen05 has no fp64 kind, so this is the sm_100a fp64 tensor path).
+// Fragment layout (g = lane >> 2, tq = lane & 3): a = A[g][tq], b = B[tq][g], c0/c1 = C[g][2 tq], C[g][2 tq + 1].
+__device__ __forceinline__ void dmma8x8x4(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+#endif
+
 }  // namespace ws
 
 // ---------------------------------------------------------------------------------------

@@ -29,10 +29,11 @@ void spmv_launch(const ws_pattern* p, const double* vals, const double* x, doubl
 void spmv_launch2(const ws_pattern* p, const double* vals, const double* x, double* y, cudaStream_t st);
 
 // =============================================================================================
-// host dense eigen-solvers (n <= ~64)
+// host dense eigen-solvers (n <= MAX_NCV)
 // =============================================================================================
-// symmetric: cyclic Jacobi.  A row-major n x n (destroyed), w eigenvalues, V[i*n+j] = component i of vector j
-void jacobi_sym(int n, std::vector<double>& A, std::vector<double>& w, std::vector<double>& V) {
+// symmetric, small (n <= 48): cyclic Jacobi.  A row-major n x n (destroyed), w eigenvalues,
+// V[i*n+j] = component i of vector j
+static void jacobi_small(int n, std::vector<double>& A, std::vector<double>& w, std::vector<double>& V) {
     V.assign((size_t)n * n, 0.0);
     for (int i = 0; i < n; ++i) V[(size_t)i * n + i] = 1.0;
     auto a = [&](int i, int j) -> double& { return A[(size_t)i * n + j]; };
@@ -69,6 +70,121 @@ void jacobi_sym(int n, std::vector<double>& A, std::vector<double>& w, std::vect
     }
     w.resize(n);
     for (int i = 0; i < n; ++i) w[i] = a(i, i);
+}
+
+// symmetric, wide bases (ncv up to 256 for Nmax ~ 100: Jacobi would cost ~10^8 flops per restart):
+// Householder reduction to tridiagonal form with the transformation accumulated in place, then the
+// implicit-shift QL iteration on the tridiagonal (the classical tred2 / tql2 scheme), O(n^3) once.
+static bool tridiag_ql(int n, std::vector<double>& A, std::vector<double>& w, std::vector<double>& V) {
+    V = A;
+    auto z = [&](int i, int j) -> double& { return V[(size_t)i * n + j]; };
+    std::vector<double> d(n, 0.0), e(n, 0.0);
+    for (int i = n - 1; i >= 1; --i) {
+        const int l = i;                       // columns 0..l-1 of row i are eliminated down to one entry
+        double h = 0.0, scale = 0.0;
+        if (l > 1) {
+            for (int k = 0; k < l; ++k) scale += std::fabs(z(i, k));
+            if (scale == 0.0) {
+                e[i] = z(i, l - 1);
+            } else {
+                for (int k = 0; k < l; ++k) {
+                    z(i, k) /= scale;
+                    h += z(i, k) * z(i, k);
+                }
+                double f = z(i, l - 1);
+                double g = f >= 0.0 ? -std::sqrt(h) : std::sqrt(h);
+                e[i] = scale * g;
+                h -= f * g;
+                z(i, l - 1) = f - g;
+                f = 0.0;
+                for (int j = 0; j < l; ++j) {
+                    z(j, i) = z(i, j) / h;
+                    g = 0.0;
+                    for (int k = 0; k <= j; ++k) g += z(j, k) * z(i, k);
+                    for (int k = j + 1; k < l; ++k) g += z(k, j) * z(i, k);
+                    e[j] = g / h;
+                    f += e[j] * z(i, j);
+                }
+                const double hh = f / (h + h);
+                for (int j = 0; j < l; ++j) {
+                    f = z(i, j);
+                    e[j] = g = e[j] - hh * f;
+                    for (int k = 0; k <= j; ++k) z(j, k) -= f * e[k] + g * z(i, k);
+                }
+            }
+        } else {
+            e[i] = z(i, l - 1);
+        }
+        d[i] = h;
+    }
+    d[0] = 0.0;
+    e[0] = 0.0;
+    for (int i = 0; i < n; ++i) {
+        if (d[i] != 0.0)
+            for (int j = 0; j < i; ++j) {
+                double g = 0.0;
+                for (int k = 0; k < i; ++k) g += z(i, k) * z(k, j);
+                for (int k = 0; k < i; ++k) z(k, j) -= g * z(k, i);
+            }
+        d[i] = z(i, i);
+        z(i, i) = 1.0;
+        for (int j = 0; j < i; ++j) z(j, i) = z(i, j) = 0.0;
+    }
+    // implicit QL on (d, e), rotations applied to the columns of V
+    for (int i = 1; i < n; ++i) e[i - 1] = e[i];
+    e[n - 1] = 0.0;
+    for (int l = 0; l < n; ++l) {
+        int iter = 0, m;
+        do {
+            for (m = l; m < n - 1; ++m) {
+                const double dd = std::fabs(d[m]) + std::fabs(d[m + 1]);
+                if (std::fabs(e[m]) <= 2.220446049250313e-16 * dd) break;
+            }
+            if (m != l) {
+                if (++iter > 120) return false;
+                double g = (d[l + 1] - d[l]) / (2.0 * e[l]);
+                double r = std::hypot(g, 1.0);
+                g = d[m] - d[l] + e[l] / (g + (g >= 0.0 ? std::fabs(r) : -std::fabs(r)));
+                double s = 1.0, c = 1.0, p = 0.0;
+                int i;
+                for (i = m - 1; i >= l; --i) {
+                    double f = s * e[i];
+                    const double b = c * e[i];
+                    e[i + 1] = (r = std::hypot(f, g));
+                    if (r == 0.0) {
+                        d[i + 1] -= p;
+                        e[m] = 0.0;
+                        break;
+                    }
+                    s = f / r;
+                    c = g / r;
+                    g = d[i + 1] - p;
+                    r = (d[i] - g) * s + 2.0 * c * b;
+                    d[i + 1] = g + (p = s * r);
+                    g = c * r - b;
+                    for (int k = 0; k < n; ++k) {
+                        f = z(k, i + 1);
+                        z(k, i + 1) = s * z(k, i) + c * f;
+                        z(k, i) = c * z(k, i) - s * f;
+                    }
+                }
+                if (r == 0.0 && i >= l) continue;
+                d[l] -= p;
+                e[l] = g;
+                e[m] = 0.0;
+            }
+        } while (m != l);
+    }
+    w = d;
+    return true;
+}
+
+void jacobi_sym(int n, std::vector<double>& A, std::vector<double>& w, std::vector<double>& V) {
+    if (n > 48) {
+        std::vector<double> A2 = A;
+        if (tridiag_ql(n, A2, w, V)) return;
+    }
+    jacobi_small(n, A, w, V);
 }
 
 // general real matrix: Householder reduction to Hessenberg form + implicit double-shift QR with
@@ -233,7 +349,7 @@ bool eig_general(int nn, std::vector<double>& Hm, std::vector<double>& wr, std::
                 }
             }
             iter++;
-            if (++total > 3000) return false;
+            if (++total > 3000 + 60 * nn) return false;
             int m = n - 2;
             while (m >= l) {
                 z = H(m, m);
@@ -416,7 +532,8 @@ bool eig_general(int nn, std::vector<double>& Hm, std::vector<double>& wr, std::
 // device kernels on the Krylov basis (rows of length N)
 // =============================================================================================
 constexpr int DOT_CHUNK = 2048;
-constexpr int MAXV = 64;
+constexpr int MAXV = 64;        // basis rows the FUSED CGS kernel and the block-2 kernels handle (static buffers)
+constexpr int MAX_NCV = 256;    // largest Krylov basis: Nmax = 100 (lantern-demo.ipynb cells 2, 4) needs ncv = 204
 
 // partial[c*nvec + i] = sum over chunk c of Z_i[n] * u[n];  8 warps, warp w takes vectors w, w+8, ...
 __global__ void __launch_bounds__(256) k_dots_partial(const double* __restrict__ Z, int64_t ldz, int nvec,
@@ -464,8 +581,8 @@ __global__ void __launch_bounds__(32) k_dots_reduce(const double* __restrict__ p
 // w -= sum_i h[i] V_i
 __global__ void __launch_bounds__(256) k_update(double* __restrict__ w, const double* __restrict__ V, int64_t ldv,
                                                 int nvec, const double* __restrict__ h, int64_t N) {
-    __shared__ double hs[MAXV];
-    if (threadIdx.x < nvec) hs[threadIdx.x] = h[threadIdx.x];
+    extern __shared__ double hs[];             // [nvec]
+    for (int i = threadIdx.x; i < nvec; i += blockDim.x) hs[i] = h[i];
     __syncthreads();
     const int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (n >= N) return;
@@ -631,26 +748,68 @@ __global__ void k_random(double* __restrict__ v, int64_t N, uint64_t seed) {
 
 // in-place basis rotation (K10): rows 0..k-1 <- Q^T rows 0..m-1, per column of the basis;
 // row k <- row m (the residual direction).  Q is m x k row-major in device memory.
-__global__ void __launch_bounds__(128) k_rotate(double* __restrict__ V, int64_t ldv, int m, int k,
-                                                const double* __restrict__ Q, int64_t N, int move_residual,
-                                                double* __restrict__ out, int64_t ldo) {
-    extern __shared__ double qs[];
-    for (int i = threadIdx.x; i < m * k; i += blockDim.x) qs[i] = Q[i];
-    __syncthreads();
-    const int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (n >= N) return;
-    double col[MAXV];
-#pragma unroll 4
-    for (int j = 0; j < m; ++j) col[j] = V[(size_t)j * ldv + n];
-    const double res = move_residual ? V[(size_t)m * ldv + n] : 0.0;
+//
+// Wide bases (m > 32; Nmax = 80 / 100 of lantern-demo.ipynb gives m = 164 / 204): the rotation is a GEMM
+// (k x m) (m x N) with 2 m k / (8 (m + k)) flop per byte -- 21 flop/B at m = 204, k = 150, above the fp64
+// ridge of the B200 (~5.6 flop/B) -- so it runs on the fp64 tensor pipe (DMMA m8n8k4; tcgen05 has no fp64
+// kind).  A CTA stages RT_TN columns of ALL m basis rows in shared memory (which is what makes the
+// rotation safe in place: the tile is complete before its first row is overwritten), streams Q in slabs
+// of RT_QC output rows and accumulates 2 x 2 MMA tiles per warp (8 warps = 2 x 4 over a 32 x 64 slab).
+constexpr int RT_TN = 64, RT_VS = RT_TN + 4, RT_QC = 32, RT_QS = RT_QC + 4;
+static size_t rotate_mma_smem(int m) { return (size_t)((m + 3) & ~3) * (RT_VS + RT_QS) * sizeof(double); }
+__global__ void __launch_bounds__(256) k_rotate_mma(double* __restrict__ V, int64_t ldv, int m, int k,
+                                                    const double* __restrict__ Q, int64_t N, int move_residual,
+                                                    double* __restrict__ out, int64_t ldo) {
+    extern __shared__ double rsm[];
+    const int mp = (m + 3) & ~3;
+    double* Vs = rsm;                          // [mp][RT_VS]  basis tile, row j = basis vector j
+    double* Qs = rsm + (size_t)mp * RT_VS;     // [mp][RT_QS]  Q slab: Qs[j][ii] = Q[j][i0 + ii]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, tq = lane & 3;
+    const int64_t n0 = (int64_t)blockIdx.x * RT_TN;
+    const int len = (int)min((int64_t)RT_TN, N - n0);
+    for (int j = warp; j < mp; j += 8) {
+        const double* src = V + (size_t)j * ldv + n0;
+#pragma unroll
+        for (int c = lane; c < RT_TN; c += 32) Vs[j * RT_VS + c] = (j < m && c < len) ? src[c] : 0.0;
+    }
+    double res = 0.0;
+    if (move_residual && tid < len) res = V[(size_t)m * ldv + n0 + tid];
+    const int wm = warp & 1, wn = warp >> 1;
     double* dst = out ? out : V;
     const int64_t ldd = out ? ldo : ldv;
-    for (int i = 0; i < k; ++i) {
-        double s = 0.0;
-        for (int j = 0; j < m; ++j) s += qs[j * k + i] * col[j];
-        dst[(size_t)i * ldd + n] = s;
+    for (int i0 = 0; i0 < k; i0 += RT_QC) {
+        __syncthreads();                       // tile staged (first slab) / previous slab consumed
+        for (int idx = tid; idx < mp * RT_QC; idx += 256) {
+            const int j = idx >> 5, ii = idx & 31;
+            Qs[j * RT_QS + ii] = (j < m && i0 + ii < k) ? Q[(size_t)j * k + i0 + ii] : 0.0;
+        }
+        __syncthreads();
+        double acc[2][2][2];
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+            for (int b = 0; b < 2; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+        const double* qa = Qs + tq * RT_QS + wm * 16 + g;
+        const double* vb = Vs + tq * RT_VS + wn * 16 + g;
+#pragma unroll 4
+        for (int j0 = 0; j0 < mp; j0 += 4, qa += 4 * RT_QS, vb += 4 * RT_VS) {
+            const double a0 = qa[0], a1 = qa[8], b0 = vb[0], b1 = vb[8];
+            dmma8x8x4(acc[0][0][0], acc[0][0][1], a0, b0);
+            dmma8x8x4(acc[0][1][0], acc[0][1][1], a0, b1);
+            dmma8x8x4(acc[1][0][0], acc[1][0][1], a1, b0);
+            dmma8x8x4(acc[1][1][0], acc[1][1][1], a1, b1);
+        }
+#pragma unroll
+        for (int mb = 0; mb < 2; ++mb)
+#pragma unroll
+            for (int nb = 0; nb < 2; ++nb)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int row = i0 + wm * 16 + mb * 8 + g, col = wn * 16 + nb * 8 + 2 * tq + e;
+                    if (row < k && col < len) dst[(size_t)row * ldd + n0 + col] = acc[mb][nb][e];
+                }
     }
-    if (move_residual) V[(size_t)k * ldv + n] = res;
+    if (move_residual && tid < len) V[(size_t)k * ldv + n0 + tid] = res;
 }
 
 // the same rotation with the basis column held in REGISTERS (MM >= m, fully unrolled, statically
@@ -688,7 +847,11 @@ static void launch_rotate(double* V, int64_t ldv, int m, int k, const double* Q,
     const int grid = ceil_div(N, 128);
     if (m <= 24) k_rotate_t<24><<<grid, 128, sh, st>>>(V, ldv, m, k, Q, N, move_residual, out, ldo);
     else if (m <= 32) k_rotate_t<32><<<grid, 128, sh, st>>>(V, ldv, m, k, Q, N, move_residual, out, ldo);
-    else k_rotate<<<grid, 128, sh, st>>>(V, ldv, m, k, Q, N, move_residual, out, ldo);
+    else {
+        static PerDeviceOnce configure;
+        configure([] { WS_CUDA(cudaFuncSetAttribute(k_rotate_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rotate_mma_smem(MAX_NCV))); });
+        k_rotate_mma<<<ceil_div(N, RT_TN), 256, rotate_mma_smem(m), st>>>(V, ldv, m, k, Q, N, move_residual, out, ldo);
+    }
 }
 
 __global__ void k_scale_rows(double* __restrict__ X, int64_t ld, int nrows, const double* __restrict__ nrm2, int64_t N) {
@@ -780,7 +943,7 @@ static void eig_solve_block2(const ws_pattern* p, ws_solver* s, const double* B_
     auto orth_into = [&](cudaStream_t q, double* wv, int nvec, int slot, double* Hcol) {
         for (int pass = 0; pass < 2 && nvec > 0; ++pass) {
             dots(W, q, V, nvec, wv, W.h.get(), Hcol);
-            k_update<<<nb, T, 0, q>>>(wv, V, N, nvec, W.h.get(), N);
+            k_update<<<nb, T, (size_t)nvec * sizeof(double), q>>>(wv, V, N, nvec, W.h.get(), N);
             count_launch(1);
         }
         dots(W, q, wv, 1, wv, W.nrm.get(), nullptr);
@@ -807,7 +970,7 @@ static void eig_solve_block2(const ws_pattern* p, ws_solver* s, const double* B_
         count_launch(1);
         for (int pass = 0; pass < 2; ++pass) {
             dots(W, q, V + (size_t)(j + 2) * N, 1, w1, W.h.get(), H1 + (j + 2));
-            k_update<<<nb, T, 0, q>>>(w1, V + (size_t)(j + 2) * N, N, 1, W.h.get(), N);
+            k_update<<<nb, T, sizeof(double), q>>>(w1, V + (size_t)(j + 2) * N, N, 1, W.h.get(), N);
             count_launch(1);
         }
         dots(W, q, w1, 1, w1, W.nrm.get(), nullptr);
@@ -1048,9 +1211,11 @@ int ws_eig_solve(const ws_pattern* p, ws_solver* s, const double* B_vals, double
     // scipy's default is ncv = max(2k+1, 20) (arpack.py); with the convergence test at tol = eps that
     // size sits on a cliff for these problems (86 or 97 operator applications for k = 10 depending on
     // rounding noise), three more vectors make it 80 for every mesh tried (tools/ncv_sweep.py)
-    if (ncv <= 0) ncv = std::max(2 * nev + 4, 20);
+    // Wide bases: the reference's own calls go up to Nmax = 100 (lantern-demo.ipynb cell 2; cell 4 sweeps with
+    // Nmax = 80), i.e. ncv = 204; beyond MAX_NCV the default is clamped (fewer spare directions, more restarts).
+    if (ncv <= 0) ncv = std::min(std::max(2 * nev + 4, 20), std::max(MAX_NCV, nev + 2));
     ncv = (int)std::min<int64_t>(ncv, N);
-    WS_REQUIRE(ncv > nev + 1 && ncv < MAXV, "nev+1 < ncv < 64");
+    WS_REQUIRE(ncv > nev + 1 && ncv <= MAX_NCV, "nev+1 < ncv <= 256 (Nmax <= 254)");
     WS_REQUIRE(kind == 0 || (edges && xy), "the vector eigensolver needs the edge table and coordinates");
     if (tol <= 0) tol = 2.220446049250313e-16;          // ARPACK: tol=0 -> machine epsilon
     if (maxit <= 0) maxit = 300;
@@ -1065,6 +1230,7 @@ int ws_eig_solve(const ws_pattern* p, ws_solver* s, const double* B_vals, double
         if (kind == 1 && (block == 2 || want_block) && N > 4 * ncv) {
             int mb = ncv + (ncv & 1);
             if (mb + 2 >= MAXV) mb -= 2;
+            WS_REQUIRE(mb + 2 < MAXV && mb > nev + 1, "the block-2 iteration (kind 2) handles bases below 62 vectors (Nmax <= 28)");
             eig_solve_block2(p, s, B_vals, sigma, nev, mb, tol, maxit, seed, edges, xy, Ntt, w_out, V_out, h_info, h_resid,
                              device, st);
             return WS_OK;
@@ -1077,11 +1243,11 @@ int ws_eig_solve(const ws_pattern* p, ws_solver* s, const double* B_vals, double
     W.V.alloc((size_t)(m + 1) * N, st);
     if (kind == 0) W.Z.alloc((size_t)(m + 1) * N, st);
     W.w.alloc(N, st); W.t1.alloc(N, st); W.t2.alloc(N, st); W.t3.alloc(N, st);
-    W.partial.alloc((size_t)W.nchunks * MAXV, st);
-    W.h.alloc(MAXV, st);
+    W.partial.alloc((size_t)W.nchunks * (m + 1), st);
+    W.h.alloc(m + 1, st);
     W.Hd.alloc((size_t)(m + 1) * m, st);
-    W.nrm.alloc(MAXV, st);
-    W.Q.alloc((size_t)MAXV * MAXV, st);
+    W.nrm.alloc(m + 1, st);
+    W.Q.alloc((size_t)m * m, st);
     double* V = W.V.get();
     double* Z = kind == 0 ? W.Z.get() : V;
     const int T = 256;
@@ -1127,19 +1293,19 @@ int ws_eig_solve(const ws_pattern* p, ws_solver* s, const double* B_vals, double
         apply_op(q, j);
         double* Hcol = W.Hd.get() + (size_t)j * (m + 1);
         const int nv = j + 1;
-        if (kind == 1 && fuse_cgs) {
+        if (kind == 1 && fuse_cgs && nv + 1 <= MAXV) {
             // Euclidean inner product (dual basis = basis): the update of pass 1 and the inner products
             // of pass 2 share one pass over the basis -- three basis reads per step instead of four
             dots(W, q, V, nv, W.w.get(), W.h.get(), Hcol);
             k_update_dots<<<W.nchunks, 256, (size_t)(nv + 1) * UD_TILE * sizeof(double), q>>>(W.w.get(), V, N, nv, W.h.get(), N,
                                                                                          W.partial.get());
             k_dots_reduce<<<nv, 32, 0, q>>>(W.partial.get(), W.nchunks, nv, W.h.get(), Hcol);
-            k_update<<<nb, T, 0, q>>>(W.w.get(), V, N, nv, W.h.get(), N);
+            k_update<<<nb, T, (size_t)nv * sizeof(double), q>>>(W.w.get(), V, N, nv, W.h.get(), N);
             count_launch(3);
         } else {
             for (int pass = 0; pass < 2; ++pass) {
                 dots(W, q, Z, nv, W.w.get(), W.h.get(), Hcol);
-                k_update<<<nb, T, 0, q>>>(W.w.get(), V, N, nv, W.h.get(), N);
+                k_update<<<nb, T, (size_t)nv * sizeof(double), q>>>(W.w.get(), V, N, nv, W.h.get(), N);
                 count_launch(1);
             }
         }
@@ -1411,6 +1577,54 @@ int ws_eig_solve(const ws_pattern* p, ws_solver* s, const double* B_vals, double
     {
         int rc = ws_solver_check(s, device, (void*)st);
         if (rc) throw Error(rc, ws_last_error());
+    }
+    // ---- true residuals of the returned pairs, || OP x - theta x || / (|theta| ||x||), with OP applied through
+    // the (refined) solves.  The Ritz estimates above are statements about the operator the iteration saw; when
+    // the factorisation needed static pivots or refinement (interior shifts) the returned pairs are re-checked
+    // against a fresh application, and the call fails rather than return pairs that miss 1e-9.
+    // WS_EIG_VERIFY=1 / 0 forces / disables the check.
+    {
+        int64_t qi[4] = {0, 0, 0, 0};
+        double qd[4];
+        ws_solver_quality(s, qi, qd);
+        static const int verify_env = getenv("WS_EIG_VERIFY") ? atoi(getenv("WS_EIG_VERIFY")) : -1;
+        const bool verify = verify_env >= 0 ? verify_env != 0 : (qi[0] > 0 || qi[1] > 0);
+        if (verify && nconv >= nev) {
+            DevBuf<double> vr((size_t)3 * nev, st);
+            std::vector<double> th(nev), back((size_t)3 * nev, 0.0);
+            for (int i = 0; i < nev; ++i) th[i] = 1.0 / (wh[i] - sigma);
+            WS_CUDA(cudaMemcpyAsync(vr.get(), th.data(), nev * sizeof(double), cudaMemcpyHostToDevice, st));
+            for (int i = 0; i < nev; ++i) {
+                const double* xi = V_out + (size_t)i * N;
+                spmv_launch(p, B_vals, xi, W.t1.get(), st);
+                if (kind == 0) {
+                    solve(st, W.t1.get(), W.w.get());
+                } else {
+                    vecT(st, 1, W.t1.get(), W.t2.get());
+                    solve(st, W.t2.get(), W.t3.get());
+                    vecT(st, 0, W.t3.get(), W.w.get());
+                }
+                k_update<<<nb, T, sizeof(double), st>>>(W.w.get(), xi, N, 1, vr.get() + i, N);
+                count_launch(1);
+                dots(W, st, W.w.get(), 1, W.w.get(), vr.get() + nev + i, nullptr);
+                dots(W, st, xi, 1, xi, vr.get() + 2 * nev + i, nullptr);
+            }
+            WS_CUDA(cudaMemcpyAsync(back.data(), vr.get(), back.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
+            WS_CUDA(cudaStreamSynchronize(st));
+            double worst = 0.0;
+            int worst_i = -1;
+            for (int i = 0; i < nev; ++i) {
+                if (lam_i[ord2[i]] != 0.0) continue;           // complex pair: only the real part is returned
+                const double r = std::sqrt(back[nev + i] / back[2 * nev + i]) / std::fabs(th[i]);
+                if (!(r <= worst)) { worst = r; worst_i = i; }
+            }
+            if (getenv("WS_TRACE"))
+                fprintf(stderr, "[ws_eig verify] worst true residual %.3e (pair %d), solver: %lld perturbed pivots, %lld refinement steps\n",
+                        worst, worst_i, (long long)qi[0], (long long)qi[1]);
+            if (!(worst <= 1e-9))
+                throw Error(WS_ERR_NUMERIC, "eigenpair " + std::to_string(worst_i) + " fails the residual check against the operator (" +
+                                                std::to_string(worst) + "): the factorisation at this shift is not accurate enough");
+        }
     }
     if (etrace) {
         cudaStreamSynchronize(st);

@@ -68,7 +68,9 @@ struct ws_solver {
     ws::DevBuf<ws::FrontRec> recs;
     ws::DevBuf<int32_t> wsrc0, wsrc1;       // gather maps of the forward sweep
     ws::DevBuf<int32_t> sflags;             // per-front completion counters of the two sweeps [2 * nfronts]
-    ws::DevBuf<unsigned long long> stats;   // [0] negative pivots [1] zero/NaN pivots [2] min |pivot| bits [3] max |pivot| bits
+    // [0] negative pivots [1] NaN/Inf pivots [2] min |pivot| bits [3] max |pivot| bits [4] perturbed pivots
+    // [5] max |M_ij| bits (k_scatter: the scale of the static-pivot threshold) [6..8] probe norms |r|, |x|, |b| (bits)
+    ws::DevBuf<unsigned long long> stats;
     // tasks
     ws::DevBuf<ws::GemmTask> gemm_tasks;
     ws::DevBuf<ws::PanelTask> panel_tasks;
@@ -91,6 +93,16 @@ struct ws_solver {
     int64_t h_neg = 0, h_bad = 0;
     double h_minpiv = 0, h_maxpiv = 0;
     int64_t bytes = 0;
+    // accuracy guard (static pivoting + probe + iterative refinement, see ws_solver_factor)
+    const ws_pattern* pat = nullptr;        // the pattern M lives on (outlives the solver)
+    const double* fA = nullptr;             // value arrays of the last factorisation (caller keeps them alive
+    const double* fB = nullptr;             // while refined solves run: M x = fA x - fsigma fB x)
+    double fsigma = 0.0;
+    int refine_steps = 0;                   // refinement steps every solve performs (0: the factorisation passed the probe as is)
+    int64_t h_pert = 0;                     // pivots replaced by +-tau
+    int probe_iters = 0;
+    double h_eta0 = 0.0, h_eta = 0.0, h_maxabs = 0.0;   // probe backward error before / after refinement; max |M_ij|
+    ws::DevBuf<double> rf_b, rf_r, rf_y, rf_dx, rf_x;
 };
 
 namespace ws {
@@ -98,10 +110,19 @@ namespace ws {
 // ---------------------------------------------------------------------------------------------
 // kernels
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void dmma8x8x4(double& c0, double& c1, double a, double b) {
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-                 : "+d"(c0), "+d"(c1)
-                 : "d"(a), "d"(b));
+constexpr int NSTATS = 12;
+// static pivoting: |pivot| < PIV_REL * max|M_ij| is replaced by +-that (a diagonal backward error of 1e-10 relative;
+// growth bounded by 1e10, which two refinement steps absorb); counted in stats[4]
+constexpr double PIV_REL = 1e-10;
+__device__ __forceinline__ double pivot_tau(const unsigned long long* stats) {
+    return PIV_REL * __longlong_as_double((long long)stats[5]);
+}
+__device__ __forceinline__ double guard_pivot(double pv, double tau, unsigned long long* stats) {
+    if (fabs(pv) < tau) {
+        pv = copysign(tau, pv);
+        atomicAdd(&stats[4], 1ull);
+    }
+    return pv;
 }
 
 constexpr int KC = 16;
@@ -251,12 +272,17 @@ __global__ void __launch_bounds__(PANEL_ROWS) k_panel(const PanelTask* __restric
         // warp 0: lane r holds row r of the (symmetric) block in registers; column c is eliminated
         // with shuffles: A[r][c2] -= (A[r][c] / A[c][c]) * A[c][c2]  for r, c2 > c.
         const int lane = tid;
+        const double tau = pivot_tau(stats);
         double row[NB];
 #pragma unroll
         for (int c = 0; c < NB; ++c) row[c] = (lane >= c) ? Dg[lane][c] : Dg[c][lane];
 #pragma unroll
         for (int c = 0; c < NB; ++c) {
-            const double dc = __shfl_sync(0xffffffffu, row[c], c);
+            double dc = __shfl_sync(0xffffffffu, row[c], c);
+            if (c < t.nb && fabs(dc) < tau) {          // static pivot (uniform across the warp and across the CTAs of this block column)
+                dc = copysign(tau, dc);
+                if (lane == c && t.write_diag) atomicAdd(&stats[4], 1ull);
+            }
             const bool act = lane > c;
             const double lr = act ? row[c] / dc : 0.0;
 #pragma unroll
@@ -383,13 +409,69 @@ __global__ void k_dest_map(int64_t N, const int32_t* __restrict__ rowptr, const 
 }
 
 __global__ void k_scatter(int64_t nnz, const int64_t* __restrict__ dest, const double* __restrict__ A,
-                          const double* __restrict__ B, double sigma, double* __restrict__ L) {
+                          const double* __restrict__ B, double sigma, double* __restrict__ L,
+                          unsigned long long* __restrict__ stats) {
     int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    double mx = 0.0;
     for (; s < nnz; s += stride) {
         const int64_t dst = dest[s];
-        if (dst >= 0) L[dst] = B ? A[s] - sigma * B[s] : A[s];
+        if (dst >= 0) {
+            const double v = B ? A[s] - sigma * B[s] : A[s];
+            L[dst] = v;
+            mx = fmax(mx, fabs(v));                 // (NaN entries drop out here and surface as bad pivots)
+        }
     }
+    // max |M_ij|: non-negative doubles order like their bit patterns
+    unsigned long long b = (unsigned long long)__double_as_longlong(mx);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) b = max(b, __shfl_xor_sync(0xffffffffu, b, o));
+    if ((threadIdx.x & 31) == 0 && b) atomicMax(&stats[5], b);
+}
+
+// ---- accuracy guard: probe right-hand side, residual, correction -------------------------------
+__global__ void k_probe_rhs(int64_t N, double* __restrict__ b) {
+    const int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    uint64_t z = 0x2545F4914F6CDD1Dull + 0x9E3779B97F4A7C15ull * (uint64_t)(n + 1);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    b[n] = ((double)(z >> 11) * (1.0 / 9007199254740992.0)) * 2.0 - 1.0;
+}
+// r = b - (ya - sigma * yb)   (ya = A x, yb = B x or nullptr); when nrm != nullptr also max |r|, |x|, |b| -> nrm[0..2]
+__global__ void __launch_bounds__(256) k_residual(int64_t N, const double* __restrict__ b, const double* __restrict__ ya,
+                                                  const double* __restrict__ yb, double sigma, const double* __restrict__ x,
+                                                  double* __restrict__ r, unsigned long long* __restrict__ nrm) {
+    const int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    double rv = 0.0, xv = 0.0, bv = 0.0;
+    if (n < N) {
+        bv = b[n];
+        xv = x[n];
+        rv = bv - (yb ? ya[n] - sigma * yb[n] : ya[n]);
+        r[n] = rv;
+    }
+    if (nrm) {
+        // NaN -> +inf so that a broken solve can never look accurate
+        unsigned long long m0 = (unsigned long long)__double_as_longlong(rv == rv ? fabs(rv) : __longlong_as_double(0x7ff0000000000000ll));
+        unsigned long long m1 = (unsigned long long)__double_as_longlong(xv == xv ? fabs(xv) : __longlong_as_double(0x7ff0000000000000ll));
+        unsigned long long m2 = (unsigned long long)__double_as_longlong(fabs(bv));
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            m0 = max(m0, __shfl_xor_sync(0xffffffffu, m0, o));
+            m1 = max(m1, __shfl_xor_sync(0xffffffffu, m1, o));
+            m2 = max(m2, __shfl_xor_sync(0xffffffffu, m2, o));
+        }
+        if ((threadIdx.x & 31) == 0) {
+            if (m0) atomicMax(&nrm[0], m0);
+            if (m1) atomicMax(&nrm[1], m1);
+            if (m2) atomicMax(&nrm[2], m2);
+        }
+    }
+}
+__global__ void k_add_inplace(int64_t N, double* __restrict__ x, const double* __restrict__ dx) {
+    const int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (n < N) x[n] += dx[n];
 }
 
 // child update matrix (lower triangle of U_c) added into the parent's panel / update matrix.
@@ -499,6 +581,7 @@ __global__ void k_front_fused(int64_t first, int has_children, FusedCtx cx) {
     // row k+1 has the shortest update of step k, so it also inverts the next pivot while the others
     // finish: the division is off the critical path and rows are scaled by multiplication.
     double* rd = rb;
+    const double tau = pivot_tau(cx.stats);
     if constexpr (PMAX > 0) {
         // wide pivot blocks (leaf fronts): the row lives in REGISTERS (PMAX columns, statically
         // indexed: the k and j loops are fully unrolled), so one update is one DFMA plus half a
@@ -507,7 +590,10 @@ __global__ void k_front_fused(int64_t first, int has_children, FusedCtx cx) {
         double row[PMAX > 0 ? PMAX : 1];
 #pragma unroll
         for (int j = 0; j < PMAX; ++j) row[j] = (tid < m && j < p) ? P[tid + j * ld] : 0.0;
-        if (tid == 0 && p > 0) rd[0] = 1.0 / row[0];
+        if (tid == 0 && p > 0) {
+            row[0] = guard_pivot(row[0], tau, cx.stats);
+            rd[0] = 1.0 / row[0];
+        }
 #pragma unroll
         for (int k = 0; k < PMAX; ++k) {
             if (k >= p) break;
@@ -533,7 +619,10 @@ __global__ void k_front_fused(int64_t first, int has_children, FusedCtx cx) {
                         if (c * 8 + 7 > k) row[c * 8 + 7] -= li * v3.y;
                     }
                 }
-                if (k + 1 < PMAX && tid == k + 1 && tid < p) rd[k + 1] = 1.0 / row[k + 1 < PMAX ? k + 1 : 0];
+                if (k + 1 < PMAX && tid == k + 1 && tid < p) {
+                    row[k + 1 < PMAX ? k + 1 : 0] = guard_pivot(row[k + 1 < PMAX ? k + 1 : 0], tau, cx.stats);
+                    rd[k + 1] = 1.0 / row[k + 1 < PMAX ? k + 1 : 0];
+                }
             }
         }
         __syncthreads();
@@ -543,7 +632,10 @@ __global__ void k_front_fused(int64_t first, int has_children, FusedCtx cx) {
     } else {
         // narrow pivot blocks (separator fronts): the panel stays in shared memory -- fewer registers,
         // more resident CTAs, no work on columns that do not exist
-        if (tid == 0 && p > 0) rd[0] = 1.0 / P[0];
+        if (tid == 0 && p > 0) {
+            P[0] = guard_pivot(P[0], tau, cx.stats);
+            rd[0] = 1.0 / P[0];
+        }
         for (int k = 0; k < p; ++k) {
             double* buf = vb + (k & 1) * pe;
             if (tid >= k && tid < p) buf[tid] = P[tid + k * ld];
@@ -566,7 +658,10 @@ __global__ void k_front_fused(int64_t first, int has_children, FusedCtx cx) {
                     pr[3 * ld] = a3 - li * b3;
                 }
                 for (; j <= jmax; ++j, pr += ld) *pr -= li * bj[j];
-                if (tid == k + 1 && tid < p) rd[tid] = 1.0 / P[tid + tid * ld];
+                if (tid == k + 1 && tid < p) {
+                    P[tid + tid * ld] = guard_pivot(P[tid + tid * ld], tau, cx.stats);
+                    rd[tid] = 1.0 / P[tid + tid * ld];
+                }
             }
         }
     }
@@ -1667,6 +1762,23 @@ static void sweep_launches(ws_solver* s, const double* bi, double* xi, cudaStrea
     count_launch(nl);
 }
 
+static void configure_sweeps() {
+    static PerDeviceOnce configure;
+    configure([] {
+        const int big = 200 * 1024;
+        WS_CUDA(cudaFuncSetAttribute(k_fwd_tile<8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+        WS_CUDA(cudaFuncSetAttribute(k_fwd_tile<32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+        WS_CUDA(cudaFuncSetAttribute(k_bwd_tile<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+        WS_CUDA(cudaFuncSetAttribute(k_bwd_tile<4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+        WS_CUDA(cudaFuncSetAttribute(k_fwd_tile<8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+        WS_CUDA(cudaFuncSetAttribute(k_fwd_tile<32, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+        WS_CUDA(cudaFuncSetAttribute(k_bwd_tile<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+        WS_CUDA(cudaFuncSetAttribute(k_bwd_tile<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    });
+}
+
+void spmv_launch(const ws_pattern* p, const double* vals, const double* x, double* y, cudaStream_t st);
+
 }  // namespace ws
 
 using namespace ws;
@@ -1762,14 +1874,15 @@ int ws_solver_create(const ws_pattern* p, const ws_symbolic* sym, ws_solver** ou
                 count_launch(1);
             }
         }
-        s->stats.alloc(4, st);
+        s->stats.alloc(NSTATS, st);
+        s->pat = p;
         s->dest.alloc(p->nnz, st);
         s->bytes = (3 * Y.Ltotal + Y.Utotal + 2 * Y.Wtotal + 4 * Y.N) * 8 + p->nnz * 8;
         const double tc1 = tnow();
         const int T = 128;
         k_dest_map<<<ceil_div(Y.N, T), T, 0, st>>>(Y.N, p->rowptr.get(), p->colidx.get(), s->iperm.get(),
                                                      s->node_of_new.get(), view(s), s->dest.get());
-        WS_CUDA(cudaMemsetAsync(s->stats.get(), 0, 4 * sizeof(unsigned long long), st));
+        WS_CUDA(cudaMemsetAsync(s->stats.get(), 0, NSTATS * sizeof(unsigned long long), st));
         k_count_bad_dest<<<ceil_div(p->nnz, 256), 256, 0, st>>>(p->nnz, s->dest.get(), s->stats.get());
         unsigned long long bad = 0;
         WS_CUDA(cudaMemcpyAsync(&bad, s->stats.get(), sizeof bad, cudaMemcpyDeviceToHost, st));
@@ -1797,14 +1910,19 @@ int ws_solver_factor(ws_solver* s, const double* A_vals, const double* B_vals, d
     cudaStream_t st = (cudaStream_t)stream;
     const Symbolic& Y = s->sym;
     s->factored = false;
+    configure_sweeps();
     WS_CUDA(cudaMemsetAsync(s->L.get(), 0, s->L.bytes(), st));
     WS_CUDA(cudaMemsetAsync(s->U.get(), 0, s->U.bytes(), st));
     WS_CUDA(cudaMemsetAsync(s->S.get(), 0, s->S.bytes(), st));   // blocks above the block diagonal are read as zeros
-    unsigned long long init[4] = {0ull, 0ull, ~0ull, 0ull};
+    s->refine_steps = 0;
+    s->fA = A_vals;
+    s->fB = B_vals;
+    s->fsigma = sigma;
+    unsigned long long init[NSTATS] = {0ull, 0ull, ~0ull, 0ull};
     WS_CUDA(cudaMemcpyAsync(s->stats.get(), init, sizeof init, cudaMemcpyHostToDevice, st));
     {
         int blocks = (int)std::min<int64_t>((s->nnz + 255) / 256, (int64_t)kNumSMs * 32);
-        k_scatter<<<blocks, 256, 0, st>>>(s->nnz, s->dest.get(), A_vals, B_vals, sigma, s->L.get());
+        k_scatter<<<blocks, 256, 0, st>>>(s->nnz, s->dest.get(), A_vals, B_vals, sigma, s->L.get(), s->stats.get());
         count_launch(1);
     }
     FrontView fv = view(s);
@@ -1856,20 +1974,120 @@ int ws_solver_factor(ws_solver* s, const double* A_vals, const double* B_vals, d
     launch_gemm(s, s->w21, false, st);
     k_recip<<<ceil_div(s->N, 256), 256, 0, st>>>(s->N, s->d.get(), s->dinv.get());
     count_launch(1);
-    unsigned long long h[4];
+    // ---- accuracy guard -------------------------------------------------------------------------------
+    // The factorisation does not pivot.  That is backward stable for the definite scalar matrix at the default
+    // shift and, in practice, for the quasi-definite vector matrix; with target_neff the shift sits inside the
+    // spectrum (fe_solver.py:313-316; getting-started.ipynb cell 26 uses target_neff = 0.995 under every index
+    // of the fibre) and A - sigma B is genuinely indefinite.  So every factorisation is CHECKED instead of
+    // trusted: tiny pivots are replaced by +-tau (above), then a probe system M x = b is solved with the new
+    // factors and its normwise backward error eta = |b - M x| / (max|M| |x| + |b|) decides how many steps of
+    // iterative refinement every later solve performs (0 when the factors pass as they are -- the default-shift
+    // cost of the guard is this one solve + one SpMV).  If refinement cannot bring eta below ETA_FAIL the call
+    // fails with WS_ERR_NUMERIC: degraded eigenpairs are never returned silently.
+    static const bool guard = !(getenv("WS_NO_GUARD") && atoi(getenv("WS_NO_GUARD")));
+    constexpr double ETA_OK = 1e-13, ETA_FAIL = 1e-11;
+    constexpr int MAX_REFINE = 5;
+    s->factored = true;                       // the probe goes through the regular sweeps
+    const int T = 256;
+    const int nbN = ceil_div(s->N, T);
+    auto probe_pass = [&](bool first) {
+        // residual of the current iterate rf_x against rf_b, norms -> stats[6..8]
+        spmv_launch(s->pat, s->fA, s->rf_x.get(), s->rf_y.get(), st);
+        const double* yb = nullptr;
+        if (s->fB) {
+            spmv_launch(s->pat, s->fB, s->rf_x.get(), s->rf_dx.get(), st);
+            yb = s->rf_dx.get();
+        }
+        if (!first) WS_CUDA(cudaMemsetAsync(s->stats.get() + 6, 0, 3 * sizeof(unsigned long long), st));
+        k_residual<<<nbN, T, 0, st>>>(s->N, s->rf_b.get(), s->rf_y.get(), yb, s->fsigma, s->rf_x.get(), s->rf_r.get(),
+                                      s->stats.get() + 6);
+        count_launch(1);
+    };
+    if (guard && s->N > 0) {
+        if (!s->rf_b.get()) {
+            s->rf_b.alloc(s->N, st); s->rf_r.alloc(s->N, st); s->rf_y.alloc(s->N, st); s->rf_dx.alloc(s->N, st); s->rf_x.alloc(s->N, st);
+            s->bytes += 5 * s->N * 8;
+        }
+        k_probe_rhs<<<nbN, T, 0, st>>>(s->N, s->rf_b.get());
+        count_launch(1);
+        sweep_launches<1>(s, s->rf_b.get(), s->rf_x.get(), st);
+        probe_pass(true);
+    }
+    unsigned long long h[NSTATS];
     WS_CUDA(cudaMemcpyAsync(h, s->stats.get(), sizeof h, cudaMemcpyDeviceToHost, st));
     WS_CUDA(cudaStreamSynchronize(st));
     WS_CUDA(cudaGetLastError());
+    s->factored = false;
+    auto as_double = [](unsigned long long bits) { double d; std::memcpy(&d, &bits, 8); return d; };
     s->h_neg = (int64_t)h[0];
     s->h_bad = (int64_t)h[1];
-    long long mn = (long long)h[2], mx = (long long)h[3];
-    std::memcpy(&s->h_minpiv, &mn, 8);
-    std::memcpy(&s->h_maxpiv, &mx, 8);
-    if (h[2] == ~0ull) s->h_minpiv = 0.0;
+    s->h_minpiv = h[2] == ~0ull ? 0.0 : as_double(h[2]);
+    s->h_maxpiv = as_double(h[3]);
+    s->h_pert = (int64_t)h[4];
+    s->h_maxabs = as_double(h[5]);
+    s->probe_iters = 0;
+    s->h_eta0 = s->h_eta = 0.0;
     if (s->h_bad)
-        throw Error(WS_ERR_NUMERIC, "factorisation met " + std::to_string(s->h_bad) + " zero / non-finite pivots (matrix singular at this shift)");
+        throw Error(WS_ERR_NUMERIC, "factorisation met " + std::to_string(s->h_bad) + " non-finite pivots (matrix entries not finite?)");
+    if (guard && s->N > 0) {
+        auto eta_of = [&](const unsigned long long* hh) {
+            const double r = as_double(hh[6]), x = as_double(hh[7]), bb = as_double(hh[8]);
+            const double den = s->h_maxabs * x + bb;
+            return den > 0.0 && std::isfinite(r) && std::isfinite(x) ? r / den : INFINITY;
+        };
+        double eta = eta_of(h);
+        s->h_eta0 = eta;
+        int steps = 0;
+        while (eta > ETA_OK && steps < MAX_REFINE) {
+            // one refinement step on the probe: x += M~^-1 (b - M x)
+            s->factored = true;
+            sweep_launches<1>(s, s->rf_r.get(), s->rf_y.get(), st);
+            s->factored = false;
+            k_add_inplace<<<nbN, T, 0, st>>>(s->N, s->rf_x.get(), s->rf_y.get());
+            count_launch(1);
+            probe_pass(false);
+            WS_CUDA(cudaMemcpyAsync(h, s->stats.get(), sizeof h, cudaMemcpyDeviceToHost, st));
+            WS_CUDA(cudaStreamSynchronize(st));
+            const double e2 = eta_of(h);
+            ++steps;
+            const bool stalled = !(e2 < 0.25 * eta);
+            eta = std::min(eta, e2);
+            if (stalled) break;
+        }
+        s->probe_iters = steps;
+        s->h_eta = eta;
+        if (getenv("WS_TRACE"))
+            fprintf(stderr, "[ws_solver_factor] guard: perturbed pivots %lld, max|M| %.3e, eta0 %.2e -> eta %.2e after %d refinement steps\n",
+                    (long long)s->h_pert, s->h_maxabs, s->h_eta0, eta, steps);
+        if (!(eta <= ETA_FAIL))
+            throw Error(WS_ERR_NUMERIC, "factorisation of A - sigma B is not accurate at this shift: probe backward error " +
+                                            std::to_string(eta) + " after " + std::to_string(steps) + " refinement steps, " +
+                                            std::to_string(s->h_pert) + " perturbed pivots (shift too close to an eigenvalue, or the "
+                                            "pivot-free LDL^T is unstable for this matrix)");
+        // one spare step when refinement was needed at all: other right-hand sides may converge a little slower
+        s->refine_steps = steps ? std::min(steps + 1, MAX_REFINE) : 0;
+    }
     s->factored = true;
     WS_API_END
+}
+
+// one refined solve: x = M~^-1 b, then `steps` times x += M~^-1 (b - M x) with M applied as SpMV on the pattern
+static void refined_solve(ws_solver* s, const double* b, double* x, cudaStream_t st) {
+    const int T = 256;
+    const int nbN = ceil_div(s->N, T);
+    sweep_launches<1>(s, b, x, st);
+    for (int it = 0; it < s->refine_steps; ++it) {
+        spmv_launch(s->pat, s->fA, x, s->rf_y.get(), st);
+        const double* yb = nullptr;
+        if (s->fB) {
+            spmv_launch(s->pat, s->fB, x, s->rf_dx.get(), st);
+            yb = s->rf_dx.get();
+        }
+        k_residual<<<nbN, T, 0, st>>>(s->N, b, s->rf_y.get(), yb, s->fsigma, x, s->rf_r.get(), nullptr);
+        sweep_launches<1>(s, s->rf_r.get(), s->rf_y.get(), st);
+        k_add_inplace<<<nbN, T, 0, st>>>(s->N, x, s->rf_y.get());
+        count_launch(2);
+    }
 }
 
 int ws_solver_solve(ws_solver* s, const double* b, double* x, int nrhs, int device, void* stream) {
@@ -1878,20 +2096,22 @@ int ws_solver_solve(ws_solver* s, const double* b, double* x, int nrhs, int devi
     if (!s->factored) throw Error(WS_ERR_STATE, "ws_solver_solve before a successful ws_solver_factor");
     DeviceGuard g(device);
     cudaStream_t st = (cudaStream_t)stream;
-    const Symbolic& Y = s->sym;
     // (b may alias x: b is read by the forward sweep only, x is written by the backward sweep only)
-    static PerDeviceOnce configure;
-    configure([] {
-        const int big = 200 * 1024;
-        WS_CUDA(cudaFuncSetAttribute(k_fwd_tile<8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-        WS_CUDA(cudaFuncSetAttribute(k_fwd_tile<32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-        WS_CUDA(cudaFuncSetAttribute(k_bwd_tile<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-        WS_CUDA(cudaFuncSetAttribute(k_bwd_tile<4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-        WS_CUDA(cudaFuncSetAttribute(k_fwd_tile<8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-        WS_CUDA(cudaFuncSetAttribute(k_fwd_tile<32, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-        WS_CUDA(cudaFuncSetAttribute(k_bwd_tile<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-        WS_CUDA(cudaFuncSetAttribute(k_bwd_tile<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-    });
+    configure_sweeps();
+    if (s->refine_steps > 0) {
+        // (refinement reads b again after x has been written: aliasing is resolved through a copy)
+        for (int rhs = 0; rhs < nrhs; ++rhs) {
+            const double* bi = b + (size_t)rhs * s->N;
+            double* xi = x + (size_t)rhs * s->N;
+            if (bi == xi) {
+                WS_CUDA(cudaMemcpyAsync(s->rf_b.get(), bi, s->N * sizeof(double), cudaMemcpyDeviceToDevice, st));
+                bi = s->rf_b.get();
+            }
+            refined_solve(s, bi, xi, st);
+        }
+        WS_CUDA(cudaGetLastError());
+        return WS_OK;
+    }
     int rhs = 0;
     for (; rhs + 2 <= nrhs; rhs += 2) sweep_launches<2>(s, b + (size_t)rhs * s->N, x + (size_t)rhs * s->N, st);
     for (; rhs < nrhs; ++rhs) sweep_launches<1>(s, b + (size_t)rhs * s->N, x + (size_t)rhs * s->N, st);
@@ -1926,6 +2146,18 @@ int ws_solver_stats(const ws_solver* s, int64_t* h_info, double* h_dinfo) {
     }
     if (h_dinfo) {
         h_dinfo[0] = s->sym.flops; h_dinfo[1] = s->h_minpiv; h_dinfo[2] = s->h_maxpiv;
+    }
+    WS_API_END
+}
+
+int ws_solver_quality(const ws_solver* s, int64_t* h_info, double* h_dinfo) {
+    WS_API_BEGIN
+    WS_REQUIRE(s, "solver == NULL");
+    if (h_info) {
+        h_info[0] = s->h_pert; h_info[1] = s->refine_steps; h_info[2] = s->probe_iters; h_info[3] = 0;
+    }
+    if (h_dinfo) {
+        h_dinfo[0] = s->h_eta0; h_dinfo[1] = s->h_eta; h_dinfo[2] = s->h_maxabs; h_dinfo[3] = PIV_REL * s->h_maxabs;
     }
     WS_API_END
 }

@@ -240,5 +240,46 @@ def lantern_cross_section(target_elements, n_cores=7, order=2, seed=0, jitter=0.
     return Mesh(pts, tris.astype(dtype), sets)
 
 
+def holey_fiber(target_elements, pitch=3.0, r_hole=1.0, rings=2, r_clad=9.0, order=2, seed=0, jitter=0.2,
+                hollow_core=False, dtype=np.int64):
+    """Air-hole fibre (in the spirit of ``PhotonicCrystalFiber`` / ``PhotonicBandgapFiber``, reference
+    waveguide.py:604-726 and getting-started.ipynb cells 15, 24): a silica disc with a hexagonal lattice of
+    ``rings`` rings of air holes (n = 1.0) around the centre; the centre site is solid silica (index-guiding
+    PCF) or, with ``hollow_core``, a larger air hole.  High index contrast and -- solved with ``target_neff``
+    inside the band -- a shift-invert matrix that is strongly indefinite: the stress test for the
+    factorisation's accuracy guard.  Labels: 'air', 'silica'."""
+    from scipy.spatial import Delaunay
+
+    rng = np.random.default_rng(seed)
+    centres = []
+    for i in range(-rings, rings + 1):
+        for j in range(-rings, rings + 1):
+            if max(abs(i), abs(j), abs(i + j)) <= rings and (i, j) != (0, 0):
+                centres.append((pitch * (i + 0.5 * j), pitch * (np.sqrt(3.0) / 2.0) * j))
+    hole_r = [(cx, cy, r_hole) for (cx, cy) in centres]
+    if hollow_core:
+        hole_r.append((0.0, 0.0, 1.4 * r_hole))
+    npts = max(64, target_elements // 2)
+    h = np.sqrt(np.pi * r_clad ** 2 / npts)
+    P = _disc_points(h, r_clad, rng, jitter, [(0.0, 0.0, r_clad)] + hole_r)
+    tri = Delaunay(P)
+    pts = np.zeros((P.shape[0], 3))
+    pts[:, :2] = P
+    tris = _ccw(pts, tri.simplices.astype(np.int64))
+    p = pts[:, :2]
+    a, b, c = p[tris[:, 0]], p[tris[:, 1]], p[tris[:, 2]]
+    J = (b[:, 0] - a[:, 0]) * (c[:, 1] - a[:, 1]) - (c[:, 0] - a[:, 0]) * (b[:, 1] - a[:, 1])
+    tris = tris[J > 1e-3 * h * h]
+    if order == 2:
+        pts, tris = _add_midside_nodes(pts, tris)
+    cen = pts[tris[:, :3], :2].mean(axis=1)
+    air = np.zeros(len(tris), dtype=bool)
+    for (cx, cy, r) in hole_r:
+        air |= (cen[:, 0] - cx) ** 2 + (cen[:, 1] - cy) ** 2 < r * r
+    sets = {"air": [None, np.nonzero(air)[0], None], "silica": [None, np.nonzero(~air)[0], None]}
+    return Mesh(pts, tris.astype(dtype), sets)
+
+
 FIBER_IOR = {"core": 1.444 + 8.8e-3, "cladding": 1.444}          # getting-started cell 9
+HOLEY_IOR = {"air": 1.0, "silica": 1.444}                         # getting-started cells 15 / 24
 LANTERN_IOR = {"core": 1.4521, "cladding": 1.44692, "jacket": 1.44692 - 5e-3}   # lantern-demo cell 1

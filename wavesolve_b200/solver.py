@@ -85,31 +85,6 @@ class Symbolic:
             pass
 
 
-class SymbolicFuture:
-    """Runs the host symbolic analysis in a worker thread (the C call releases the GIL) so that it
-    overlaps the device-side pattern build and assembly."""
-
-    def __init__(self, *args, **kw):
-        import threading
-        self._out = None
-        self._err = None
-
-        def work():
-            try:
-                self._out = Symbolic(*args, **kw)
-            except BaseException as e:      # re-raised in result()
-                self._err = e
-
-        self._th = threading.Thread(target=work, daemon=True)
-        self._th.start()
-
-    def result(self) -> Symbolic:
-        self._th.join()
-        if self._err is not None:
-            raise self._err
-        return self._out
-
-
 class Solver:
     """Device multifrontal LDL^T bound to a pattern and a symbolic analysis (``ws_solver``)."""
 
@@ -152,6 +127,12 @@ class Solver:
         keys = ("nnzL", "fronts", "maxfront", "bytes", "neg_pivots", "pos_pivots", "bad_pivots", "depth")
         out = {k: int(v) for k, v in zip(keys, info)}
         out.update(flops=float(dinfo[0]), min_pivot=float(dinfo[1]), max_pivot=float(dinfo[2]))
+        q = np.zeros(4, dtype=np.int64)
+        dq = np.zeros(4, dtype=np.float64)
+        _lib.check(_lib.lib().ws_solver_quality(self.handle, q.ctypes.data, dq.ctypes.data))
+        out.update(perturbed_pivots=int(q[0]), refine_steps=int(q[1]), probe_refinements=int(q[2]),
+                   backward_error_unrefined=float(dq[0]), backward_error=float(dq[1]), max_abs=float(dq[2]),
+                   pivot_threshold=float(dq[3]))
         return out
 
     def close(self):
