@@ -44,6 +44,13 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--elements", type=int, default=1_000_000)
     ap.add_argument("--cpu-sample-elements", type=int, default=80_000)
+    ap.add_argument("--ref-budget-s", type=float, default=float(os.environ.get("WS_REF_BUDGET_S", "1500")),
+                    help="--impl reference at N=1: the same-configuration CPU solve (the full --elements mesh, one timed "
+                         "step) runs when a calibration solve predicts it fits this many seconds; otherwise the largest "
+                         "size that does")
+    ap.add_argument("--cal-elements", type=int, default=0, help="size of the calibration solve (default 40k triangles)")
+    ap.add_argument("--sweep-problems", type=int, default=256, help="problems of the timed c5 sweep slice (0: skip)")
+    ap.add_argument("--sweep-elements", type=int, default=50_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--lite", action="store_true",
                     help="time the steps only: skip the kernel micro-measurements and the end-to-end pass "
@@ -144,6 +151,38 @@ def make_mesh(n_elements, seed=0):
 # ---------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the oracle port on the host cores
 # ---------------------------------------------------------------------------------------------
+def host_info():
+    """Core count and thread environment of the host the CPU arm runs on."""
+    try:
+        aff = len(os.sched_getaffinity(0))
+    except Exception:
+        aff = None
+    return {"cpu_count": os.cpu_count(), "sched_affinity": aff,
+            "OMP_NUM_THREADS": os.environ.get("OMP_NUM_THREADS"), "OPENBLAS_NUM_THREADS": os.environ.get("OPENBLAS_NUM_THREADS"),
+            "MKL_NUM_THREADS": os.environ.get("MKL_NUM_THREADS"),
+            "threads_used": 1, "why": "scipy's SuperLU (splu) and ARPACK (eigs) are single-threaded; the reference's path has no other parallelism"}
+
+
+# Same-configuration CPU measurement made once in the build container (oracle/make_golden_at_size.py c4, kept in
+# tests/golden/c4_vec_1M.npz): 1545 s for ONE c4 eigensolve with oracle/restated.py; a 40k-triangle solve of the same
+# fibre took 8.9 s on the same host the same hour.  The ratio predicts the full-size time on another host from a
+# calibration solve there.
+CAL_ELEMENTS = 40_000
+CAL_SECONDS_BUILD_HOST = 8.9
+SIZE_EXPONENT = 1.83          # t ~ Ne^1.83 between 80k (24.0 s) and 1M (1545 s) triangles on the build host
+
+
+def same_config_record():
+    try:
+        z = np.load(os.path.join(ROOT, "tests", "golden", "c4_vec_1M.npz"))
+        return {"seconds": float(z["seconds"]), "elements": int(z["elements"]), "n_op": int(z["n_op"]),
+                "eigensolves_per_s": 1.0 / float(z["seconds"]), "cores": 1,
+                "where": "build container (8 cores), oracle/make_golden_at_size.py c4 -> tests/golden/c4_vec_1M.npz; "
+                         "the eigenvalues of that run are what tests/test_gpu_at_size.py asserts"}
+    except Exception:
+        return None
+
+
 def cpu_port_run(n_elements, steps=1, warmup=0, budget_s=None):
     """The reference's algorithm for this path restated in numpy/scipy (oracle/restated.py:
     vectorised get_unique_edges + construct_AB_vec + matrix-free 'transform' eigs with SuperLU),
@@ -152,7 +191,7 @@ def cpu_port_run(n_elements, steps=1, warmup=0, budget_s=None):
     take well over ten minutes per solve on the CPU, so this is a BOUNDED sample: the same
     geometry at `n_elements` triangles."""
     from oracle import restated as R
-    mesh, ior = make_mesh(n_elements, seed=1)
+    mesh, ior = make_mesh(n_elements, seed=0)        # the mesh family (and, at full size, the very mesh) of our arm's rank 0
     ts, info = [], None
     for it in range(warmup + steps):
         m = copy.copy(mesh)
@@ -168,31 +207,127 @@ def cpu_port_run(n_elements, steps=1, warmup=0, budget_s=None):
     t = float(np.mean(ts))
     return {"value": 1.0 / t, "unit": "eigensolves/s", "cores": 1, "kind": "port",
             "sample": "oracle/restated.py (numpy + scipy SuperLU/ARPACK, single-threaded like the reference's "
-                      "scipy path) on the same fibre at %d triangles instead of ~1M: %.2f s per solve, %d OP "
-                      "applications; CPU cost grows faster than linearly with size, so the 1M-triangle "
-                      "figure would be lower still" % (mesh.num_elements, t, info["n_op"]),
-            "seconds": t, "elements": mesh.num_elements, "steps_timed": len(ts)}
+                      "scipy path) on the same fibre at %d triangles: %.2f s per solve, %d OP applications"
+                      % (mesh.num_elements, t, info["n_op"]),
+            "seconds": t, "elements": mesh.num_elements, "steps_timed": len(ts), "host": host_info()}
 
 
 def run_reference(args):
+    """--impl reference: the reference's algorithm for this path on the host cores (oracle/restated.py -- the
+    literal reference cannot run the vector path beyond ~5k elements).
+
+    N = 1: the SAME configuration as our arm -- the full --elements mesh, one timed solve, no warm-up -- when a
+    40k-triangle calibration solve predicts that it fits --ref-budget-s (it took 1545 s in the build container);
+    otherwise the largest mesh predicted to fit, with same_config=false and the extrapolation stated separately.
+    N > 1 (the scaling runs): rank 0 runs a bounded sample sized for ~150 s -- the CPU path does not scale with
+    the number of GPUs, the same-configuration number is the N = 1 line."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    # every step is the same bounded sample; the run stops early once the timed steps have used ~3 minutes
-    # (the line then says how many of the K steps were timed)
-    r = cpu_port_run(args.cpu_sample_elements, steps=max(1, args.steps), warmup=min(1, args.warmup), budget_s=180.0)
+    t_arm = time.perf_counter()
+    cal = cpu_port_run(args.cal_elements or CAL_ELEMENTS)
+    rec = same_config_record()
+    full_build = rec["seconds"] if rec else 1545.0
+    cal_build = CAL_SECONDS_BUILD_HOST * (cal["elements"] / 39910.0) ** SIZE_EXPONENT
+    pred_full = full_build * cal["seconds"] / cal_build * (args.elements / 1.0e6) ** SIZE_EXPONENT
+    budget = args.ref_budget_s if args.gpus == 1 else min(args.ref_budget_s, 150.0)
+    if pred_full <= budget:
+        n_el = args.elements
+    else:
+        n_el = int(args.elements * (budget / pred_full) ** (1.0 / SIZE_EXPONENT))
+        n_el = max(min(n_el, args.elements), args.cpu_sample_elements)
+    r = cpu_port_run(n_el, steps=1, warmup=0)
+    same = abs(r["elements"] - args.elements) <= 0.02 * args.elements
+    note = ("same configuration as the GPU arm: one timed solve of the full mesh, no warm-up (a CPU solve has no "
+            "warm-up effects worth %.0f s)" % r["seconds"]) if same else \
+        ("BOUNDED sample: %d of ~%d triangles (the full-size solve was predicted at %.0f s from a %.1f s calibration "
+         "solve at %d triangles, budget %.0f s); not the same configuration -- see extrapolated_full_size"
+         % (r["elements"], args.elements, pred_full, cal["seconds"], cal["elements"], budget))
+    cfg = {"workload": WORKLOAD, "elements": r["elements"], "elements_per_gpu": r["elements"], "Nmax": NMAX,
+           "same_config": bool(same), "note": note,
+           "calibration": {"elements": cal["elements"], "seconds": cal["seconds"], "predicted_full_size_seconds": pred_full,
+                           "build_host_seconds": CAL_SECONDS_BUILD_HOST, "size_exponent": SIZE_EXPONENT}}
     line = {
         "impl": "reference", "metric": METRIC, "value": r["value"], "unit": "eigensolves/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "steps_timed": r["steps_timed"],
         "ms_per_step": r["seconds"] * 1e3, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "elements": r["elements"],
-                   "note": "bounded CPU sample of the workload (see cpu_baseline.sample)"},
-        "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "same_config": bool(same),
+        "config": cfg,
+        "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample", "host")},
         "e2e": {"value": r["value"], "unit": "eigensolves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
+        "gpu_launches": 0, "arm_seconds": None,
     }
+    if not same:
+        est = r["seconds"] * (args.elements / float(r["elements"])) ** SIZE_EXPONENT
+        line["extrapolated_full_size"] = {"seconds": est, "eigensolves_per_s": 1.0 / est, "exponent": SIZE_EXPONENT,
+                                          "basis": "t ~ Ne^%.2f fitted on the build host between 80k and 1M triangles; an "
+                                                   "estimate, NOT a measurement" % SIZE_EXPONENT}
+    if rec:
+        line["same_config_build_host"] = rec
+    line["arm_seconds"] = time.perf_counter() - t_arm
     print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+# c5: the sweep slice (BASELINE.json configs[4])
+# ---------------------------------------------------------------------------------------------
+def run_sweep_slice(args, dev, rank, world):
+    """256 problems = 16 lantern z-slices (multimode-core radius 9 .. 16 as in lantern-demo.ipynb cell 4, one
+    ~50k-triangle mesh each) x 16 wavelengths (1.0 .. 1.8), vector modes, Nmax = 10, partitioned over the ranks by
+    sweep.partition, eigenpairs gathered on rank 0 over NCCL -- the gather and the device -> host copy of the
+    gathered eigenvectors are INSIDE the timed region.  Mesh generation (host, stays on the host like gmsh in the
+    reference) and the edge tables are outside it."""
+    import torch
+    import torch.distributed as dist
+    import wavesolve_b200 as ws
+    from wavesolve_b200 import meshgen as mg, sweep
+
+    n_wl = 16
+    n_mesh = max(1, args.sweep_problems // n_wl)
+    radii = np.linspace(9.0, 16.0, n_mesh)
+    meshes = [mg.lantern_cross_section(args.sweep_elements, order=1, seed=100 + i, r_clad_bundle=float(r))
+              for i, r in enumerate(radii)]
+    for m in meshes:
+        ws.get_unique_edges(m)
+    wls = np.linspace(1.0, 1.8, n_wl)
+    probs = sweep.problem_grid(n_mesh, wls, mg.LANTERN_IOR, tags=[float(r) for r in radii])
+    sweep.solve_sweep(meshes[:1], probs[:2], Nmax=NMAX, kind="vector", dst=0)       # warm-up: kernels, pools, NCCL p2p
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+        torch.cuda.synchronize()
+    gs = {}
+    t0 = time.perf_counter()
+    res = sweep.solve_sweep(meshes, probs, Nmax=NMAX, kind="vector", dst=0, gather_stats=gs)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt, gs.get("seconds", 0.0)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dt = float(t[0])
+    out = None
+    if rank == 0:
+        ok = all(r.rc == 0 for r in res)
+        for i in (0, len(probs) // 2 + 3, len(probs) - 1):
+            pr = probs[i]
+            w, v, cnt = ws.solve_waveguide_vec(meshes[pr.mesh_id], pr.wl, pr.IOR_dict, Nmax=NMAX, verbose=False)
+            k = 2 * np.pi / pr.wl
+            ne_s, ne_i = np.sqrt(res[i].w) / k, np.sqrt(w.real) / k
+            ok = ok and bool(np.max(np.abs(ne_s - ne_i) / ne_i) < 1e-10) and res[i].mode_count == cnt and res[i].v.shape == v.shape
+        sizes = sorted(set(int(r.v.shape[1]) for r in res))
+        out = {"workload": "c5: %d problems = %d lantern z-slices (~%dk P1 triangles each, N = %d..%d) x %d wavelengths, "
+                           "solve_waveguide_vec semantics, Nmax=%d (BASELINE.json configs[4])"
+                           % (len(probs), n_mesh, args.sweep_elements // 1000, sizes[0], sizes[-1], n_wl, NMAX),
+               "problems": len(probs), "problems_per_s": len(probs) / dt, "seconds": dt,
+               "gather_ms": gs.get("seconds", 0.0) * 1e3, "gathered_bytes": int(gs.get("bytes", 0)),
+               "gather": "NCCL point-to-point to rank 0 + pinned device->host copy, inside the timed region"
+                         if world > 1 else "single rank: pinned device->host copy of the packed results, inside the timed region",
+               "ranks_that_solved": sorted(set(r.rank for r in res)),
+               "failed_problems": int(sum(1 for r in res if r.rc != 0)),
+               "parity_ok": bool(ok),
+               "parity": "3 gathered problems re-solved through solve_waveguide_vec: neff within 1e-10, same mode count"}
+    del res
+    return out
 
 
 # ---------------------------------------------------------------------------------------------
@@ -369,7 +504,7 @@ def run_ours(args):
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": WORKLOAD, "elements_per_gpu": ne, "N": N, "nnz": nnz, "Nmax": NMAX,
+        "config": {"workload": WORKLOAD, "elements": ne, "elements_per_gpu": ne, "N": N, "nnz": nnz, "Nmax": NMAX,
                    "ncv": max(2 * NMAX + 4, 20), "tol": "eps (scipy default tol=0)",
                    "l2": "inputs_larger_than_l2 (factor panels %.1f GB, basis %.2f GB per step)"
                          % (8 * fstat["nnzL"] / 1e9, 8 * 22 * N / 1e9),
@@ -397,10 +532,17 @@ def run_ours(args):
         "gpu_launches": int(launches),
         "clocks": clk.summary(),
     }
+    if args.sweep_problems > 0:
+        sw = run_sweep_slice(args, dev, rank, world)
+        if rank == 0:
+            line["sweep"] = sw
     if rank == 0:
         if not args.no_cpu_baseline and world == 1:
             r = cpu_port_run(args.cpu_sample_elements)
-            line["cpu_baseline"] = {k_: r[k_] for k_ in ("value", "unit", "cores", "kind", "sample")}
+            line["cpu_baseline"] = {k_: r[k_] for k_ in ("value", "unit", "cores", "kind", "sample", "host")}
+            rec = same_config_record()
+            if rec:
+                line["cpu_baseline"]["same_config_build_host"] = rec
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -117,7 +117,7 @@ def _worker(rank, world, port, q):
             local[i] = (wv, Vv, cnt)
         got = sweep.gather_eigenpairs(local, len(mesh_ids), packed=buf)
         ok = True
-        for i, (w, v, cnt, owner) in enumerate(got):
+        for i, (w, v, cnt, owner, rc) in enumerate(got):
             we, Ve, ce = _fake_result(i, Ns[mesh_ids[i]], k)
             ok = ok and np.array_equal(w, we.numpy()) and np.array_equal(v, Ve.numpy()) and cnt == ce
             ok = ok and i in table[owner]

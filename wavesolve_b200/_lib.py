@@ -67,7 +67,17 @@ _SIGNATURES = {
 
 
 class WavesolveB200Error(RuntimeError):
-    pass
+    """A C-ABI call failed.  ``rc`` is the library's status code (include/wavesolve_b200.h: 1 CUDA, 2 numeric,
+    3 no convergence, < 0 argument / state).  For rc == 3 (``ws_eig_solve``: fewer than ``nev`` pairs converged)
+    the output arrays have still been written; the drivers attach them as ``eigenvalues`` / ``eigenvectors``
+    (the names of scipy's ``ArpackNoConvergence``, which the reference lets propagate from eigsh / eigs)."""
+    rc = 0
+    eigenvalues = None
+    eigenvectors = None
+    info = None
+
+
+ERR_ARG, ERR_STATE, ERR_CUDA, ERR_NUMERIC, ERR_NOCONV = -1, -2, 1, 2, 3
 
 
 def lib():
@@ -90,8 +100,10 @@ def lib():
 def check(rc):
     if rc != 0:
         msg = lib().ws_last_error()
-        raise WavesolveB200Error("wavesolve_b200 C-ABI call failed (%d): %s"
-                                 % (rc, msg.decode(errors="replace") if msg else "?"))
+        e = WavesolveB200Error("wavesolve_b200 C-ABI call failed (%d): %s"
+                               % (rc, msg.decode(errors="replace") if msg else "?"))
+        e.rc = int(rc)
+        raise e
 
 
 def launch_count() -> int:

@@ -117,13 +117,6 @@ constexpr double PIV_REL = 1e-10;
 __device__ __forceinline__ double pivot_tau(const unsigned long long* stats) {
     return PIV_REL * __longlong_as_double((long long)stats[5]);
 }
-__device__ __forceinline__ double guard_pivot(double pv, double tau, unsigned long long* stats) {
-    if (fabs(pv) < tau) {
-        pv = copysign(tau, pv);
-        atomicAdd(&stats[4], 1ull);
-    }
-    return pv;
-}
 
 constexpr int KC = 16;
 constexpr int GSTAGES = 3;
@@ -524,7 +517,7 @@ __host__ __device__ inline size_t fused_smem_doubles(int m, int p) {
 }
 
 template <int PMAX>
-__global__ void k_front_fused(int64_t first, int has_children, FusedCtx cx) {
+__device__ __forceinline__ void front_fused_body(int64_t first, int has_children, const FusedCtx& cx) {
     extern __shared__ __align__(16) double fsm[];
     const int64_t t = first + blockIdx.x;
     const FrontView& fv = cx.fv;
@@ -581,7 +574,17 @@ __global__ void k_front_fused(int64_t first, int has_children, FusedCtx cx) {
     // row k+1 has the shortest update of step k, so it also inverts the next pivot while the others
     // finish: the division is off the critical path and rows are scaled by multiplication.
     double* rd = rb;
+    // static pivoting: the thread that inverts a pivot also guards it (|pivot| < tau -> +-tau) and records it in
+    // dd[]; perturbations are counted per thread and reported once (no atomics inside the elimination loop)
     const double tau = pivot_tau(cx.stats);
+    int npert = 0;
+    auto guarded = [&](double pv) {
+        if (fabs(pv) < tau) {
+            pv = copysign(tau, pv);
+            ++npert;
+        }
+        return pv;
+    };
     if constexpr (PMAX > 0) {
         // wide pivot blocks (leaf fronts): the row lives in REGISTERS (PMAX columns, statically
         // indexed: the k and j loops are fully unrolled), so one update is one DFMA plus half a
@@ -591,8 +594,9 @@ __global__ void k_front_fused(int64_t first, int has_children, FusedCtx cx) {
 #pragma unroll
         for (int j = 0; j < PMAX; ++j) row[j] = (tid < m && j < p) ? P[tid + j * ld] : 0.0;
         if (tid == 0 && p > 0) {
-            row[0] = guard_pivot(row[0], tau, cx.stats);
-            rd[0] = 1.0 / row[0];
+            const double pv = guarded(row[0]);
+            dd[0] = pv;
+            rd[0] = 1.0 / pv;
         }
 #pragma unroll
         for (int k = 0; k < PMAX; ++k) {
@@ -600,7 +604,6 @@ __global__ void k_front_fused(int64_t first, int has_children, FusedCtx cx) {
             double* buf = vb + (k & 1) * pe;
             if (tid >= k && tid < p) buf[tid] = row[k];
             __syncthreads();
-            if (tid == k) dd[k] = row[k];
             if (tid > k && tid < m) {
                 const double li = row[k] * rd[k];
                 row[k] = li;
@@ -620,8 +623,9 @@ __global__ void k_front_fused(int64_t first, int has_children, FusedCtx cx) {
                     }
                 }
                 if (k + 1 < PMAX && tid == k + 1 && tid < p) {
-                    row[k + 1 < PMAX ? k + 1 : 0] = guard_pivot(row[k + 1 < PMAX ? k + 1 : 0], tau, cx.stats);
-                    rd[k + 1] = 1.0 / row[k + 1 < PMAX ? k + 1 : 0];
+                    const double pv = guarded(row[k + 1 < PMAX ? k + 1 : 0]);
+                    dd[k + 1] = pv;
+                    rd[k + 1] = 1.0 / pv;
                 }
             }
         }
@@ -633,14 +637,14 @@ __global__ void k_front_fused(int64_t first, int has_children, FusedCtx cx) {
         // narrow pivot blocks (separator fronts): the panel stays in shared memory -- fewer registers,
         // more resident CTAs, no work on columns that do not exist
         if (tid == 0 && p > 0) {
-            P[0] = guard_pivot(P[0], tau, cx.stats);
-            rd[0] = 1.0 / P[0];
+            const double pv = guarded(P[0]);
+            dd[0] = pv;
+            rd[0] = 1.0 / pv;
         }
         for (int k = 0; k < p; ++k) {
             double* buf = vb + (k & 1) * pe;
             if (tid >= k && tid < p) buf[tid] = P[tid + k * ld];
             __syncthreads();
-            if (tid == k) dd[k] = buf[k];
             if (tid > k && tid < m) {
                 const double* __restrict__ bj = buf;
                 double* __restrict__ pr = P + tid + k * ld;
@@ -659,12 +663,14 @@ __global__ void k_front_fused(int64_t first, int has_children, FusedCtx cx) {
                 }
                 for (; j <= jmax; ++j, pr += ld) *pr -= li * bj[j];
                 if (tid == k + 1 && tid < p) {
-                    P[tid + tid * ld] = guard_pivot(P[tid + tid * ld], tau, cx.stats);
-                    rd[tid] = 1.0 / P[tid + tid * ld];
+                    const double pv = guarded(P[tid + tid * ld]);
+                    dd[tid] = pv;
+                    rd[tid] = 1.0 / pv;
                 }
             }
         }
     }
+    if (npert) atomicAdd(&cx.stats[4], (unsigned long long)npert);
     __syncthreads();
     // pivots + statistics (one set of atomics per warp that holds pivots)
     if (tid < ((p + 31) & ~31)) {
@@ -777,6 +783,14 @@ __global__ void k_front_fused(int64_t first, int has_children, FusedCtx cx) {
         Sg[p + a + (size_t)j * m] = (acc0 + acc1) + (acc2 + acc3);
     }
 }
+
+// two entry points over one body: the register-resident variant is capped at 160 registers (ptxas otherwise
+// takes 230+ and loses a resident CTA per SM on the leaf level); the shared-memory variant needs ~40
+template <int PMAX>
+__global__ void __maxnreg__(160) k_front_fused_regs(int64_t first, int has_children, FusedCtx cx) {
+    front_fused_body<PMAX>(first, has_children, cx);
+}
+__global__ void k_front_fused(int64_t first, int has_children, FusedCtx cx) { front_fused_body<0>(first, has_children, cx); }
 
 // ---- solve sweeps -----------------------------------------------------------------------------
 // x = M^-1 b with the selectively inverted panels S:  forward  y_own = S11 w_own, w_bnd -= S21 w_own
@@ -1928,16 +1942,16 @@ int ws_solver_factor(ws_solver* s, const double* A_vals, const double* B_vals, d
     FrontView fv = view(s);
     static PerDeviceOnce configure_fused;
     configure_fused([] {
-        WS_CUDA(cudaFuncSetAttribute(k_front_fused<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FUSED_MAX_SMEM));
-        WS_CUDA(cudaFuncSetAttribute(k_front_fused<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FUSED_MAX_SMEM));
+        WS_CUDA(cudaFuncSetAttribute(k_front_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FUSED_MAX_SMEM));
+        WS_CUDA(cudaFuncSetAttribute(k_front_fused_regs<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FUSED_MAX_SMEM));
     });
     for (int l = Y.depth; l >= 0; --l) {
         const LevelPlan& LP = s->levels[l];
         if (LP.fused) {
             FusedCtx fc{fv, s->L.get(), s->S.get(), s->U.get(), s->d.get(), s->stats.get(), s->wsrc0.get(), s->wsrc1.get()};
             const size_t sh = fused_smem_doubles(LP.maxm, LP.maxp) * sizeof(double);
-            if (LP.maxp <= 48) k_front_fused<0><<<(unsigned)LP.nfronts, LP.nt, sh, st>>>(LP.first_front, l < Y.depth ? 1 : 0, fc);
-            else k_front_fused<64><<<(unsigned)LP.nfronts, LP.nt, sh, st>>>(LP.first_front, l < Y.depth ? 1 : 0, fc);
+            if (LP.maxp <= 48) k_front_fused<<<(unsigned)LP.nfronts, LP.nt, sh, st>>>(LP.first_front, l < Y.depth ? 1 : 0, fc);
+            else k_front_fused_regs<64><<<(unsigned)LP.nfronts, LP.nt, sh, st>>>(LP.first_front, l < Y.depth ? 1 : 0, fc);
             count_launch(1);
             continue;
         }

@@ -42,36 +42,47 @@ def d2h(t: torch.Tensor) -> np.ndarray:
 
 
 _pinned_lock = threading.Lock()
-_pinned_free = {}          # nbytes -> [page-locked uint8 tensors that no result array uses any more]
-_PINNED_KEEP = 3           # free buffers kept per size
+_pinned_free = []          # page-locked uint8 tensors that no result array uses any more (any size)
+_PINNED_KEEP = 4           # free blocks kept in total: a loop that re-meshes per z-slice asks for a new size every
+#                            call, so the cache is bounded across sizes and a block serves any request it can hold
 
 
-def _pinned_release(nbytes, buf):
+def _pinned_release(buf):
     with _pinned_lock:
-        lst = _pinned_free.setdefault(nbytes, [])
-        if len(lst) < _PINNED_KEEP:
-            lst.append(buf)
+        _pinned_free.append(buf)
+        if len(_pinned_free) > _PINNED_KEEP:
+            _pinned_free.sort(key=lambda b: b.numel())
+            del _pinned_free[0]                # drop the smallest: the large blocks are the expensive ones to pin
+
+
+def _pinned_take(nbytes):
+    """Smallest cached block with capacity in [nbytes, 2 nbytes], else a new one (sized with 1/8 headroom so that
+    slightly larger meshes of a sweep fit the same block)."""
+    with _pinned_lock:
+        best = None
+        for i, b in enumerate(_pinned_free):
+            if nbytes <= b.numel() <= 2 * nbytes and (best is None or b.numel() < _pinned_free[best].numel()):
+                best = i
+        if best is not None:
+            return _pinned_free.pop(best)
+    return torch.empty(nbytes + (nbytes >> 3), dtype=torch.uint8, pin_memory=True)
 
 
 def d2h_pinned(t: torch.Tensor) -> np.ndarray:
     """Device -> host copy of a large result through page-locked memory.  A pageable ``.cpu()`` of
     the 160-320 MB eigenvector block costs several times the DMA time in page faults, and so does
     pinning a fresh block per call, so the blocks are recycled: the returned numpy array owns its
-    block, and when the caller drops the array (and every view of it) the block goes back to a small
-    free list for the next call of the same size."""
+    block, and when the caller drops the array (and every view of it) the block goes back to a small,
+    bounded free list that serves any later request it is large enough for."""
     t = t.detach().contiguous()
     nbytes = t.numel() * t.element_size()
     if nbytes < (1 << 20):
         return t.cpu().numpy()
-    with _pinned_lock:
-        lst = _pinned_free.get(nbytes)
-        buf = lst.pop() if lst else None
-    if buf is None:
-        buf = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
-    host = buf.view(t.dtype).view(t.shape)
+    buf = _pinned_take(nbytes)
+    host = buf[:nbytes].view(t.dtype).view(t.shape)
     host.copy_(t)
     arr = host.numpy()
-    weakref.finalize(arr, _pinned_release, nbytes, buf)
+    weakref.finalize(arr, _pinned_release, buf)
     return arr
 
 

@@ -93,6 +93,35 @@ def _as_i32(a, what):
     return np.ascontiguousarray(a.astype(np.int32))
 
 
+def _ids_to_device(a, what, dev, bound=None):
+    """Integer ids (any width, as pygmsh / get_unique_edges deliver them) -> contiguous int32 CUDA tensor,
+    validated (non-negative, < 2^31, < ``bound``).  With more than one CPU thread the 64-bit ids are narrowed by
+    torch's threaded CPU kernels before the copy (half the PCIe bytes); in a single-threaded process -- every
+    rank under torchrun, which sets OMP_NUM_THREADS=1 -- the raw ids are copied and narrowed / validated on the
+    device instead (numpy's single-threaded astype costs 6 ms per 3M ids, three times per problem)."""
+    a = np.asarray(a)
+    if a.size and a.dtype.kind in "iu" and a.dtype.itemsize == 8 and a.flags.c_contiguous and a.flags.writeable \
+            and torch.get_num_threads() == 1:
+        t = torch.from_numpy(a.view(np.int64)).to(dev)          # unsigned ids >= 2^63 show up as negative
+        lo, hi = (int(x) for x in torch.stack(t.aminmax()).tolist())
+        if lo < 0 or hi >= 2 ** 31:
+            raise ValueError("%s must be non-negative integers that fit in int32" % what)
+        if bound is not None and hi >= bound:
+            raise IndexError("%s: id %d out of bounds for size %d" % (what, hi, bound))
+        return t.to(torch.int32), a.size * 8
+    h = _as_i32(a, what)
+    if bound is not None and h.size and int(_imax(h)) >= bound:
+        raise IndexError("%s: id %d out of bounds for size %d" % (what, int(_imax(h)), bound))
+    return _dev.h2d(h, dev), h.nbytes
+
+
+def _imax(a):
+    """max of an int32 array (torch's threaded reduction for the large ones)."""
+    if a.size > (1 << 16) and a.flags.c_contiguous and a.flags.writeable:
+        return torch.from_numpy(a).max()
+    return a.max() if a.size else 0
+
+
 class DevicePattern:
     """Owns a ``ws_pattern`` handle."""
 
@@ -157,6 +186,13 @@ class ScalarProblem:
         else:
             conn, k2 = _material_major(mesh, IOR_dict, k)
         conn = _as_i32(conn, "node ids")
+        # the device kernels index xy[] with these ids unchecked: refuse what numpy would refuse (IndexError at
+        # points[tris], shape_funcs.py:196) and the wrong element order (fe_solver.py:140, :143)
+        width = 6 if order == 2 else 3
+        if conn.ndim != 2 or conn.shape[1] < width:
+            raise AssertionError("must use order %d mesh for order %d solver" % (order, order))
+        if conn.size and int(conn.max()) >= len(mesh.points):
+            raise IndexError("node id %d out of bounds for %d mesh points" % (int(conn.max()), len(mesh.points)))
         if order == 1:
             # linear triangles ride the six-unknown pattern machinery as (v0 v1 v2 v0 v1 v2)
             conn = np.ascontiguousarray(np.hstack([conn[:, :3], conn[:, :3]]))
@@ -250,9 +286,7 @@ class VectorProblem:
         self.Nzz = len(mesh.points)
         self.N = self.Ntt + self.Nzz
         self.first_class_start = self.Ntt
-        tris32 = _as_i32(tris_all[:, :3], "vertex ids")
-        eidx32 = _as_i32(eidx_all, "edge ids")
-        edges32 = _as_i32(np.asarray(mesh.cells[0].data), "edge table")
+        tris_h = tris_all if tris_all.shape[1] == 3 else tris_all[:, :3]
         pts = np.asarray(mesh.points)
         whole = pts.dtype == np.float64 and pts.ndim == 2 and pts.shape[1] > 2 and pts.flags.c_contiguous
         # (Np, 3) float64 as pygmsh delivers it: the z column is dropped on the device (a strided host copy of
@@ -260,9 +294,11 @@ class VectorProblem:
         xy = pts if whole else np.ascontiguousarray(np.asarray(pts, dtype=np.float64)[:, :2])
         with torch.cuda.device(dev):
             self.xy = _dev.h2d(xy, dev)[:, :2].contiguous() if whole else _dev.h2d(xy, dev)
-            self.edges = _dev.h2d(edges32, dev)
+            # ids are used unchecked by the kernels: validated here (numpy raises IndexError for these in the reference)
+            self.edges, nb_e = _ids_to_device(np.asarray(mesh.cells[0].data), "edge table", dev, self.Nzz)
             self.k2n2 = _dev.h2d(k2, dev)
-            t_d, e_d = _dev.h2d(tris32, dev), _dev.h2d(eidx32, dev)
+            t_d, nb_t = _ids_to_device(tris_h, "vertex ids", dev, self.Nzz)
+            e_d, nb_i = _ids_to_device(eidx_all, "edge ids (stale edge_indices? run get_unique_edges)", dev, self.Ntt)
             if order is not None:
                 # material-major element order (fe_solver.py:179) gathered on the device
                 o_d = _dev.h2d(order, dev)
@@ -270,8 +306,7 @@ class VectorProblem:
             self.tris = t_d.contiguous()
             self.dofs = torch.cat([e_d, self.tris + self.Ntt], dim=1).contiguous()   # edges first, then nodes
             self.pattern = DevicePattern(self.dofs, self.N) if build_pattern else None
-        self.h2d_bytes = (xy.nbytes + tris32.nbytes + eidx32.nbytes + k2.nbytes + edges32.nbytes +
-                          (order.nbytes if order is not None else 0))
+        self.h2d_bytes = (xy.nbytes + nb_t + nb_i + k2.nbytes + nb_e + (order.nbytes if order is not None else 0))
 
     # host copies of the resident arrays (tests and diagnostics; the solve path does not need them)
     @property
@@ -441,9 +476,15 @@ def _eig_device(pattern, solver, B_vals, sigma, kind, nev, N, dev, ncv=0, tol=0.
                                  int(nev), int(ncv), float(tol), int(maxit), int(seed),
                                  _dev.ptr(edges), _dev.ptr(xy), int(Ntt), _dev.ptr(w), _dev.ptr(V),
                                  info.ctypes.data, resid.ctypes.data, dev.index, _dev.stream_ptr(dev))
-    _lib.check(rc)
-    return w, V, dict(nconv=int(info[0]), n_op=int(info[1]), restarts=int(info[2]), ncomplex=int(info[3]),
-                      resid=resid)
+    out_info = dict(nconv=int(info[0]), n_op=int(info[1]), restarts=int(info[2]), ncomplex=int(info[3]), resid=resid)
+    try:
+        _lib.check(rc)
+    except _lib.WavesolveB200Error as e:
+        if e.rc == _lib.ERR_NOCONV:
+            # like scipy's ArpackNoConvergence, the partial results travel with the exception
+            e.eigenvalues, e.eigenvectors, e.info = w, V, out_info
+        raise
+    return w, V, out_info
 
 
 def _count_modes(w_iter, k, IOR_dict, always=False):

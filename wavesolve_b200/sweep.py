@@ -45,6 +45,9 @@ class SweepResult:
     mode_count: int
     rank: int
     info: dict = field(default_factory=dict)
+    rc: int = 0                  # 0 ok; 3: fewer than Nmax pairs converged (w, v hold what the iteration had);
+    #                              other codes: the problem failed (w, v are NaN), ``info["error"]`` says why --
+    #                              one failing problem never aborts the sweep
 
 
 def problem_grid(n_meshes: int, wavelengths: Sequence[float], IOR_dicts, target_neff: Optional[float] = None,
@@ -124,65 +127,109 @@ def _dist():
     return dist
 
 
+def _to_host(t: torch.Tensor) -> np.ndarray:
+    """Device -> host through page-locked memory for CUDA tensors (a pageable .cpu() of a multi-GB gather
+    payload spends most of its time in page faults)."""
+    if t.is_cuda and t.numel() * t.element_size() >= (1 << 20):
+        from . import device as _dev
+        return _dev.d2h_pinned(t)
+    return t.cpu().numpy()
+
+
 def gather_eigenpairs(local: Dict[int, tuple], n_problems: int, group=None, with_vectors=True,
-                      dst: Optional[int] = None, packed: Optional[torch.Tensor] = None):
+                      dst: Optional[int] = None, packed: Optional[torch.Tensor] = None, stats: Optional[dict] = None):
     """Collect per-problem results from all ranks.
 
-    ``local``: {problem index: (w tensor (k,), V tensor (k, N), mode_count int)} -- tensors on the
+    ``local``: {problem index: (w tensor (k,), V tensor (k, N), mode_count int[, rc int])} -- tensors on the
     rank's device (CUDA for NCCL, CPU for gloo).  Returns a list of ``n_problems`` entries
-    ``(w ndarray, v ndarray | None, mode_count, owner_rank)`` on every rank (``dst=None``) or on
-    rank ``dst`` only (other ranks get None).  Without an initialised process group this is the
-    single-rank identity.  ``packed``: the flat buffer [w_i | V_i ...] (in ``local``'s insertion order) the tensors
-    of ``local`` are views of; when it is at least as long as the largest rank payload it is sent
-    as is (no staging copy)."""
+    ``(w ndarray, v ndarray | None, mode_count, owner_rank, rc)`` on every rank (``dst=None``) or on rank ``dst``
+    only (other ranks get None).  Without an initialised process group this is the single-rank identity.
+
+    ``dst=None``: one padded ``all_gather`` (every rank needs everything).  ``dst=r``: every other rank sends its
+    payload -- exactly its own size, no padding -- to ``r`` with point-to-point ``send`` / ``recv`` (NCCL over
+    NVLink on GPUs), so only ``r`` receives and only ``r`` pays the device -> host copy (through pinned memory).
+    ``packed``: the flat buffer [w_i | V_i ...] (in ``local``'s insertion order) the tensors of ``local`` are views
+    of; it is sent as is (no staging copy).  ``stats``: if a dict, filled with ``bytes`` received / held on this
+    rank and ``seconds`` of the collective + host copy."""
+    import time as _time
     dist = _dist()
     multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
     rank = dist.get_rank(group) if multi else 0
     world = dist.get_world_size(group) if multi else 1
     keys = list(local)            # insertion order = packing order
-    meta = [(i, int(local[i][0].numel()), int(local[i][1].shape[-1]) if with_vectors else 0, int(local[i][2]))
-            for i in keys]
+    meta = [(i, int(local[i][0].numel()), int(local[i][1].shape[-1]) if with_vectors else 0, int(local[i][2]),
+             int(local[i][3]) if len(local[i]) > 3 else 0) for i in keys]
+    t_start = _time.perf_counter()
     if multi:
         metas = [None] * world
         dist.all_gather_object(metas, meta, group=group)
     else:
         metas = [meta]
-    sizes = [sum(k * (1 + n) for (_, k, n, _) in m) for m in metas]
-    pad = max(sizes) if sizes else 0
-    ref = local[keys[0]][0] if keys else torch.zeros(0, dtype=torch.float64)
+    sizes = [sum(k * (1 + n) for (_, k, n, _, _) in m) for m in metas]
+    ref = local[keys[0]][0] if keys else (packed if packed is not None else torch.zeros(0, dtype=torch.float64))
     dev = ref.device
-    if packed is not None and with_vectors and packed.numel() >= max(pad, 1) and packed.is_contiguous():
-        send = packed[:max(pad, 1)]
+    mine = sizes[rank]
+    if packed is not None and with_vectors and packed.numel() >= mine and packed.is_contiguous():
+        send = packed[:mine]
     else:
-        send = torch.zeros(max(pad, 1), dtype=torch.float64, device=dev)
+        send = torch.zeros(mine, dtype=torch.float64, device=dev)
         off = 0
         for i in keys:
-            w, V, _ = local[i]
+            w, V = local[i][0], local[i][1]
             k = w.numel()
             send[off:off + k].copy_(w.reshape(-1))
             off += k
             if with_vectors:
                 send[off:off + V.numel()].copy_(V.reshape(-1))
                 off += V.numel()
-    if multi:
-        recv = [torch.empty_like(send) for _ in range(world)]
-        dist.all_gather(recv, send, group=group)
+    recv: List[Optional[torch.Tensor]] = [None] * world
+    if not multi:
+        recv[0] = send
+    elif dst is None:
+        pad = max(max(sizes), 1)
+        sp = send if send.numel() == pad else torch.cat([send, torch.zeros(pad - send.numel(), dtype=send.dtype, device=dev)])
+        bufs = [torch.empty(pad, dtype=torch.float64, device=dev) for _ in range(world)]
+        dist.all_gather(bufs, sp, group=group)
+        recv = [bufs[r][:sizes[r]] for r in range(world)]
     else:
-        recv = [send]
+        gdst = dist.get_global_rank(group, dst) if group is not None else dst
+        if rank == dst:
+            reqs = []
+            for r in range(world):
+                if r == dst:
+                    recv[r] = send
+                elif sizes[r]:
+                    recv[r] = torch.empty(sizes[r], dtype=torch.float64, device=dev)
+                    src = dist.get_global_rank(group, r) if group is not None else r
+                    reqs.append(dist.irecv(recv[r], src=src, group=group))
+                else:
+                    recv[r] = torch.zeros(0, dtype=torch.float64, device=dev)
+            for q in reqs:
+                q.wait()
+        elif mine:
+            dist.send(send, dst=gdst, group=group)
     if dst is not None and rank != dst:
+        if stats is not None:
+            if dev.type == "cuda":
+                torch.cuda.synchronize(dev)
+            stats.update(bytes=0, seconds=_time.perf_counter() - t_start)
         return None
     out: List[Optional[tuple]] = [None] * n_problems
+    nbytes = 0
     for r, m in enumerate(metas):
-        buf = recv[r].cpu().numpy()
+        buf = _to_host(recv[r])
+        nbytes += buf.nbytes
         off = 0
-        for (i, k, n, cnt) in m:
+        for (i, k, n, cnt, rc) in m:
             w = buf[off:off + k].copy()
             off += k
             v = None
             if with_vectors:
-                v = buf[off:off + k * n].reshape(k, n).copy()
+                v = buf[off:off + k * n].reshape(k, n)      # a view of the (pinned) landing buffer: no second host copy
                 off += k * n
-            out[i] = (w, v, cnt, r)
+            out[i] = (w, v, cnt, r, rc)
+    if stats is not None:
+        stats.update(bytes=int(nbytes), seconds=_time.perf_counter() - t_start)
     missing = [i for i, o in enumerate(out) if o is None]
     if missing:
         raise RuntimeError("sweep gather: no rank reported problems %s" % missing[:8])
@@ -218,7 +265,7 @@ class _MeshContext:
 
 def solve_sweep(meshes: Sequence, problems: Sequence[SweepProblem], Nmax: int = 10, kind: str = "vector",
                 group=None, device=None, leaf_elems=None, with_vectors: bool = True, gather: bool = True,
-                dst: Optional[int] = None, lanes: Optional[int] = None):
+                dst: Optional[int] = None, lanes: Optional[int] = None, gather_stats: Optional[dict] = None):
     """Solve every problem of the sweep, this rank taking its share (``partition``), and gather.
 
     ``meshes``: mesh objects (vector sweeps: already passed through ``get_unique_edges``), the same
@@ -232,7 +279,7 @@ def solve_sweep(meshes: Sequence, problems: Sequence[SweepProblem], Nmax: int = 
     the GPU by itself.  Default 1: measured on a B200 with 32 problems of 100k unknowns, 2 lanes give
     +15 % and 4 or 8 lanes are slower than one (the lanes contend for the stream-ordered memory pool
     and the driver; tools/bench_sweep.py --lanes N) -- kept as an opt-in until that is resolved."""
-    from . import device as _dev, fe_solver as fs
+    from . import _lib, device as _dev, fe_solver as fs
     import threading
     assert kind in ("vector", "scalar")
     dist = _dist()
@@ -242,9 +289,14 @@ def solve_sweep(meshes: Sequence, problems: Sequence[SweepProblem], Nmax: int = 
     dev = _dev.require_cuda(device)
 
     def n_unknowns(mesh):
+        # the same rule the problem classes apply (fe_solver.VectorProblem / ScalarProblem.N): the packed
+        # send-buffer offsets and the gather metadata must agree
         if kind == "vector":
             return len(mesh.cells[0].data) + len(mesh.points)
-        return int(np.asarray(mesh.cells[1].data).max()) + 1
+        conn = np.asarray(mesh.cells[1].data)
+        used = [conn[np.asarray(sel[1])] if sel[1] is not None else conn for sel in mesh.cell_sets.values()]
+        used = [u for u in used if u.size]
+        return int(max(int(u.max()) for u in used)) + 1 if used else 0
 
     sizes = [n_unknowns(m) for m in meshes]
     table = partition([p.mesh_id for p in problems], [estimate_cost(sizes[p.mesh_id]) for p in problems], world)
@@ -288,14 +340,24 @@ def solve_sweep(meshes: Sequence, problems: Sequence[SweepProblem], Nmax: int = 
                         Vv = sendbuf[o + Nmax:o + Nmax + Nmax * N].view(Nmax, N)
                         nmax_ior = max(pr.IOR_dict.values())
                         sigma = float(np.power(k * (nmax_ior if pr.target_neff is None else pr.target_neff), 2))
-                        if kind == "vector":
-                            _, _, info = fs.solve_vector_resident(ctx.prob, sigma, Nmax, solver=ctx.solver, out=(wv, Vv))
-                        else:
-                            _, _, info = fs.solve_scalar_resident(ctx.prob, sigma, Nmax, solver=ctx.solver, out=(wv, Vv))
+                        rc = 0
+                        try:
+                            if kind == "vector":
+                                _, _, info = fs.solve_vector_resident(ctx.prob, sigma, Nmax, solver=ctx.solver, out=(wv, Vv))
+                            else:
+                                _, _, info = fs.solve_scalar_resident(ctx.prob, sigma, Nmax, solver=ctx.solver, out=(wv, Vv))
+                        except _lib.WavesolveB200Error as e:
+                            # per-problem failure (error code + partial results per problem):
+                            # no convergence keeps what the iteration wrote, anything else is marked NaN
+                            rc = e.rc or _lib.ERR_CUDA
+                            info = dict(e.info or {}, error=str(e))
+                            if rc != _lib.ERR_NOCONV:
+                                wv.fill_(float("nan"))
+                                Vv.fill_(float("nan"))
                         w_host = wv.cpu().numpy()
-                        cnt = fs._count_modes(w_host, k, pr.IOR_dict,
-                                              always=(kind == "vector" and pr.target_neff is not None))
-                        local[i] = (wv, Vv, cnt)
+                        cnt = 0 if rc not in (0, _lib.ERR_NOCONV) else \
+                            fs._count_modes(w_host, k, pr.IOR_dict, always=(kind == "vector" and pr.target_neff is not None))
+                        local[i] = (wv, Vv, cnt, rc)
                         infos[i] = info
                     if ctx is not None:
                         ctx.close()
@@ -323,9 +385,9 @@ def solve_sweep(meshes: Sequence, problems: Sequence[SweepProblem], Nmax: int = 
         torch.cuda.synchronize(dev)
         if not gather:
             return [SweepResult(i, local[i][0].cpu().numpy(), local[i][1].cpu().numpy() if with_vectors else None,
-                                local[i][2], rank, infos[i]) for i in mine]
+                                local[i][2], rank, infos[i], local[i][3]) for i in mine]
         got = gather_eigenpairs(local, len(problems), group=group, with_vectors=with_vectors, dst=dst,
-                                packed=sendbuf)
+                                packed=sendbuf, stats=gather_stats)
     if got is None:
         return None
-    return [SweepResult(i, w, v, cnt, r, infos.get(i, {})) for i, (w, v, cnt, r) in enumerate(got)]
+    return [SweepResult(i, w, v, cnt, r, infos.get(i, {}), rc) for i, (w, v, cnt, r, rc) in enumerate(got)]

@@ -36,12 +36,11 @@ def get_unique_edges(mesh, mutate=True, device=None):
     ``edge_indices`` (uint), ``edge_flips``, ``num_edges`` and ``num_points``.
     The O(E^2) list scan is replaced by a device sort/unique/rank (csrc/ws_pattern.cu)."""
     dev = _dev.require_cuda(device)
-    from .fe_solver import _as_i32
+    from .fe_solver import _ids_to_device
     tris = np.asarray(mesh.cells[1].data)
-    t32 = _as_i32(tris[:, :3], "vertex ids")
     with torch.cuda.device(dev):
-        td = _dev.h2d(t32, dev)
-        npts = int(t32.max()) + 1 if t32.size else 0
+        td, _ = _ids_to_device(tris if tris.shape[1] == 3 else tris[:, :3], "vertex ids", dev)
+        npts = int(td.max()) + 1 if td.numel() else 0
         edges_d, eidx_d = unique_edges_device(td, max(npts, mesh.points.shape[0]))
         # widen on the device, land in page-locked memory (the reference's arrays are 64-bit)
         wide = _torch_dtype(tris.dtype if tris.size else np.dtype(np.int64))
