@@ -250,25 +250,36 @@ def test_fast_mode_and_fused_qd_assembly(ws):
 
 def test_pinned_result_buffers_are_recycled(ws):
     """Large results come back through page-locked blocks that are recycled once the caller drops the
-    array and every view of it (wavesolve_b200.device.d2h_pinned)."""
+    array and every view of it (wavesolve_b200.device.d2h_pinned); the cache is bounded across sizes."""
     import gc
     from wavesolve_b200 import device as d
     x = torch.arange(1 << 18, dtype=torch.float64, device="cuda")
-    nbytes = x.numel() * 8
-    d._pinned_free.pop(nbytes, None)
+    del d._pinned_free[:]
     a = d.d2h_pinned(x)
     assert a.dtype == np.float64 and np.array_equal(a, np.arange(1 << 18, dtype=np.float64))
     p0 = a.ctypes.data
     view = a[:16].view(np.uint64)
     del a
     gc.collect()
-    assert not d._pinned_free.get(nbytes)                 # a view still uses the block
+    assert not d._pinned_free                             # a view still uses the block
     b = d.d2h_pinned(x * 2)                               # needs a second block
     assert b.ctypes.data != p0 and b[3] == 6.0
     del view
     gc.collect()
-    assert len(d._pinned_free[nbytes]) == 1
+    assert len(d._pinned_free) == 1
     c = d.d2h_pinned(x + 1)
     assert c.ctypes.data == p0 and c[0] == 1.0 and b[3] == 6.0   # recycled, and b is untouched
+    # a slightly smaller request (the next z-slice of a sweep) is served by the same block; many distinct sizes
+    # never park more than _PINNED_KEEP blocks
+    del c
+    gc.collect()
+    e = d.d2h_pinned(x[: (1 << 18) - 4096])
+    assert e.ctypes.data == p0 and e[7] == 7.0
+    del e, b
+    for n in range(8):
+        t = d.d2h_pinned(torch.zeros((1 << 17) + 40000 * n, dtype=torch.float64, device="cuda"))
+        del t
+    gc.collect()
+    assert len(d._pinned_free) <= d._PINNED_KEEP
     z = d.d2h_pinned(torch.view_as_complex(torch.ones(1 << 17, 2, dtype=torch.float64, device="cuda")))
     assert z.dtype == np.complex128 and z[5] == 1 + 1j
