@@ -192,6 +192,12 @@ int ws_solver_solve(ws_solver* s, const double* b, double* x, int nrhs, int devi
 int ws_solver_check(const ws_solver* s, int device, void* stream);
 int ws_solver_stats(const ws_solver* s, int64_t* h_info, double* h_dinfo);
 int ws_solver_quality(const ws_solver* s, int64_t* h_info, double* h_dinfo);
+/* ws_solver_set_overlap: 1 (default) chains the sweep kernels of a solve with programmatic dependent launch and
+ *                    per-front completion flags (a level overlaps the tail of the previous one: best for ONE large
+ *                    problem); 0 uses plain stream order (best when several problems share the GPU on different
+ *                    streams: early-resident, spinning CTAs only take slots from the other lanes).  Set before the
+ *                    first solve that a ws_eig_workspace captures.                                               */
+int ws_solver_set_overlap(ws_solver* s, int on);
 int ws_solver_destroy(ws_solver* s);
 
 /* ---- vector problem: quasi-definite form ---------------------------------------------------
@@ -235,6 +241,47 @@ int ws_eig_solve(const ws_pattern* p, ws_solver* s, const double* B_vals, double
                  double* h_resid, int device, void* stream);
 int ws_host_eig_general(int n, const double* h_A, double* h_wr, double* h_wi, double* h_V,
                         int symmetric);
+
+/* ---- K11/K12 throughput path: several eigenproblems in lockstep on one GPU ----------------------------
+ * A ~50k-triangle problem (lantern-demo.ipynb cell 4: 196 of them, run one after the other by the
+ * reference) is a chain of small dependent kernels that fills a fraction of a B200.  ws_eig_solve_batch
+ * drives `njobs` independent eigenproblems -- each with its own factorised solver, value arrays, outputs
+ * and STREAM -- from the calling host thread, interleaving their restart cycles so that their kernels
+ * overlap on the device (kind 0 / 1 only; arguments as for ws_eig_solve).  A failing job reports its own
+ * rc / error text and does not disturb the others (rc == WS_ERR_NOCONV: w / V hold what the iteration had).
+ * ws_solver_factor_begin / _end: the two halves of ws_solver_factor (enqueue everything incl. the accuracy
+ * probe / read the statistics back, refine if needed) so that several factorisations can be in flight.
+ * ws_eig_workspace: optional per-lane object that keeps the Krylov basis, the pinned staging buffers and the captured
+ * CUDA graphs of the Arnoldi steps between the problems of one mesh (same pattern / solver / value array / sizes):
+ * the ~ncv graph captures are then paid once per mesh, not once per wavelength.  The streams of the jobs that use
+ * a workspace must be idle before it is destroyed.                                                              */
+typedef struct ws_eig_workspace ws_eig_workspace;
+int ws_eig_workspace_create(ws_eig_workspace** out);
+int ws_eig_workspace_destroy(ws_eig_workspace* w);
+typedef struct ws_eig_job {
+    const ws_pattern* pattern;
+    ws_solver* solver;
+    const double* B_vals;
+    double sigma;
+    int kind, nev, ncv, maxit;
+    double tol;
+    uint64_t seed;
+    const int32_t* edges;
+    const double* xy;
+    int64_t Ntt;
+    double* w;      /* [nev]   device */
+    double* V;      /* [nev*N] device */
+    void* stream;   /* cudaStream_t of this job */
+    double* resid;  /* [nev] host, may be NULL */
+    ws_eig_workspace* workspace; /* may be NULL */
+    int64_t info[5];
+    int rc;
+    char error[228];
+} ws_eig_job;
+int ws_eig_solve_batch(ws_eig_job* jobs, int njobs, int device);
+int ws_solver_factor_begin(ws_solver* s, const double* A_vals, const double* B_vals, double sigma, int device,
+                           void* stream);
+int ws_solver_factor_end(ws_solver* s, int device, void* stream);
 
 /* ---- K13-K15: resampling of modes onto points (grid / mesh-to-mesh interpolation) -------------
  * Replaces get_tri_idxs_KDtree / find_triangle_KDtree (fe_solver.py:848-872: one KD-tree query per

@@ -114,19 +114,23 @@ def _worker(rank, world, port, q):
             wv.copy_(w)
             Vv.copy_(V)
             off += k * (1 + n)
-            local[i] = (wv, Vv, cnt)
+            local[i] = (wv, Vv, cnt, 3 * (i % 2))          # per-problem status travels with the results
         got = sweep.gather_eigenpairs(local, len(mesh_ids), packed=buf)
         ok = True
         for i, (w, v, cnt, owner, rc) in enumerate(got):
             we, Ve, ce = _fake_result(i, Ns[mesh_ids[i]], k)
             ok = ok and np.array_equal(w, we.numpy()) and np.array_equal(v, Ve.numpy()) and cnt == ce
-            ok = ok and i in table[owner]
-        # staging path (no packed buffer) and dst-only delivery
-        got2 = sweep.gather_eigenpairs(local, len(mesh_ids), dst=0)
+            ok = ok and i in table[owner] and rc == 3 * (i % 2)
+        # staging path (no packed buffer) and dst-only delivery (point-to-point to rank 0, exact sizes)
+        st = {}
+        got2 = sweep.gather_eigenpairs(local, len(mesh_ids), dst=0, stats=st)
         if rank == 0:
-            ok = ok and all(np.array_equal(a[1], b[1]) for a, b in zip(got, got2))
+            ok = ok and all(np.array_equal(a[1], b[1]) and a[4] == b[4] for a, b in zip(got, got2))
+            ok = ok and st["bytes"] == 8 * sum(k * (1 + Ns[m]) for m in mesh_ids)
         else:
-            ok = ok and got2 is None
+            ok = ok and got2 is None and st["bytes"] == 0
+        got3 = sweep.gather_eigenpairs(local, len(mesh_ids), dst=1, with_vectors=False)
+        ok = ok and ((got3 is None) if rank == 0 else all(g[1] is None and np.array_equal(g[0], a[0]) for g, a in zip(got3, got)))
         q.put((rank, bool(ok)))
     finally:
         dist.destroy_process_group()
@@ -184,3 +188,22 @@ def test_sweep_scalar_reuses_context():
         w, v, cnt = ws.solve_waveguide(mesh, pr.wl, pr.IOR_dict, Nmax=5)
         assert np.max(np.abs(r.w - w) / np.abs(w)) < 1e-11
         assert r.mode_count == cnt
+
+
+@pytest.mark.gpu
+def test_sweep_reports_a_failing_problem_and_finishes_the_rest():
+    """error code + partial results per problem.  One poisoned problem (NaN wavelength -> NaN
+    matrix) fails on its own; its neighbours -- same mesh, same lanes -- are solved."""
+    import wavesolve_b200 as ws
+    mg = ws.meshgen
+    mesh = mg.fiber_disc(4000, order=1, seed=3)
+    ws.get_unique_edges(mesh)
+    probs = [sweep.SweepProblem(0, wl, mg.FIBER_IOR) for wl in (1.5, float("nan"), 1.6, 1.55)]
+    for lanes in (1, 4):
+        res = sweep.solve_sweep([mesh], probs, Nmax=4, kind="vector", lanes=lanes)
+        assert [r.rc == 0 for r in res] == [True, False, True, True]
+        assert np.all(np.isnan(res[1].w)) and res[1].mode_count == 0 and "error" in res[1].info
+        for r, pr in zip(res, probs):
+            if r.rc == 0:
+                w, v, cnt = ws.solve_waveguide_vec(mesh, pr.wl, pr.IOR_dict, Nmax=4, verbose=False)
+                assert np.max(np.abs(np.sqrt(r.w) - np.sqrt(w.real)) / np.sqrt(w.real)) < 1e-10 and r.mode_count == cnt

@@ -50,12 +50,13 @@ for _ in range(50):
 torch.cuda.synchronize()
 out["solve_ms"] = (time.perf_counter() - t0) / 50 * 1e3
 ctx.close()
-meshes = [mg.lantern_cross_section(ne, order=1, seed=10 + i, r_clad_bundle=float(r)) for i, r in enumerate(np.linspace(9, 16, 2))]
+nm = int(os.environ.get("MESHES", "2"))
+meshes = [mg.lantern_cross_section(ne, order=1, seed=10 + i, r_clad_bundle=float(r)) for i, r in enumerate(np.linspace(9, 16, nm))]
 for m in meshes:
     ws.get_unique_edges(m)
-probs = sweep.problem_grid(2, np.linspace(1.0, 1.8, 16), ior)
-sweep.solve_sweep(meshes[:1], probs[:2], Nmax=10, kind="vector")
-for lanes in [int(x) for x in os.environ.get("LANES", "1,2,4").split(",")]:
+probs = sweep.problem_grid(nm, np.linspace(1.0, 1.8, 16), ior)
+sweep.solve_sweep(meshes[:1], probs[:16], Nmax=10, kind="vector", lanes=16, gather=False)
+for lanes in [int(x) for x in os.environ.get("LANES", "1,2,4,8").split(",")]:
     torch.cuda.synchronize(); t0 = time.perf_counter()
     res = sweep.solve_sweep(meshes, probs, Nmax=10, kind="vector", lanes=lanes, gather=False)
     torch.cuda.synchronize()

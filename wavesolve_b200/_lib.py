@@ -20,6 +20,15 @@ c_i64 = C.c_int64
 c_int = C.c_int
 c_vp = C.c_void_p
 
+class EigJob(C.Structure):
+    """``ws_eig_job`` of include/wavesolve_b200.h (one eigenproblem of ``ws_eig_solve_batch``)."""
+    _fields_ = [("pattern", C.c_void_p), ("solver", C.c_void_p), ("B_vals", C.c_void_p), ("sigma", C.c_double),
+                ("kind", C.c_int), ("nev", C.c_int), ("ncv", C.c_int), ("maxit", C.c_int), ("tol", C.c_double),
+                ("seed", C.c_uint64), ("edges", C.c_void_p), ("xy", C.c_void_p), ("Ntt", C.c_int64),
+                ("w", C.c_void_p), ("V", C.c_void_p), ("stream", C.c_void_p), ("resid", C.c_void_p),
+                ("workspace", C.c_void_p), ("info", C.c_int64 * 5), ("rc", C.c_int), ("error", C.c_char * 228)]
+
+
 _SIGNATURES = {
     "ws_version": (c_int, []),
     "ws_last_error": (C.c_char_p, []),
@@ -49,11 +58,17 @@ _SIGNATURES = {
     "ws_solver_check": (c_int, [c_vp, c_int, c_vp]),
     "ws_solver_stats": (c_int, [c_vp, c_vp, c_vp]),
     "ws_solver_quality": (c_int, [c_vp, c_vp, c_vp]),
+    "ws_solver_set_overlap": (c_int, [c_vp, c_int]),
     "ws_solver_destroy": (c_int, [c_vp]),
     "ws_assemble_vector_qd": (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, C.c_double, c_vp, c_vp, c_int, c_int, c_vp]),
     "ws_eig_solve": (c_int, [c_vp, c_vp, c_vp, C.c_double, c_int, c_int, c_int, C.c_double, c_int, C.c_uint64,
                              c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_int, c_vp]),
     "ws_host_eig_general": (c_int, [c_int, c_vp, c_vp, c_vp, c_vp, c_int]),
+    "ws_eig_solve_batch": (c_int, [c_vp, c_int, c_int]),
+    "ws_eig_workspace_create": (c_int, [C.POINTER(c_vp)]),
+    "ws_eig_workspace_destroy": (c_int, [c_vp]),
+    "ws_solver_factor_begin": (c_int, [c_vp, c_vp, c_vp, C.c_double, c_int, c_vp]),
+    "ws_solver_factor_end": (c_int, [c_vp, c_int, c_vp]),
     "ws_locator_create": (c_int, [c_vp, c_vp, c_i64, c_int, C.c_double, C.c_double, C.c_double, C.c_double,
                                   C.POINTER(c_vp), c_int, c_vp]),
     "ws_locator_destroy": (c_int, [c_vp]),

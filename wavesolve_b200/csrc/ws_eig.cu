@@ -19,6 +19,7 @@
 #include <cmath>
 #include <complex>
 #include <cstdlib>
+#include <memory>
 #include <numeric>
 
 #include "ws_solver.cuh"
@@ -1197,105 +1198,139 @@ static void eig_solve_block2(const ws_pattern* p, ws_solver* s, const double* B_
                                                     " eigenpairs converged in " + std::to_string(restarts) + " restarts");
 }
 
-int ws_eig_solve(const ws_pattern* p, ws_solver* s, const double* B_vals, double sigma, int kind, int nev, int ncv,
-                 double tol, int maxit, uint64_t seed, const int32_t* edges, const double* xy, int64_t Ntt,
-                 double* w_out, double* V_out, int64_t* h_info, double* h_resid, int device, void* stream) {
-    WS_API_BEGIN
-    WS_REQUIRE(p && s && B_vals && w_out && V_out, "null pointer");
-    WS_REQUIRE(kind == 0 || kind == 1 || kind == 2,
-               "kind must be 0 (B-orthogonal, symmetric), 1 (Euclidean, non-symmetric) or 2 (as 1, block size 2)");
-    const bool want_block = kind == 2;
-    if (kind == 2) kind = 1;
-    const int64_t N = p->N;
-    WS_REQUIRE(nev >= 1 && nev < N - 1, "1 <= nev < N-1");
-    // scipy's default is ncv = max(2k+1, 20) (arpack.py); with the convergence test at tol = eps that
-    // size sits on a cliff for these problems (86 or 97 operator applications for k = 10 depending on
-    // rounding noise), three more vectors make it 80 for every mesh tried (tools/ncv_sweep.py)
-    // Wide bases: the reference's own calls go up to Nmax = 100 (lantern-demo.ipynb cell 2; cell 4 sweeps with
-    // Nmax = 80), i.e. ncv = 204; beyond MAX_NCV the default is clamped (fewer spare directions, more restarts).
-    if (ncv <= 0) ncv = std::min(std::max(2 * nev + 4, 20), std::max(MAX_NCV, nev + 2));
-    ncv = (int)std::min<int64_t>(ncv, N);
-    WS_REQUIRE(ncv > nev + 1 && ncv <= MAX_NCV, "nev+1 < ncv <= 256 (Nmax <= 254)");
-    WS_REQUIRE(kind == 0 || (edges && xy), "the vector eigensolver needs the edge table and coordinates");
-    if (tol <= 0) tol = 2.220446049250313e-16;          // ARPACK: tol=0 -> machine epsilon
-    if (maxit <= 0) maxit = 300;
-    DeviceGuard g(device);
-    cudaStream_t st = (cudaStream_t)stream;
-    {
-        static PerDeviceOnce configure;
-        configure([] { WS_CUDA(cudaFuncSetAttribute(k_update_dots, cudaFuncAttributeMaxDynamicSharedMemorySize, (MAXV + 1) * UD_TILE * (int)sizeof(double))); });
+// ---------------------------------------------------------------------------------------------
+// The single-vector iteration as a RESUMABLE object.  One restart cycle = (enqueue the Arnoldi steps and
+// the copy of the projected matrix) / (wait, analyse on the host, enqueue the restart rotation).  Nothing
+// between the two halves blocks the host, so one host thread can drive several eigenproblems on several
+// streams in lockstep (ws_eig_solve_batch): the kernels of a ~50k-triangle problem are a chain of small
+// dependent launches that fills a fraction of a B200, and independent problems on other streams fill the
+// rest (measured: 4 streams, 3.2 solves in the time of one).  ws_eig_solve is the same object driven alone.
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+struct PinnedBuf {
+    double* p = nullptr;
+    size_t n = 0;
+    void alloc(size_t n_) {
+        release();
+        n = n_;
+        if (n) WS_CUDA(cudaMallocHost((void**)&p, n * sizeof(double)));
     }
-    {
-        static const int block = getenv("WS_EIG_BLOCK") ? atoi(getenv("WS_EIG_BLOCK")) : 1;
-        if (kind == 1 && (block == 2 || want_block) && N > 4 * ncv) {
-            int mb = ncv + (ncv & 1);
-            if (mb + 2 >= MAXV) mb -= 2;
-            WS_REQUIRE(mb + 2 < MAXV && mb > nev + 1, "the block-2 iteration (kind 2) handles bases below 62 vectors (Nmax <= 28)");
-            eig_solve_block2(p, s, B_vals, sigma, nev, mb, tol, maxit, seed, edges, xy, Ntt, w_out, V_out, h_info, h_resid,
-                             device, st);
-            return WS_OK;
-        }
+    void release() {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        n = 0;
     }
-    const int m = ncv;
+    ~PinnedBuf() { release(); }
+};
+
+struct GraphSet {
+    std::vector<cudaGraphExec_t> exec;
+    cudaStream_t cap = nullptr;
+    ~GraphSet() {
+        for (auto e : exec)
+            if (e) cudaGraphExecDestroy(e);
+        if (cap) cudaStreamDestroy(cap);
+    }
+};
+
+struct EigRun {
+    // problem
+    const ws_pattern* p = nullptr;
+    ws_solver* s = nullptr;
+    const double* B_vals = nullptr;
+    double sigma = 0.0;
+    int kind = 0, nev = 0, m = 0, maxit = 0, device = 0;
+    double tol = 0.0;
+    uint64_t seed = 0;
+    const int32_t* edges = nullptr;
+    const double* xy = nullptr;
+    int64_t Ntt = 0, N = 0;
+    double* w_out = nullptr;
+    double* V_out = nullptr;
+    cudaStream_t st = nullptr;
+    // device work space
     EigWork W;
-    W.N = N; W.ncv = m; W.st = st;
-    W.nchunks = ceil_div(N, DOT_CHUNK);
-    W.V.alloc((size_t)(m + 1) * N, st);
-    if (kind == 0) W.Z.alloc((size_t)(m + 1) * N, st);
-    W.w.alloc(N, st); W.t1.alloc(N, st); W.t2.alloc(N, st); W.t3.alloc(N, st);
-    W.partial.alloc((size_t)W.nchunks * (m + 1), st);
-    W.h.alloc(m + 1, st);
-    W.Hd.alloc((size_t)(m + 1) * m, st);
-    W.nrm.alloc(m + 1, st);
-    W.Q.alloc((size_t)m * m, st);
-    double* V = W.V.get();
-    double* Z = kind == 0 ? W.Z.get() : V;
-    const int T = 256;
-    const int nb = ceil_div(N, T);
-    // every enqueue helper takes the stream explicitly: the Arnoldi steps are recorded once into
-    // CUDA graphs (stream capture on a private stream) and replayed on the caller's stream, so an
-    // eigensolve costs ~10^2 host launches instead of ~7000 and does not depend on host latency.
-    auto solve = [&](cudaStream_t q, const double* b, double* x) {
+    GraphSet graphs;
+    bool use_graphs = true;
+    double* V = nullptr;
+    double* Z = nullptr;
+    int nb = 0;
+    static constexpr int T = 256;
+    // host state
+    PinnedBuf hH, hUp;                      // projected matrix coming back / (H, Q) going up
+    cudaEvent_t ev = nullptr;
+    std::vector<double> Hm, theta_r, theta_i, Y, resid;
+    std::vector<int> order;
+    int j0 = 0, nconv = 0, restarts = 0, kkeep = 0, ncomplex = 0;
+    int64_t nops = 1;
+    std::vector<double> wh, rh, lam_i_sorted;
+    // tracing (WS_TRACE=1: synchronises after every phase, diagnostic only; WS_TRACE=2: events around every step)
+    bool trace = false, etrace = false;
+    std::vector<cudaEvent_t> evs;
+    double wall0 = 0, tr_op = 0, tr_host = 0, tr_rot = 0, tr_t0 = 0;
+
+    ~EigRun() {
+        if (ev) cudaEventDestroy(ev);
+        for (auto e : evs) cudaEventDestroy(e);
+    }
+    static double now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+    double tick() {
+        if (!trace) return 0.0;
+        cudaStreamSynchronize(st);
+        return now();
+    }
+    void mark() {
+        if (!etrace) return;
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, st);
+        evs.push_back(e);
+    }
+
+    void solve(cudaStream_t q, const double* b, double* x) {
         int rc = ws_solver_solve(s, b, x, 1, device, (void*)q);
         if (rc) throw Error(rc, ws_last_error());
-    };
-    auto vecT = [&](cudaStream_t q, int mode, const double* in, double* out) {
+    }
+    void vecT(cudaStream_t q, int mode, const double* in, double* out) {
         int rc = ws_vector_T(p, edges, xy, Ntt, mode, in, out, device, (void*)q);
         if (rc) throw Error(rc, ws_last_error());
-    };
-    // OP applied to basis vector j -> W.w
-    auto apply_op = [&](cudaStream_t q, int j) {
+    }
+    // OP applied to an arbitrary vector x (kind 0: bx = B x must be given) -> W.w
+    void apply_op_vec(cudaStream_t q, const double* x, const double* bx) {
         if (kind == 0) {
-            solve(q, Z + (size_t)j * N, W.w.get());                    // Z_j = B v_j is carried along
+            solve(q, bx, W.w.get());
         } else {
-            spmv_launch(p, B_vals, V + (size_t)j * N, W.t1.get(), q);
+            spmv_launch(p, B_vals, x, W.t1.get(), q);
             vecT(q, 1, W.t1.get(), W.t2.get());
             solve(q, W.t2.get(), W.t3.get());
             vecT(q, 0, W.t3.get(), W.w.get());
         }
-    };
+    }
+    // OP applied to basis vector j -> W.w   (kind 0: Z_j = B v_j is carried along)
+    void apply_op(cudaStream_t q, int j) { apply_op_vec(q, V + (size_t)j * N, kind == 0 ? Z + (size_t)j * N : nullptr); }
     // normalise W.w in the inner product into basis slot j (H entry written to hslot)
-    auto normalize_into = [&](cudaStream_t q, int j, double* hslot) {
+    void normalize_into(cudaStream_t q, int j, double* hslot) {
         const double* dual = W.w.get();
         if (kind == 0) {
             spmv_launch(p, B_vals, W.w.get(), W.t1.get(), q);
             dual = W.t1.get();
         }
         dots(W, q, dual, 1, W.w.get(), W.nrm.get(), nullptr);
-        k_normalize<<<nb, T, 0, q>>>(W.w.get(), kind == 0 ? W.t1.get() : nullptr, W.nrm.get(), hslot,
-                                    V + (size_t)j * N, kind == 0 ? Z + (size_t)j * N : nullptr, N);
+        k_normalize<<<nb, T, 0, q>>>(W.w.get(), kind == 0 ? W.t1.get() : nullptr, W.nrm.get(), hslot, V + (size_t)j * N,
+                                    kind == 0 ? Z + (size_t)j * N : nullptr, N);
         count_launch(1);
-    };
-    // one Arnoldi step: w = OP v_j, CGS2 against rows 0..j (coefficients with the dual basis,
-    // update with the primal one), normalise into slot j+1
-    static const bool fuse_cgs = !(getenv("WS_NO_CGS_FUSE") && atoi(getenv("WS_NO_CGS_FUSE")));
-    auto arnoldi_step = [&](cudaStream_t q, int j) {
+    }
+    // one Arnoldi step: w = OP v_j, CGS2 against rows 0..j (coefficients with the dual basis, update with the
+    // primal one), normalise into slot j+1
+    void arnoldi_step(cudaStream_t q, int j) {
+        static const bool fuse_cgs = !(getenv("WS_NO_CGS_FUSE") && atoi(getenv("WS_NO_CGS_FUSE")));
         apply_op(q, j);
         double* Hcol = W.Hd.get() + (size_t)j * (m + 1);
         const int nv = j + 1;
         if (kind == 1 && fuse_cgs && nv + 1 <= MAXV) {
-            // Euclidean inner product (dual basis = basis): the update of pass 1 and the inner products
-            // of pass 2 share one pass over the basis -- three basis reads per step instead of four
+            // Euclidean inner product (dual basis = basis): the update of pass 1 and the inner products of pass 2
+            // share one pass over the basis -- three basis reads per step instead of four
             dots(W, q, V, nv, W.w.get(), W.h.get(), Hcol);
             k_update_dots<<<W.nchunks, 256, (size_t)(nv + 1) * UD_TILE * sizeof(double), q>>>(W.w.get(), V, N, nv, W.h.get(), N,
                                                                                          W.partial.get());
@@ -1310,21 +1345,11 @@ int ws_eig_solve(const ws_pattern* p, ws_solver* s, const double* B_vals, double
             }
         }
         normalize_into(q, j + 1, Hcol + (j + 1));
-    };
-    struct GraphSet {
-        std::vector<cudaGraphExec_t> exec;
-        cudaStream_t cap = nullptr;
-        ~GraphSet() {
-            for (auto e : exec)
-                if (e) cudaGraphExecDestroy(e);
-            if (cap) cudaStreamDestroy(cap);
-        }
-    } graphs;
-    graphs.exec.assign(m, nullptr);
-    const char* nog = getenv("WS_NO_GRAPH");
-    const bool use_graphs = !(nog && atoi(nog));
-    if (use_graphs) WS_CUDA(cudaStreamCreateWithFlags(&graphs.cap, cudaStreamNonBlocking));
-    auto run_step = [&](int j) {
+    }
+    // every enqueue helper takes the stream explicitly: the Arnoldi steps are recorded once into CUDA graphs
+    // (stream capture on a private stream) and replayed on the caller's stream, so an eigensolve costs ~10^2
+    // host launches instead of ~7000 and does not depend on host latency
+    void run_step(int j) {
         if (!use_graphs) {
             arnoldi_step(st, j);
             return;
@@ -1346,48 +1371,84 @@ int ws_eig_solve(const ws_pattern* p, ws_solver* s, const double* B_vals, double
         }
         WS_CUDA(cudaGraphLaunch(graphs.exec[j], st));
         count_launch(1);
-    };
+    }
 
-    // optional phase timing (WS_TRACE=1): synchronises after every phase, diagnostic only
-    const char* trace_env = getenv("WS_TRACE");
-    const bool trace = trace_env != nullptr && atoi(trace_env) == 1;
-    const bool etrace = trace_env != nullptr && atoi(trace_env) == 2;
-    std::vector<cudaEvent_t> evs;
-    auto mark = [&]() {
-        if (!etrace) return;
-        cudaEvent_t e;
-        cudaEventCreate(&e);
-        cudaEventRecord(e, st);
-        evs.push_back(e);
-    };
-    const double wall0 = std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
-    double tr_op = 0, tr_orth = 0, tr_norm = 0, tr_host = 0, tr_rot = 0, tr_t0 = 0;
-    auto tick = [&]() {
-        if (!trace) return 0.0;
-        cudaStreamSynchronize(st);
-        return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
-    };
-    tr_t0 = tick();
-    // ---- start vector: random, pushed once through OP (stays in range(OP), as ARPACK does)
-    k_random<<<nb, T, 0, st>>>(W.w.get(), N, seed ? seed : 0x5DEECE66Dull);
-    count_launch(1);
-    normalize_into(st, 0, nullptr);
-    apply_op(st, 0);
-    normalize_into(st, 0, nullptr);
-    // every kernel of a step has now run once outside stream capture, except the update:
-    k_update<<<nb, T, 0, st>>>(W.w.get(), V, N, 0, W.h.get(), N);   // nvec = 0: no-op, loads the kernel
-    WS_CUDA(cudaMemsetAsync(W.Hd.get(), 0, W.Hd.bytes(), st));
+    // What the captured step graphs and the work space depend on.  A run object kept in a ws_eig_workspace is
+    // reused as it is while this key stays the same (the wavelengths of one mesh on one sweep lane: same pattern,
+    // solver, value array, sizes), so the ~ncv graph captures / instantiations, the pinned buffers and the basis are
+    // paid once per mesh instead of once per problem.
+    struct Key {
+        const void *p = nullptr, *s = nullptr, *B = nullptr, *edges = nullptr, *xy = nullptr, *st = nullptr;
+        int64_t N = 0, Ntt = 0;
+        int kind = -1, m = 0, refine = -1;
+        bool operator==(const Key& o) const {
+            return p == o.p && s == o.s && B == o.B && edges == o.edges && xy == o.xy && st == o.st && N == o.N && Ntt == o.Ntt &&
+                   kind == o.kind && m == o.m && refine == o.refine;
+        }
+    } key;
 
-    std::vector<double> Hh((size_t)(m + 1) * m, 0.0);    // column-major (m+1) x m, as on the device
-    std::vector<double> theta_r(m), theta_i(m), Y, resid(m, 0.0);
-    std::vector<int> order(m);
-    int j0 = 0, nconv = 0, restarts = 0;
-    int64_t nops = 1;
-    bool done = false;
-    const double eps23 = std::pow(2.220446049250313e-16, 2.0 / 3.0);
-    std::vector<double> Qh;
-    int kkeep = 0;
-    while (!done) {
+    // allocate (or keep) the work space, then build the start vector (random, pushed once through OP: stays in
+    // range(OP), as ARPACK does)
+    void init() {
+        N = p->N;
+        int64_t qi[4] = {0, 0, 0, 0};
+        ws_solver_quality(s, qi, nullptr);
+        Key k2;
+        k2.p = p; k2.s = s; k2.B = B_vals; k2.edges = edges; k2.xy = xy; k2.st = st; k2.N = N; k2.Ntt = Ntt; k2.kind = kind; k2.m = m;
+        k2.refine = (int)qi[1];
+        if (!(k2 == key)) {
+            for (auto& e : graphs.exec)
+                if (e) cudaGraphExecDestroy(e);
+            W.N = N; W.ncv = m; W.st = st;
+            W.nchunks = ceil_div(N, DOT_CHUNK);
+            W.V.alloc((size_t)(m + 1) * N, st);
+            if (kind == 0) W.Z.alloc((size_t)(m + 1) * N, st);
+            else W.Z.release();
+            W.w.alloc(N, st); W.t1.alloc(N, st); W.t2.alloc(N, st); W.t3.alloc(N, st);
+            W.partial.alloc((size_t)W.nchunks * (m + 1), st);
+            W.h.alloc(m + 1, st);
+            W.Hd.alloc((size_t)(m + 1) * m, st);
+            W.nrm.alloc(m + 1, st);
+            W.Q.alloc((size_t)m * m, st);
+            hH.alloc((size_t)(m + 1) * m);
+            hUp.alloc((size_t)(m + 1) * m + (size_t)m * m);
+            if (!ev) WS_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+            graphs.exec.assign(m, nullptr);
+            key = k2;
+        }
+        V = W.V.get();
+        Z = kind == 0 ? W.Z.get() : V;
+        nb = ceil_div(N, T);
+        j0 = nconv = restarts = kkeep = ncomplex = 0;
+        nops = 1;
+        tr_op = tr_host = tr_rot = 0;
+        for (auto e : evs) cudaEventDestroy(e);
+        evs.clear();
+        const char* nog = getenv("WS_NO_GRAPH");
+        use_graphs = !(nog && atoi(nog));
+        if (use_graphs && !graphs.cap) WS_CUDA(cudaStreamCreateWithFlags(&graphs.cap, cudaStreamNonBlocking));
+        const char* trace_env = getenv("WS_TRACE");
+        trace = trace_env != nullptr && atoi(trace_env) == 1;
+        etrace = trace_env != nullptr && atoi(trace_env) == 2;
+        wall0 = now();
+        tr_t0 = tick();
+        k_random<<<nb, T, 0, st>>>(W.w.get(), N, seed ? seed : 0x5DEECE66Dull);
+        count_launch(1);
+        normalize_into(st, 0, nullptr);
+        apply_op(st, 0);
+        normalize_into(st, 0, nullptr);
+        // every kernel of a step has now run once outside stream capture, except the update:
+        k_update<<<nb, T, 0, st>>>(W.w.get(), V, N, 0, W.h.get(), N);   // nvec = 0: no-op, loads the kernel
+        WS_CUDA(cudaMemsetAsync(W.Hd.get(), 0, W.Hd.bytes(), st));
+        theta_r.assign(m, 0.0);
+        theta_i.assign(m, 0.0);
+        resid.assign(m, 0.0);
+        order.assign(m, 0);
+        Hm.assign((size_t)m * m, 0.0);
+    }
+
+    // first half of a restart cycle: steps j0 .. m-1, projected matrix -> pinned host memory; never blocks
+    void enqueue_cycle() {
         for (int j = j0; j < m; ++j) {
             double ta = tick();
             mark();
@@ -1396,13 +1457,18 @@ int ws_eig_solve(const ws_pattern* p, ws_solver* s, const double* B_vals, double
             ++nops;
             tr_op += tick() - ta;
         }
+        WS_CUDA(cudaMemcpyAsync(hH.p, W.Hd.get(), (size_t)(m + 1) * m * sizeof(double), cudaMemcpyDeviceToHost, st));
+        WS_CUDA(cudaEventRecord(ev, st));
+    }
+
+    // second half: wait for the cycle, Ritz analysis; returns true when the iteration is over, otherwise the thick
+    // restart (host) and its basis rotation (enqueued) have been set up for the next cycle
+    bool finish_cycle() {
         double th0 = tick();
-        WS_CUDA(cudaMemcpyAsync(Hh.data(), W.Hd.get(), Hh.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
-        WS_CUDA(cudaStreamSynchronize(st));
+        WS_CUDA(cudaEventSynchronize(ev));
         WS_CUDA(cudaGetLastError());
+        const double* Hh = hH.p;                         // column-major (m+1) x m, as on the device
         const double beta_m = Hh[(size_t)(m - 1) * (m + 1) + m];
-        // projected matrix, row-major m x m
-        std::vector<double> Hm((size_t)m * m);
         for (int i = 0; i < m; ++i)
             for (int j = 0; j < m; ++j) Hm[(size_t)i * m + j] = Hh[(size_t)j * (m + 1) + i];
         bool finite = std::isfinite(beta_m);
@@ -1426,12 +1492,12 @@ int ws_eig_solve(const ws_pattern* p, ws_solver* s, const double* B_vals, double
         std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return theta_r[a] < theta_r[b]; });
         // Ritz residual estimates |beta_m * (last component of the unit eigenvector)|
         auto colnorm = [&](int c, bool cplx) {
-            double s = 0.0;
+            double sacc = 0.0;
             for (int i = 0; i < m; ++i) {
-                s += Y[(size_t)i * m + c] * Y[(size_t)i * m + c];
-                if (cplx) s += Y[(size_t)i * m + c + 1] * Y[(size_t)i * m + c + 1];
+                sacc += Y[(size_t)i * m + c] * Y[(size_t)i * m + c];
+                if (cplx) sacc += Y[(size_t)i * m + c + 1] * Y[(size_t)i * m + c + 1];
             }
-            return std::sqrt(s);
+            return std::sqrt(sacc);
         };
         auto ritz_res = [&](int c) {
             if (theta_i[c] == 0.0) return std::fabs(beta_m * Y[(size_t)(m - 1) * m + c]) / colnorm(c, false);
@@ -1439,6 +1505,7 @@ int ws_eig_solve(const ws_pattern* p, ws_solver* s, const double* B_vals, double
             const double lr = Y[(size_t)(m - 1) * m + c0], li = Y[(size_t)(m - 1) * m + c0 + 1];
             return std::fabs(beta_m) * std::sqrt(lr * lr + li * li) / colnorm(c0, true);
         };
+        const double eps23 = std::pow(2.220446049250313e-16, 2.0 / 3.0);
         nconv = 0;
         for (int i = 0; i < nev; ++i) {
             const int c = order[i];
@@ -1447,10 +1514,7 @@ int ws_eig_solve(const ws_pattern* p, ws_solver* s, const double* B_vals, double
             if (resid[i] <= tol * std::max(eps23, mag)) ++nconv;
         }
         ++restarts;
-        if (nconv >= nev || restarts >= maxit) {
-            done = true;
-            break;
-        }
+        if (nconv >= nev || restarts >= maxit) return true;
         // ---- thick restart: keep k Ritz directions (ARPACK-style: more as they converge)
         static const int keep_policy = getenv("WS_EIG_KEEP") ? atoi(getenv("WS_EIG_KEEP")) : 0;
         int k = nev + std::min(nconv, (m - nev) / 2);
@@ -1479,7 +1543,7 @@ int ws_eig_solve(const ws_pattern* p, ws_solver* s, const double* B_vals, double
             k = (int)keep.size();
         }
         // orthonormal basis Q (m x k) of the kept invariant subspace (modified Gram-Schmidt, twice)
-        Qh.assign((size_t)m * k, 0.0);
+        std::vector<double> Qh((size_t)m * k, 0.0);
         for (int i = 0; i < k; ++i) {
             const int c = keep[i];
             for (int r = 0; r < m; ++r) Qh[(size_t)r * k + i] = Y[(size_t)r * m + c];
@@ -1499,91 +1563,103 @@ int ws_eig_solve(const ws_pattern* p, ws_solver* s, const double* B_vals, double
             for (int r = 0; r < m; ++r) Qh[(size_t)r * k + kk] = Qh[(size_t)r * k + i] / nn;
             ++kk;
         }
-        // compact to m x kk row-major
-        std::vector<double> Qc((size_t)m * kk);
+        kkeep = kk;
+        // (H, Q) of the restarted factorisation go up through pinned memory: [Q^T H Q ; beta_m * (last row of Q)]
+        double* Hup = hUp.p;
+        double* Qc = hUp.p + (size_t)(m + 1) * m;        // m x kk row-major
         for (int r = 0; r < m; ++r)
             for (int i = 0; i < kk; ++i) Qc[(size_t)r * kk + i] = Qh[(size_t)r * k + i];
-        kkeep = kk;
-        // new projected matrix: [Q^T H Q ; beta_m * (last row of Q)]
-        std::vector<double> HQ((size_t)m * kk, 0.0), Tn((size_t)kk * kk, 0.0);
+        std::vector<double> HQ((size_t)m * kk, 0.0);
         for (int r = 0; r < m; ++r)
-            for (int c = 0; c < kk; ++c) {
-                double sacc = 0.0;
-                for (int q2 = 0; q2 < m; ++q2) sacc += Hm[(size_t)r * m + q2] * Qc[(size_t)q2 * kk + c];
-                HQ[(size_t)r * kk + c] = sacc;
+            for (int q2 = 0; q2 < m; ++q2) {
+                const double hv = Hm[(size_t)r * m + q2];
+                if (hv == 0.0) continue;
+                const double* qrow = Qc + (size_t)q2 * kk;
+                double* dst = HQ.data() + (size_t)r * kk;
+                for (int c = 0; c < kk; ++c) dst[c] += hv * qrow[c];
             }
-        for (int r = 0; r < kk; ++r)
-            for (int c = 0; c < kk; ++c) {
+        std::fill(Hup, Hup + (size_t)(m + 1) * m, 0.0);
+        for (int c = 0; c < kk; ++c) {
+            for (int r = 0; r < kk; ++r) {
                 double sacc = 0.0;
                 for (int q2 = 0; q2 < m; ++q2) sacc += Qc[(size_t)q2 * kk + r] * HQ[(size_t)q2 * kk + c];
-                Tn[(size_t)r * kk + c] = sacc;
+                Hup[(size_t)c * (m + 1) + r] = sacc;
             }
-        std::fill(Hh.begin(), Hh.end(), 0.0);
-        for (int c = 0; c < kk; ++c) {
-            for (int r = 0; r < kk; ++r) Hh[(size_t)c * (m + 1) + r] = Tn[(size_t)r * kk + c];
-            Hh[(size_t)c * (m + 1) + kk] = beta_m * Qc[(size_t)(m - 1) * kk + c];
+            Hup[(size_t)c * (m + 1) + kk] = beta_m * Qc[(size_t)(m - 1) * kk + c];
         }
         double th1 = tick();
         tr_host += th1 - th0;
-        WS_CUDA(cudaMemcpyAsync(W.Hd.get(), Hh.data(), Hh.size() * sizeof(double), cudaMemcpyHostToDevice, st));
-        WS_CUDA(cudaMemcpyAsync(W.Q.get(), Qc.data(), Qc.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+        WS_CUDA(cudaMemcpyAsync(W.Hd.get(), Hup, (size_t)(m + 1) * m * sizeof(double), cudaMemcpyHostToDevice, st));
+        WS_CUDA(cudaMemcpyAsync(W.Q.get(), Qc, (size_t)m * kk * sizeof(double), cudaMemcpyHostToDevice, st));
         launch_rotate(V, N, m, kk, W.Q.get(), N, 1, nullptr, 0, st);
-        if (kind == 0)
-            launch_rotate(Z, N, m, kk, W.Q.get(), N, 1, nullptr, 0, st);
+        if (kind == 0) launch_rotate(Z, N, m, kk, W.Q.get(), N, 1, nullptr, 0, st);
         count_launch(kind == 0 ? 2 : 1);
-        WS_CUDA(cudaStreamSynchronize(st));     // Qc / Hh are host temporaries
+        // (hUp is rewritten only after the next cycle's event: that cycle is enqueued behind these copies)
         tr_rot += tick() - th1;
         j0 = kk;
+        return false;
     }
-    // ---- Ritz vectors of the nev wanted eigenvalues, ordered by descending lambda = sigma + 1/theta
-    std::vector<int> sel(order.begin(), order.begin() + nev);
-    std::vector<double> lam(nev), lam_i(nev);
-    for (int i = 0; i < nev; ++i) {
-        const std::complex<double> th(theta_r[sel[i]], theta_i[sel[i]]);
-        const std::complex<double> l = sigma + 1.0 / th;
-        lam[i] = l.real();
-        lam_i[i] = l.imag();
-    }
-    std::vector<int> ord2(nev);
-    std::iota(ord2.begin(), ord2.end(), 0);
-    std::stable_sort(ord2.begin(), ord2.end(), [&](int a, int b) { return lam[a] > lam[b]; });
-    std::vector<double> Qx((size_t)m * nev), wh(nev), rh(nev);
-    int ncomplex = 0;
-    for (int i = 0; i < nev; ++i) {
-        const int c = sel[ord2[i]];
-        wh[i] = lam[ord2[i]];
-        rh[i] = resid[ord2[i]];
-        if (lam_i[ord2[i]] != 0.0) ++ncomplex;
-        const int c0 = theta_i[c] < 0 ? c - 1 : c;    // complex pair: return the real part
-        double nn = 0.0;
-        for (int r = 0; r < m; ++r) nn += Y[(size_t)r * m + c0] * Y[(size_t)r * m + c0];
-        nn = std::sqrt(nn);
-        for (int r = 0; r < m; ++r) Qx[(size_t)r * nev + i] = Y[(size_t)r * m + c0] / nn;
-    }
-    WS_CUDA(cudaMemcpyAsync(W.Q.get(), Qx.data(), Qx.size() * sizeof(double), cudaMemcpyHostToDevice, st));
-    launch_rotate(V, N, m, nev, W.Q.get(), N, 0, V_out, N, st);
-    count_launch(1);
-    if (kind == 1) {
-        // unit 2-norm rows (what ARPACK's dneupd returns)
+
+    // Ritz vectors of the nev wanted eigenvalues, ordered by descending lambda = sigma + 1/theta; enqueued, no sync
+    void enqueue_results() {
+        std::vector<int> sel(order.begin(), order.begin() + nev);
+        std::vector<double> lam(nev), lam_i(nev);
         for (int i = 0; i < nev; ++i) {
-            dots(W, st, V_out + (size_t)i * N, 1, V_out + (size_t)i * N, W.nrm.get() + i, nullptr);
+            const std::complex<double> th(theta_r[sel[i]], theta_i[sel[i]]);
+            const std::complex<double> l = sigma + 1.0 / th;
+            lam[i] = l.real();
+            lam_i[i] = l.imag();
         }
-        k_scale_rows<<<nb, T, 0, st>>>(V_out, N, nev, W.nrm.get(), N);
+        std::vector<int> ord2(nev);
+        std::iota(ord2.begin(), ord2.end(), 0);
+        std::stable_sort(ord2.begin(), ord2.end(), [&](int a, int b) { return lam[a] > lam[b]; });
+        double* Qx = hUp.p + (size_t)(m + 1) * m;        // m x nev row-major
+        double* whp = hUp.p;                              // nev eigenvalues
+        wh.assign(nev, 0.0);
+        rh.assign(nev, 0.0);
+        lam_i_sorted.assign(nev, 0.0);
+        ncomplex = 0;
+        for (int i = 0; i < nev; ++i) {
+            const int c = sel[ord2[i]];
+            wh[i] = whp[i] = lam[ord2[i]];
+            rh[i] = resid[ord2[i]];
+            lam_i_sorted[i] = lam_i[ord2[i]];
+            if (lam_i[ord2[i]] != 0.0) ++ncomplex;
+            const int c0 = theta_i[c] < 0 ? c - 1 : c;    // complex pair: return the real part
+            double nn = 0.0;
+            for (int r = 0; r < m; ++r) nn += Y[(size_t)r * m + c0] * Y[(size_t)r * m + c0];
+            nn = std::sqrt(nn);
+            for (int r = 0; r < m; ++r) Qx[(size_t)r * nev + i] = Y[(size_t)r * m + c0] / nn;
+        }
+        WS_CUDA(cudaMemcpyAsync(W.Q.get(), Qx, (size_t)m * nev * sizeof(double), cudaMemcpyHostToDevice, st));
+        launch_rotate(V, N, m, nev, W.Q.get(), N, 0, V_out, N, st);
         count_launch(1);
+        if (kind == 1) {
+            // unit 2-norm rows (what ARPACK's dneupd returns)
+            for (int i = 0; i < nev; ++i) dots(W, st, V_out + (size_t)i * N, 1, V_out + (size_t)i * N, W.nrm.get() + i, nullptr);
+            k_scale_rows<<<nb, T, 0, st>>>(V_out, N, nev, W.nrm.get(), N);
+            count_launch(1);
+        }
+        WS_CUDA(cudaMemcpyAsync(w_out, whp, nev * sizeof(double), cudaMemcpyHostToDevice, st));
     }
-    WS_CUDA(cudaMemcpyAsync(w_out, wh.data(), nev * sizeof(double), cudaMemcpyHostToDevice, st));
-    WS_CUDA(cudaStreamSynchronize(st));
-    WS_CUDA(cudaGetLastError());
-    {
-        int rc = ws_solver_check(s, device, (void*)st);
-        if (rc) throw Error(rc, ws_last_error());
-    }
-    // ---- true residuals of the returned pairs, || OP x - theta x || / (|theta| ||x||), with OP applied through
-    // the (refined) solves.  The Ritz estimates above are statements about the operator the iteration saw; when
-    // the factorisation needed static pivots or refinement (interior shifts) the returned pairs are re-checked
-    // against a fresh application, and the call fails rather than return pairs that miss 1e-9.
-    // WS_EIG_VERIFY=1 / 0 forces / disables the check.
-    {
+
+    // wait for the results, solver sanity, true-residual check; fills the caller's diagnostics; throws on failure
+    void finish(int64_t* h_info, double* h_resid) {
+        WS_CUDA(cudaStreamSynchronize(st));
+        WS_CUDA(cudaGetLastError());
+        {
+            int rc = ws_solver_check(s, device, (void*)st);
+            if (rc) throw Error(rc, ws_last_error());
+        }
+        if (h_info) {
+            h_info[0] = nconv; h_info[1] = nops; h_info[2] = restarts; h_info[3] = ncomplex; h_info[4] = kkeep;
+        }
+        if (h_resid) std::copy(rh.begin(), rh.end(), h_resid);
+        // ---- true residuals of the returned pairs, || OP x - theta x || / (|theta| ||x||), with OP applied through
+        // the (refined) solves.  The Ritz estimates are statements about the operator the iteration saw; when the
+        // factorisation needed static pivots or refinement (interior shifts) the returned pairs are re-checked
+        // against a fresh application, and the call fails rather than return pairs that miss 1e-9.
+        // WS_EIG_VERIFY=1 / 0 forces / disables the check.
         int64_t qi[4] = {0, 0, 0, 0};
         double qd[4];
         ws_solver_quality(s, qi, qd);
@@ -1596,14 +1672,12 @@ int ws_eig_solve(const ws_pattern* p, ws_solver* s, const double* B_vals, double
             WS_CUDA(cudaMemcpyAsync(vr.get(), th.data(), nev * sizeof(double), cudaMemcpyHostToDevice, st));
             for (int i = 0; i < nev; ++i) {
                 const double* xi = V_out + (size_t)i * N;
-                spmv_launch(p, B_vals, xi, W.t1.get(), st);
+                const double* bx = nullptr;
                 if (kind == 0) {
-                    solve(st, W.t1.get(), W.w.get());
-                } else {
-                    vecT(st, 1, W.t1.get(), W.t2.get());
-                    solve(st, W.t2.get(), W.t3.get());
-                    vecT(st, 0, W.t3.get(), W.w.get());
+                    spmv_launch(p, B_vals, xi, W.t1.get(), st);
+                    bx = W.t1.get();
                 }
+                apply_op_vec(st, xi, bx);
                 k_update<<<nb, T, sizeof(double), st>>>(W.w.get(), xi, N, 1, vr.get() + i, N);
                 count_launch(1);
                 dots(W, st, W.w.get(), 1, W.w.get(), vr.get() + nev + i, nullptr);
@@ -1614,7 +1688,7 @@ int ws_eig_solve(const ws_pattern* p, ws_solver* s, const double* B_vals, double
             double worst = 0.0;
             int worst_i = -1;
             for (int i = 0; i < nev; ++i) {
-                if (lam_i[ord2[i]] != 0.0) continue;           // complex pair: only the real part is returned
+                if (lam_i_sorted[i] != 0.0) continue;           // complex pair: only the real part is returned
                 const double r = std::sqrt(back[nev + i] / back[2 * nev + i]) / std::fabs(th[i]);
                 if (!(r <= worst)) { worst = r; worst_i = i; }
             }
@@ -1625,31 +1699,183 @@ int ws_eig_solve(const ws_pattern* p, ws_solver* s, const double* B_vals, double
                 throw Error(WS_ERR_NUMERIC, "eigenpair " + std::to_string(worst_i) + " fails the residual check against the operator (" +
                                                 std::to_string(worst) + "): the factorisation at this shift is not accurate enough");
         }
-    }
-    if (etrace) {
-        cudaStreamSynchronize(st);
-        const double wall1 = std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
-        double op_ms = 0, mx = 0, mn = 1e30, span = 0;
-        for (size_t i = 0; i + 1 < evs.size(); i += 2) {
-            float ms = 0;
-            cudaEventElapsedTime(&ms, evs[i], evs[i + 1]);
-            op_ms += ms; mx = std::max<double>(mx, ms); mn = std::min<double>(mn, ms);
+        if (etrace) {
+            const double wall1 = now();
+            double op_ms = 0, mx = 0, mn = 1e30, span = 0;
+            for (size_t i = 0; i + 1 < evs.size(); i += 2) {
+                float ms = 0;
+                cudaEventElapsedTime(&ms, evs[i], evs[i + 1]);
+                op_ms += ms; mx = std::max<double>(mx, ms); mn = std::min<double>(mn, ms);
+            }
+            if (evs.size() >= 2) { float ms = 0; cudaEventElapsedTime(&ms, evs.front(), evs.back()); span = ms; }
+            fprintf(stderr, "[ws_eig etrace] wall %.1f ms, first-op-start..last-op-end %.1f ms, sum(op) %.1f ms over %zu ops (min %.3f max %.3f)\n",
+                    (wall1 - wall0) * 1e3, span, op_ms, evs.size() / 2, mn, mx);
         }
-        if (evs.size() >= 2) { float ms = 0; cudaEventElapsedTime(&ms, evs.front(), evs.back()); span = ms; }
-        fprintf(stderr, "[ws_eig etrace] wall %.1f ms, first-op-start..last-op-end %.1f ms, sum(op) %.1f ms over %zu ops (min %.3f max %.3f)\n",
-                (wall1 - wall0) * 1e3, span, op_ms, evs.size() / 2, mn, mx);
-        for (auto e : evs) cudaEventDestroy(e);
+        if (trace)
+            fprintf(stderr, "[ws_eig] kind=%d N=%lld ops=%lld restarts=%d total=%.1f ms: op=%.1f host=%.1f rotate=%.1f\n",
+                    kind, (long long)N, (long long)nops, restarts, (tick() - tr_t0) * 1e3, tr_op * 1e3, tr_host * 1e3, tr_rot * 1e3);
+        if (nconv < nev) throw Error(WS_ERR_NOCONV, "eigensolver: " + std::to_string(nconv) + " of " + std::to_string(nev) +
+                                                        " eigenpairs converged in " + std::to_string(restarts) + " restarts");
     }
-    if (trace)
-        fprintf(stderr, "[ws_eig] kind=%d N=%lld ops=%lld restarts=%d total=%.1f ms: op=%.1f orth=%.1f norm=%.1f host=%.1f rotate=%.1f\n",
-                kind, (long long)N, (long long)nops, restarts, (tick() - tr_t0) * 1e3, tr_op * 1e3, tr_orth * 1e3, tr_norm * 1e3,
-                tr_host * 1e3, tr_rot * 1e3);
-    if (h_info) {
-        h_info[0] = nconv; h_info[1] = nops; h_info[2] = restarts; h_info[3] = ncomplex; h_info[4] = kkeep;
+};
+
+// argument checks and defaults shared by the single and the batched entry point; returns false when the problem goes
+// to the block-2 iteration instead
+void eig_configure(EigRun& R, const ws_pattern* p, ws_solver* s, const double* B_vals, double sigma, int kind, int nev, int ncv,
+                   double tol, int maxit, uint64_t seed, const int32_t* edges, const double* xy, int64_t Ntt, double* w_out,
+                   double* V_out, int device, cudaStream_t st) {
+    WS_REQUIRE(p && s && B_vals && w_out && V_out, "null pointer");
+    WS_REQUIRE(kind == 0 || kind == 1, "kind must be 0 (B-orthogonal, symmetric) or 1 (Euclidean, non-symmetric)");
+    const int64_t N = p->N;
+    WS_REQUIRE(nev >= 1 && nev < N - 1, "1 <= nev < N-1");
+    // scipy's default is ncv = max(2k+1, 20) (arpack.py); with the convergence test at tol = eps that size sits on a
+    // cliff for these problems (86 or 97 operator applications for k = 10 depending on rounding noise), three more
+    // vectors make it 80 for every mesh tried (tools/ncv_sweep.py).
+    // Wide bases: the reference's own calls go up to Nmax = 100 (lantern-demo.ipynb cell 2; cell 4 sweeps with
+    // Nmax = 80), i.e. ncv = 204; beyond MAX_NCV the default is clamped (fewer spare directions, more restarts).
+    if (ncv <= 0) ncv = std::min(std::max(2 * nev + 4, 20), std::max(MAX_NCV, nev + 2));
+    ncv = (int)std::min<int64_t>(ncv, N);
+    WS_REQUIRE(ncv > nev + 1 && ncv <= MAX_NCV, "nev+1 < ncv <= 256 (Nmax <= 254)");
+    WS_REQUIRE(kind == 0 || (edges && xy), "the vector eigensolver needs the edge table and coordinates");
+    if (tol <= 0) tol = 2.220446049250313e-16;          // ARPACK: tol=0 -> machine epsilon
+    if (maxit <= 0) maxit = 300;
+    {
+        static PerDeviceOnce configure;
+        configure([] { WS_CUDA(cudaFuncSetAttribute(k_update_dots, cudaFuncAttributeMaxDynamicSharedMemorySize, (MAXV + 1) * UD_TILE * (int)sizeof(double))); });
     }
-    if (h_resid) std::copy(rh.begin(), rh.end(), h_resid);
-    if (nconv < nev) throw Error(WS_ERR_NOCONV, "eigensolver: " + std::to_string(nconv) + " of " + std::to_string(nev) +
-                                                    " eigenpairs converged in " + std::to_string(restarts) + " restarts");
+    R.p = p; R.s = s; R.B_vals = B_vals; R.sigma = sigma; R.kind = kind; R.nev = nev; R.m = ncv; R.tol = tol; R.maxit = maxit;
+    R.seed = seed; R.edges = edges; R.xy = xy; R.Ntt = Ntt; R.w_out = w_out; R.V_out = V_out; R.device = device; R.st = st;
+}
+
+}  // namespace
+
+struct ws_eig_workspace {
+    EigRun run;
+};
+
+int ws_eig_solve(const ws_pattern* p, ws_solver* s, const double* B_vals, double sigma, int kind, int nev, int ncv,
+                 double tol, int maxit, uint64_t seed, const int32_t* edges, const double* xy, int64_t Ntt,
+                 double* w_out, double* V_out, int64_t* h_info, double* h_resid, int device, void* stream) {
+    WS_API_BEGIN
+    WS_REQUIRE(kind == 0 || kind == 1 || kind == 2,
+               "kind must be 0 (B-orthogonal, symmetric), 1 (Euclidean, non-symmetric) or 2 (as 1, block size 2)");
+    DeviceGuard g(device);
+    cudaStream_t st = (cudaStream_t)stream;
+    {
+        static const int block = getenv("WS_EIG_BLOCK") ? atoi(getenv("WS_EIG_BLOCK")) : 1;
+        if (kind == 2 || (kind == 1 && block == 2)) {
+            WS_REQUIRE(p && s && B_vals && w_out && V_out && edges && xy, "null pointer");
+            int nc = ncv <= 0 ? std::max(2 * nev + 4, 20) : ncv;
+            nc = (int)std::min<int64_t>(nc, p->N);
+            if (p->N > 4 * nc) {
+                int mb = nc + (nc & 1);
+                if (mb + 2 >= MAXV) mb -= 2;
+                WS_REQUIRE(mb + 2 < MAXV && mb > nev + 1, "the block-2 iteration (kind 2) handles bases below 62 vectors (Nmax <= 28)");
+                if (tol <= 0) tol = 2.220446049250313e-16;
+                if (maxit <= 0) maxit = 300;
+                eig_solve_block2(p, s, B_vals, sigma, nev, mb, tol, maxit, seed, edges, xy, Ntt, w_out, V_out, h_info, h_resid,
+                                 device, st);
+                return WS_OK;
+            }
+            kind = 1;
+        }
+    }
+    EigRun R;
+    eig_configure(R, p, s, B_vals, sigma, kind, nev, ncv, tol, maxit, seed, edges, xy, Ntt, w_out, V_out, device, st);
+    R.init();
+    do {
+        R.enqueue_cycle();
+    } while (!R.finish_cycle());
+    R.enqueue_results();
+    R.finish(h_info, h_resid);
+    WS_API_END
+}
+
+// Several eigenproblems in lockstep, one per stream, driven by this one host thread (see EigRun).  A job that fails
+// gets its own rc / message; the others run to the end.  Returns WS_OK unless the arguments themselves are bad.
+int ws_eig_solve_batch(ws_eig_job* jobs, int njobs, int device) {
+    WS_API_BEGIN
+    WS_REQUIRE(jobs && njobs >= 1, "bad arguments");
+    DeviceGuard g(device);
+    std::vector<std::unique_ptr<EigRun>> owned((size_t)njobs);
+    std::vector<EigRun*> runs((size_t)njobs, nullptr);
+    std::vector<int> state((size_t)njobs, 0);      // 0 iterating, 1 results enqueued, 2 finished / failed
+    auto guarded = [&](int i, auto&& fn) {
+        try {
+            fn();
+            return true;
+        } catch (const Error& e) {
+            jobs[i].rc = e.code;
+            snprintf(jobs[i].error, sizeof jobs[i].error, "%s", e.what());
+        } catch (const std::exception& e) {
+            jobs[i].rc = WS_ERR_CUDA;
+            snprintf(jobs[i].error, sizeof jobs[i].error, "%s", e.what());
+        }
+        state[i] = 2;
+        return false;
+    };
+    for (int i = 0; i < njobs; ++i) {
+        ws_eig_job& J = jobs[i];
+        J.rc = WS_OK;
+        J.error[0] = 0;
+        if (J.workspace) {
+            runs[i] = &J.workspace->run;                 // persistent: basis, pinned buffers and step graphs are reused
+        } else {
+            owned[i].reset(new EigRun());
+            runs[i] = owned[i].get();
+        }
+        guarded(i, [&] {
+            eig_configure(*runs[i], J.pattern, J.solver, J.B_vals, J.sigma, J.kind, J.nev, J.ncv, J.tol, J.maxit, J.seed, J.edges,
+                          J.xy, J.Ntt, J.w, J.V, device, (cudaStream_t)J.stream);
+            runs[i]->init();
+        });
+    }
+    const bool btrace = getenv("WS_BATCH_TRACE") != nullptr;
+    double t_enq = 0, t_fin = 0;
+    int ncycles = 0;
+    for (;;) {
+        bool any = false;
+        const double t0 = EigRun::now();
+        for (int i = 0; i < njobs; ++i)
+            if (state[i] == 0) any = guarded(i, [&] { runs[i]->enqueue_cycle(); }) || any;
+        if (!any) break;
+        const double t1 = EigRun::now();
+        for (int i = 0; i < njobs; ++i)
+            if (state[i] == 0)
+                guarded(i, [&] {
+                    if (runs[i]->finish_cycle()) {
+                        runs[i]->enqueue_results();
+                        state[i] = 1;
+                    }
+                });
+        t_enq += t1 - t0;
+        t_fin += EigRun::now() - t1;
+        ++ncycles;
+    }
+    if (btrace)
+        fprintf(stderr, "[ws_eig_solve_batch] %d jobs, %d cycles: host enqueue %.1f ms, wait + restart analysis %.1f ms\n", njobs, ncycles,
+                t_enq * 1e3, t_fin * 1e3);
+    for (int i = 0; i < njobs; ++i)
+        if (state[i] == 1) {
+            if (guarded(i, [&] { runs[i]->finish(jobs[i].info, jobs[i].resid); })) state[i] = 2;
+            else if (jobs[i].rc == WS_ERR_NOCONV) {   // results are written: report what the iteration had
+                jobs[i].info[0] = runs[i]->nconv; jobs[i].info[1] = runs[i]->nops; jobs[i].info[2] = runs[i]->restarts;
+            }
+        }
+    owned.clear();
+    WS_API_END
+}
+
+int ws_eig_workspace_create(ws_eig_workspace** out) {
+    WS_API_BEGIN
+    WS_REQUIRE(out, "out == NULL");
+    *out = new ws_eig_workspace();
+    WS_API_END
+}
+
+int ws_eig_workspace_destroy(ws_eig_workspace* w) {
+    WS_API_BEGIN
+    delete w;
     WS_API_END
 }
 

@@ -80,6 +80,7 @@ struct ws_solver {
     ws::DevBuf<ws::BwdTile> bwd_tiles;
     std::vector<ws::LevelPlan> levels;      // index = tree level
     bool plan_built = false;                // tile tasks are emitted on the first factorisation (see build_plan)
+    bool overlap = true;                    // sweeps chained with programmatic dependent launch + per-front flags (ws_solver_set_overlap)
     std::vector<ws::GemmTask> h_gemm;       // host copies stay alive: the uploads are asynchronous
     std::vector<ws::PanelTask> h_panel;
     std::vector<ws::ExtTask> h_ext;
@@ -103,6 +104,11 @@ struct ws_solver {
     int probe_iters = 0;
     double h_eta0 = 0.0, h_eta = 0.0, h_maxabs = 0.0;   // probe backward error before / after refinement; max |M_ij|
     ws::DevBuf<double> rf_b, rf_r, rf_y, rf_dx, rf_x;
+    unsigned long long* h_stats = nullptr;  // pinned landing buffer of the statistics (factor_begin -> factor_end)
+    bool factor_pending = false;
+    ~ws_solver() {
+        if (h_stats) cudaFreeHost(h_stats);
+    }
 };
 
 namespace ws {
@@ -842,7 +848,9 @@ __device__ __forceinline__ void flag_signal(int32_t* f) {
 
 struct FrontRec {
     int64_t Loff, start, woff, bndoff;
-    int32_t p, q, pad0, pad1;
+    int32_t p, q, pad0, pad1;       // pad0 / pad1: CTAs the forward / backward sweep spends on this front
+    int32_t cf0, cf1, pb, pad2;     // the same counts of the two children (forward) and of the parent (backward): a waiter
+                                    // finds what it has to wait for in its own record, not behind another dependent load
 };
 
 constexpr int FRONT_MAX_M = 1024;   // fronts up to this size are handled by one CTA
@@ -865,24 +873,48 @@ struct SolveCtx {
 };
 
 // forward: wait for the two children of front t (their CTA counts are in their records)
-__device__ __forceinline__ void fwd_wait_children(const SolveCtx& cx, int64_t t) {
+__device__ __forceinline__ void fwd_wait_children(const SolveCtx& cx, int64_t t, const FrontRec& R) {
     if (threadIdx.x == 0) {
-        flag_wait(cx.ffl + 2 * t, cx.recs[2 * t].pad0, cx.ffl);          // slot 0 (front ids start at 1) = abort flag
-        flag_wait(cx.ffl + 2 * t + 1, cx.recs[2 * t + 1].pad0, cx.ffl);
+        flag_wait(cx.ffl + 2 * t, R.cf0, cx.ffl);          // slot 0 (front ids start at 1) = abort flag
+        flag_wait(cx.ffl + 2 * t + 1, R.cf1, cx.ffl);
     }
     __syncthreads();
 }
 // backward: wait for the front's own forward pass and for its parent's backward pass
-__device__ __forceinline__ void bwd_wait_parent(const SolveCtx& cx, int64_t t, int own_fwd_ctas) {
+__device__ __forceinline__ void bwd_wait_parent(const SolveCtx& cx, int64_t t, const FrontRec& R) {
     if (threadIdx.x == 0) {
-        flag_wait(cx.ffl + t, own_fwd_ctas, cx.ffl);
-        if (t > 1) flag_wait(cx.bfl + (t >> 1), cx.recs[t >> 1].pad1, cx.ffl);
+        flag_wait(cx.ffl + t, R.pad0, cx.ffl);
+        if (t > 1) flag_wait(cx.bfl + (t >> 1), R.pb, cx.ffl);
     }
     __syncthreads();
 }
 
 // NR right-hand sides share every load of the inverted panels: a sweep is bound by the panel bytes,
 // so a second vector costs its own (small) vector traffic and arithmetic only.
+// the static part of the gather (permutation / child positions): can be loaded before the dependency is resolved
+struct GatherIdx {
+    int32_t pi, s0, s1;
+};
+__device__ __forceinline__ GatherIdx fwd_gather_idx(const SolveCtx& cx, const FrontRec& R, int i, int has_children) {
+    GatherIdx g;
+    g.pi = (i < R.p) ? cx.perm[R.start + i] : -1;
+    g.s0 = g.s1 = -1;
+    if (has_children) {
+        g.s0 = cx.wsrc0[R.woff + i];
+        g.s1 = cx.wsrc1[R.woff + i];
+    }
+    return g;
+}
+template <int NR>
+__device__ __forceinline__ void fwd_gather_val(const SolveCtx& cx, const GatherIdx& g, const double* __restrict__ b, double (&v)[NR]) {
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+        double t = g.pi >= 0 ? b[g.pi + r * cx.sN] : 0.0;
+        if (g.s0 >= 0) t += cx.W[g.s0 + r * cx.sW];
+        if (g.s1 >= 0) t += cx.W[g.s1 + r * cx.sW];
+        v[r] = t;
+    }
+}
 template <int NR>
 __device__ __forceinline__ void fwd_gather(const SolveCtx& cx, const FrontRec& R, int i, int has_children,
                                            const double* __restrict__ b, double (&v)[NR]) {
@@ -924,10 +956,16 @@ __global__ void __launch_bounds__(MAXT) k_fwd_front(int64_t first, int has_child
     double wv[NR];
 #pragma unroll
     for (int q = 0; q < NR; ++q) wv[q] = 0.0;
-    if (cx.ffl && has_children) fwd_wait_children(cx, first + blockIdx.x);
+    GatherIdx gi{-1, -1, -1};
+    double di = 0.0;
+    if (act) {
+        gi = fwd_gather_idx(cx, R, r, has_children);
+        if (r < p) di = cx.dinv[R.start + r];
+    }
+    if (cx.ffl && has_children) fwd_wait_children(cx, first + blockIdx.x, R);
     else pdl_wait();
     if (act) {
-        fwd_gather<NR>(cx, R, r, has_children, b, wv);
+        fwd_gather_val<NR>(cx, gi, b, wv);
         if (r < p) {
 #pragma unroll
             for (int q = 0; q < NR; ++q) sw[q * pstride + r] = wv[q];
@@ -960,7 +998,6 @@ __global__ void __launch_bounds__(MAXT) k_fwd_front(int64_t first, int has_child
         for (int j = 0; j < KB; ++j) c[j] = (k0 + 3 * KB + j < kend) ? __ldg(Sr + (size_t)(k0 + 3 * KB + j) * ld) : 0.0;
     }
     if (act) {
-        const double di = r < p ? cx.dinv[R.start + r] : 0.0;
 #pragma unroll
         for (int q = 0; q < NR; ++q) {
             const double acc = acc0[q] + acc1[q];
@@ -996,7 +1033,7 @@ __global__ void __launch_bounds__(32 * KL) k_fwd_tile(const FwdTile* __restrict_
     double a[NL];
 #pragma unroll
     for (int j = 0; j < NL; ++j) a[j] = (kl + j * KL < kend) ? __ldg(Sr + (size_t)(kl + j * KL) * ld) : 0.0;
-    if (cx.ffl && has_children) fwd_wait_children(cx, t.front);
+    if (cx.ffl && has_children) fwd_wait_children(cx, t.front, R);
     else pdl_wait();
     for (int k = threadIdx.x; k < kend_tile; k += 32 * KL) {
         double g[NR];
@@ -1065,10 +1102,12 @@ __global__ void __launch_bounds__(MAXT) k_bwd_front(int64_t first, SolveCtx cx, 
             a[i][j] = (c < p && r < m) ? __ldg(Sf + r + (size_t)c * m) : 0.0;
         }
     }
-    if (cx.bfl) bwd_wait_parent(cx, first + blockIdx.x, R.pad0);
+    int64_t src0 = 0;
+    if ((int)threadIdx.x < m) src0 = ((int)threadIdx.x < p) ? R.start + threadIdx.x : (int64_t)cx.bnd[R.bndoff + threadIdx.x - p];
+    if (cx.bfl) bwd_wait_parent(cx, first + blockIdx.x, R);
     else pdl_wait();
     for (int i = threadIdx.x; i < m; i += blockDim.x) {
-        const int64_t src = (i < p) ? R.start + i : (int64_t)cx.bnd[R.bndoff + i - p];
+        const int64_t src = i == (int)threadIdx.x ? src0 : ((i < p) ? R.start + i : (int64_t)cx.bnd[R.bndoff + i - p]);
 #pragma unroll
         for (int q = 0; q < NR; ++q) sg[q * mstride + i] = (i < p) ? cx.yd[src + q * cx.sN] : -cx.x[src + q * cx.sN];
     }
@@ -1168,7 +1207,7 @@ __global__ void __launch_bounds__(32 * GEMVT_COLS * WPC) k_bwd_tile(const BwdTil
     double a[NL];
 #pragma unroll
     for (int j = 0; j < NL; ++j) a[j] = (on && rb + j * step < m) ? __ldg(Sc + rb + j * step) : 0.0;
-    if (cx.bfl) bwd_wait_parent(cx, t.front, R.pad0);
+    if (cx.bfl) bwd_wait_parent(cx, t.front, R);
     else pdl_wait();
     for (int i = t.c0 + threadIdx.x; i < m; i += blockDim.x) {
         const int64_t src = (i < p) ? R.start + i : (int64_t)cx.bnd[R.bndoff + i - p];
@@ -1615,9 +1654,11 @@ static void launch_gemm(const ws_solver* s, const Range& r, bool narrow, cudaStr
 // override them for experiments (tools/sweep_variants.py).
 // launch with the programmatic-stream-serialisation attribute (the kernel may start before its
 // predecessor in the stream has finished; it synchronises itself with griddepcontrol.wait)
+static thread_local bool g_pdl_on = true;        // set by sweep_launches from the solver's overlap mode
 template <class... KArgs, class... Args>
 static void launch_pdl(void (*kern)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t st, Args... args) {
-    static const bool pdl = !(getenv("WS_NO_PDL") && atoi(getenv("WS_NO_PDL")));
+    static const bool pdl_env = !(getenv("WS_NO_PDL") && atoi(getenv("WS_NO_PDL")));
+    const bool pdl = pdl_env && g_pdl_on;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(block);
@@ -1707,8 +1748,10 @@ constexpr int MAX_NRHS = 2;     // right-hand sides one sweep can carry
 template <int NR>
 static void sweep_launches(ws_solver* s, const double* bi, double* xi, cudaStream_t st) {
     const Symbolic& Y = s->sym;
-    static const bool flagsync = !(getenv("WS_NO_FLAGSYNC") && atoi(getenv("WS_NO_FLAGSYNC"))) &&
-                                 !(getenv("WS_NO_PDL") && atoi(getenv("WS_NO_PDL")));
+    static const bool flagsync_env = !(getenv("WS_NO_FLAGSYNC") && atoi(getenv("WS_NO_FLAGSYNC"))) &&
+                                     !(getenv("WS_NO_PDL") && atoi(getenv("WS_NO_PDL")));
+    const bool flagsync = flagsync_env && s->overlap;
+    g_pdl_on = s->overlap;
     SolveCtx cx{s->recs.get(), s->S.get(), s->perm.get(), s->wsrc0.get(), s->wsrc1.get(), s->bnd.get(),
                 s->dinv.get(), s->W.get(), s->yd.get(), s->x.get(), (int64_t)((Y.Wtotal + 1) & ~(int64_t)1), s->N,
                 flagsync ? s->sflags.get() : nullptr, flagsync ? s->sflags.get() + Y.nfronts : nullptr};
@@ -1720,7 +1763,8 @@ static void sweep_launches(ws_solver* s, const double* bi, double* xi, cudaStrea
     // per-front flags the left half of level l-1 depends on the left half of level l only, so it can run while the
     // right half of level l drains.  Measured: 0.977 ms against 0.970 ms per solve -- the tails are not what is
     // left to gain -- so it is off by default.
-    static const bool halves = flagsync && getenv("WS_SPLIT") && atoi(getenv("WS_SPLIT"));
+    static const bool halves_env = getenv("WS_SPLIT") && atoi(getenv("WS_SPLIT"));
+    const bool halves = flagsync && halves_env;
     for (int l = Y.depth; l >= 0; --l) {
         const LevelPlan& LP = s->levels[l];
         const int hc = l < Y.depth ? 1 : 0;
@@ -1873,7 +1917,14 @@ int ws_solver_create(const ws_pattern* p, const ws_symbolic* sym, ws_solver** ou
                     }
                     nbk = (p_ + GEMVT_COLS - 1) / GEMVT_COLS;
                 }
-                recs[t] = FrontRec{Y.Loff[t], Y.start[t], Y.woff[t], Y.bndoff[t], Y.p[t], Y.q[t], nf, nbk};
+                recs[t] = FrontRec{Y.Loff[t], Y.start[t], Y.woff[t], Y.bndoff[t], Y.p[t], Y.q[t], nf, nbk, 0, 0, 0, 0};
+            }
+            for (int64_t t = 1; t < Y.nfronts; ++t) {
+                if (2 * t + 1 < Y.nfronts) {
+                    recs[t].cf0 = recs[2 * t].pad0;
+                    recs[t].cf1 = recs[2 * t + 1].pad0;
+                }
+                if (t > 1) recs[t].pb = recs[t >> 1].pad1;
             }
             upload(s->recs, recs, st);
             WS_CUDA(cudaStreamSynchronize(st));   // recs dies here
@@ -1918,6 +1969,13 @@ int ws_solver_create(const ws_pattern* p, const ws_symbolic* sym, ws_solver** ou
 
 int ws_solver_factor(ws_solver* s, const double* A_vals, const double* B_vals, double sigma, int device,
                      void* stream) {
+    int rc = ws_solver_factor_begin(s, A_vals, B_vals, sigma, device, stream);
+    if (rc) return rc;
+    return ws_solver_factor_end(s, device, stream);
+}
+
+int ws_solver_factor_begin(ws_solver* s, const double* A_vals, const double* B_vals, double sigma, int device,
+                           void* stream) {
     WS_API_BEGIN
     WS_REQUIRE(s && A_vals, "null pointer");
     DeviceGuard g(device);
@@ -1999,8 +2057,6 @@ int ws_solver_factor(ws_solver* s, const double* A_vals, const double* B_vals, d
     // cost of the guard is this one solve + one SpMV).  If refinement cannot bring eta below ETA_FAIL the call
     // fails with WS_ERR_NUMERIC: degraded eigenpairs are never returned silently.
     static const bool guard = !(getenv("WS_NO_GUARD") && atoi(getenv("WS_NO_GUARD")));
-    constexpr double ETA_OK = 1e-13, ETA_FAIL = 1e-11;
-    constexpr int MAX_REFINE = 5;
     s->factored = true;                       // the probe goes through the regular sweeps
     const int T = 256;
     const int nbN = ceil_div(s->N, T);
@@ -2027,11 +2083,40 @@ int ws_solver_factor(ws_solver* s, const double* A_vals, const double* B_vals, d
         sweep_launches<1>(s, s->rf_b.get(), s->rf_x.get(), st);
         probe_pass(true);
     }
-    unsigned long long h[NSTATS];
-    WS_CUDA(cudaMemcpyAsync(h, s->stats.get(), sizeof h, cudaMemcpyDeviceToHost, st));
+    if (!s->h_stats) WS_CUDA(cudaMallocHost((void**)&s->h_stats, NSTATS * sizeof(unsigned long long)));
+    WS_CUDA(cudaMemcpyAsync(s->h_stats, s->stats.get(), NSTATS * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    s->factored = false;
+    s->factor_pending = true;
+    WS_API_END
+}
+
+int ws_solver_factor_end(ws_solver* s, int device, void* stream) {
+    WS_API_BEGIN
+    WS_REQUIRE(s, "solver == NULL");
+    if (!s->factor_pending) throw Error(WS_ERR_STATE, "ws_solver_factor_end without ws_solver_factor_begin");
+    s->factor_pending = false;
+    DeviceGuard g(device);
+    cudaStream_t st = (cudaStream_t)stream;
+    static const bool guard = !(getenv("WS_NO_GUARD") && atoi(getenv("WS_NO_GUARD")));
+    constexpr double ETA_OK = 1e-13, ETA_FAIL = 1e-11;
+    constexpr int MAX_REFINE = 5;
+    const int T = 256;
+    const int nbN = ceil_div(s->N, T);
+    auto probe_pass = [&](bool first) {
+        spmv_launch(s->pat, s->fA, s->rf_x.get(), s->rf_y.get(), st);
+        const double* yb = nullptr;
+        if (s->fB) {
+            spmv_launch(s->pat, s->fB, s->rf_x.get(), s->rf_dx.get(), st);
+            yb = s->rf_dx.get();
+        }
+        if (!first) WS_CUDA(cudaMemsetAsync(s->stats.get() + 6, 0, 3 * sizeof(unsigned long long), st));
+        k_residual<<<nbN, T, 0, st>>>(s->N, s->rf_b.get(), s->rf_y.get(), yb, s->fsigma, s->rf_x.get(), s->rf_r.get(),
+                                      s->stats.get() + 6);
+        count_launch(1);
+    };
+    unsigned long long* h = s->h_stats;
     WS_CUDA(cudaStreamSynchronize(st));
     WS_CUDA(cudaGetLastError());
-    s->factored = false;
     auto as_double = [](unsigned long long bits) { double d; std::memcpy(&d, &bits, 8); return d; };
     s->h_neg = (int64_t)h[0];
     s->h_bad = (int64_t)h[1];
@@ -2060,7 +2145,7 @@ int ws_solver_factor(ws_solver* s, const double* A_vals, const double* B_vals, d
             k_add_inplace<<<nbN, T, 0, st>>>(s->N, s->rf_x.get(), s->rf_y.get());
             count_launch(1);
             probe_pass(false);
-            WS_CUDA(cudaMemcpyAsync(h, s->stats.get(), sizeof h, cudaMemcpyDeviceToHost, st));
+            WS_CUDA(cudaMemcpyAsync(h, s->stats.get(), NSTATS * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
             WS_CUDA(cudaStreamSynchronize(st));
             const double e2 = eta_of(h);
             ++steps;
@@ -2161,6 +2246,13 @@ int ws_solver_stats(const ws_solver* s, int64_t* h_info, double* h_dinfo) {
     if (h_dinfo) {
         h_dinfo[0] = s->sym.flops; h_dinfo[1] = s->h_minpiv; h_dinfo[2] = s->h_maxpiv;
     }
+    WS_API_END
+}
+
+int ws_solver_set_overlap(ws_solver* s, int on) {
+    WS_API_BEGIN
+    WS_REQUIRE(s, "solver == NULL");
+    s->overlap = on != 0;
     WS_API_END
 }
 

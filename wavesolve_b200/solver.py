@@ -8,7 +8,10 @@ import numpy as np
 
 from . import _lib
 
-DEFAULT_LEAF_ELEMS = 48
+import os as _os
+
+# elements per leaf of the nested-dissection tree (profiles/r02_leaf_elems_sweep.txt: solve / factor time against this)
+DEFAULT_LEAF_ELEMS = int(_os.environ.get("WS_LEAF_ELEMS", "48"))
 
 
 class Symbolic:

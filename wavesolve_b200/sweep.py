@@ -239,10 +239,43 @@ def gather_eigenpairs(local: Dict[int, tuple], n_problems: int, group=None, with
 # ---------------------------------------------------------------------------------------------
 # driver
 # ---------------------------------------------------------------------------------------------
-class _MeshContext:
-    """Everything that depends on the mesh only, resident on this rank's GPU."""
+class _Lane:
+    """One of the eigenproblems a GPU works on concurrently: its own CUDA stream, solver (front storage), material
+    array and value arrays.  Everything that depends on the mesh only is shared through the _MeshContext."""
 
-    def __init__(self, mesh, kind, IOR_dict, k, device, leaf_elems):
+    def __init__(self, ctx, stream):
+        from . import solver as sv
+        self.ctx, self.stream = ctx, stream
+        prob = ctx.prob
+        with torch.cuda.stream(stream):
+            self.solver = sv.Solver(prob.pattern, ctx.symbolic)
+            if len(ctx.streams) > 1:
+                # several lanes share the GPU: plain stream order inside a solve (measured +12 % problems/s at 8 lanes)
+                from . import _lib
+                _lib.check(_lib.lib().ws_solver_set_overlap(self.solver.handle, 0))
+            self.k2n2 = torch.empty_like(prob.k2n2)
+            nnz = prob.pattern.nnz
+            self.M = torch.empty(nnz, dtype=torch.float64, device=prob.dev)
+            self.B = torch.empty(nnz, dtype=torch.float64, device=prob.dev)
+        import ctypes as C
+        from . import _lib
+        self.workspace = C.c_void_p()
+        _lib.check(_lib.lib().ws_eig_workspace_create(C.byref(self.workspace)))
+
+    def close(self):
+        from . import _lib
+        self.stream.synchronize()
+        if self.workspace is not None and self.workspace.value:
+            _lib.lib().ws_eig_workspace_destroy(self.workspace)
+            self.workspace = None
+        self.solver.close()
+
+
+class _MeshContext:
+    """Everything that depends on the mesh only, resident on this rank's GPU: arrays, pattern, incidence lists,
+    symbolic analysis (shared by the lanes), plus the lanes themselves."""
+
+    def __init__(self, mesh, kind, IOR_dict, k, device, leaf_elems, streams=None):
         from . import fe_solver as fs, solver as sv
         self.kind = kind
         self.mesh = mesh
@@ -255,12 +288,39 @@ class _MeshContext:
         self.prob.build_pattern()
         self.symbolic = sv.Symbolic.on_device(self.prob.dofs, self.prob.xy, self.prob.N, fcs,
                                               leaf_elems or sv.DEFAULT_LEAF_ELEMS)
-        self.solver = sv.Solver(self.prob.pattern, self.symbolic)
+        self.lanes = []
+        self.streams = list(streams or [])
+        if streams is None:
+            self.solver = sv.Solver(self.prob.pattern, self.symbolic)      # single-lane use (tools, tests)
+        else:
+            self.solver = None
+            if kind == "vector":
+                # the T / T^T tables hang off the shared pattern and are built on first use: build them before the
+                # lanes (other streams) read them
+                self.prob.apply_T(torch.zeros(self.prob.N, dtype=torch.float64, device=self.prob.dev))
+            cur = torch.cuda.current_stream(self.prob.dev)
+            for st in streams:
+                st.wait_stream(cur)
+                self.lanes.append(_Lane(self, st))
 
     def close(self):
-        self.solver.close()
+        for ln in self.lanes:
+            ln.close()
+        if self.solver is not None:
+            self.solver.close()
         self.prob.pattern.close()
         self.symbolic.close()
+
+
+def default_lanes(n_unknowns: int) -> int:
+    """Problems a B200 works on concurrently: an eigensolve of ~100k unknowns is a chain of ~4000 small dependent
+    kernels that fills a fraction of the GPU (4 streams finish 3.2 solves in the time of one); from ~1M unknowns
+    on a single problem saturates it."""
+    if n_unknowns >= 1_000_000:
+        return 1
+    if n_unknowns >= 400_000:
+        return 2
+    return 8
 
 
 def solve_sweep(meshes: Sequence, problems: Sequence[SweepProblem], Nmax: int = 10, kind: str = "vector",
@@ -270,23 +330,26 @@ def solve_sweep(meshes: Sequence, problems: Sequence[SweepProblem], Nmax: int = 
 
     ``meshes``: mesh objects (vector sweeps: already passed through ``get_unique_edges``), the same
     list on every rank.  Returns a list of ``SweepResult`` in problem order (on every rank, or on
-    ``dst`` only), or this rank's own results when ``gather=False``.
+    ``dst`` only), or this rank's own results when ``gather=False``.  A problem that fails (no convergence,
+    inaccurate factorisation at its shift, ...) is reported through ``SweepResult.rc`` / ``info["error"]``
+    and does not stop the others.
 
-    ``lanes``: problems solved concurrently on this GPU, each on its own CUDA stream with its own
-    solver storage, driven by its own host thread (the C calls release the GIL).  An eigensolve on a
-    mesh of ~50k triangles is a chain of ~3000 short dependent kernels that fills a fraction of a
-    B200, so several independent problems overlap almost for free; a 1M-triangle problem saturates
-    the GPU by itself.  Default 1: measured on a B200 with 32 problems of 100k unknowns, 2 lanes give
-    +15 % and 4 or 8 lanes are slower than one (the lanes contend for the stream-ordered memory pool
-    and the driver; tools/bench_sweep.py --lanes N) -- kept as an opt-in until that is resolved."""
+    ``lanes``: problems solved concurrently on this GPU (default: ``default_lanes``).  The lanes of a mesh share
+    its pattern, incidence lists and symbolic analysis; each has its own CUDA stream, solver storage and value
+    arrays.  ONE host thread drives them in lockstep: re-assembly and factorisation of the next wavelength of
+    every lane are enqueued back to back (``ws_solver_factor_begin`` / ``_end``), then the eigen-iterations run
+    interleaved through ``ws_eig_solve_batch``, so the kernels of the lanes overlap on the device.  (Round 1 drove
+    the lanes from one host thread each: the threads serialised on the driver and 4 lanes were no faster than
+    one.)"""
+    import ctypes as C
     from . import _lib, device as _dev, fe_solver as fs
-    import threading
     assert kind in ("vector", "scalar")
     dist = _dist()
     multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
     rank = dist.get_rank(group) if multi else 0
     world = dist.get_world_size(group) if multi else 1
     dev = _dev.require_cuda(device)
+    L = _lib.lib()
 
     def n_unknowns(mesh):
         # the same rule the problem classes apply (fe_solver.VectorProblem / ScalarProblem.N): the packed
@@ -302,86 +365,141 @@ def solve_sweep(meshes: Sequence, problems: Sequence[SweepProblem], Nmax: int = 
     table = partition([p.mesh_id for p in problems], [estimate_cost(sizes[p.mesh_id]) for p in problems], world)
     mine = table[rank]
     if lanes is None:
-        lanes = 1
+        lanes = default_lanes(max([sizes[problems[i].mesh_id] for i in mine], default=0))
     lanes = max(1, min(int(lanes), max(1, len(mine))))
     local, infos = {}, {}
     # one flat send buffer per rank: [w_0 | V_0 | w_1 | V_1 ...]; the eigensolver writes into its views
-    # (sized for the largest rank payload so that it can be handed to all_gather unpadded)
-    total = max(sum(Nmax * (1 + sizes[problems[i].mesh_id]) for i in r) for r in table)
+    total = sum(Nmax * (1 + sizes[problems[i].mesh_id]) for i in mine)
     with torch.cuda.device(dev):
+        main_stream = torch.cuda.current_stream(dev)
         sendbuf = torch.zeros(max(total, 1), dtype=torch.float64, device=dev)
         offsets, off = {}, 0
         for i in mine:
             offsets[i] = off
             off += Nmax * (1 + sizes[problems[i].mesh_id])
-        # problems of one mesh are dealt round-robin to the lanes (consecutive in `mine`), so the lanes
-        # work on the same mesh at the same time and each keeps one resident context
-        lane_items = [mine[l::lanes] for l in range(lanes)]
-        main_stream = torch.cuda.current_stream(dev)
-        errors = []
+        streams = [torch.cuda.Stream(device=dev) for _ in range(lanes)]
+        # the problems of one mesh, in order; `lanes` of them are in flight at a time
+        groups: List[List[int]] = []
+        for i in mine:
+            if groups and problems[groups[-1][-1]].mesh_id == problems[i].mesh_id:
+                groups[-1].append(i)
+            else:
+                groups.append([i])
 
-        def run_lane(items, stream):
+        def fail(i, wv, Vv, e):
+            rc = getattr(e, "rc", 0) or _lib.ERR_CUDA
+            if rc != _lib.ERR_NOCONV:
+                wv.fill_(float("nan"))
+                Vv.fill_(float("nan"))
+            return rc
+
+        import os as _os, time as _time
+        _trace = bool(_os.environ.get("WS_SWEEP_TRACE"))
+        _tm = {"context": 0.0, "assemble+factor_begin": 0.0, "factor_end": 0.0, "eig_batch": 0.0, "post": 0.0, "close": 0.0}
+
+        def _tick(name, t0):
+            if _trace:
+                _tm[name] += _time.perf_counter() - t0
+            return _time.perf_counter()
+
+        for grp in groups:
+            pr0 = problems[grp[0]]
+            _t = _time.perf_counter()
+            ctx = _MeshContext(meshes[pr0.mesh_id], kind, pr0.IOR_dict, 2 * np.pi / pr0.wl, dev, leaf_elems,
+                               streams=streams[:min(lanes, len(grp))])
+            prob = ctx.prob
+            N = prob.N
+            if _trace:
+                torch.cuda.synchronize(dev)
+            _t = _tick("context", _t)
             try:
-                with torch.cuda.device(dev), torch.cuda.stream(stream):
-                    ctx, ctx_mesh = None, None
-                    for i in items:
+                for r0 in range(0, len(grp), len(ctx.lanes)):
+                    batch = grp[r0:r0 + len(ctx.lanes)]
+                    _t = _time.perf_counter()
+                    act = []                                   # (problem index, lane, k, sigma, views)
+                    # ---- phase 1: new materials, re-assembly (K11) and factorisation of every lane, all enqueued
+                    for i, ln in zip(batch, ctx.lanes):
                         pr = problems[i]
                         k = 2 * np.pi / pr.wl
-                        if ctx_mesh != pr.mesh_id:
-                            if ctx is not None:
-                                ctx.close()
-                            ctx = _MeshContext(meshes[pr.mesh_id], kind, pr.IOR_dict, k, dev, leaf_elems)
-                            ctx_mesh = pr.mesh_id
-                        else:
-                            ctx.prob.set_materials(ctx.mesh, pr.IOR_dict, k)
-                        N = ctx.prob.N
                         o = offsets[i]
                         wv = sendbuf[o:o + Nmax]
                         Vv = sendbuf[o + Nmax:o + Nmax + Nmax * N].view(Nmax, N)
                         nmax_ior = max(pr.IOR_dict.values())
                         sigma = float(np.power(k * (nmax_ior if pr.target_neff is None else pr.target_neff), 2))
-                        rc = 0
+                        sp = ln.stream.cuda_stream
                         try:
-                            if kind == "vector":
-                                _, _, info = fs.solve_vector_resident(ctx.prob, sigma, Nmax, solver=ctx.solver, out=(wv, Vv))
-                            else:
-                                _, _, info = fs.solve_scalar_resident(ctx.prob, sigma, Nmax, solver=ctx.solver, out=(wv, Vv))
+                            with torch.cuda.stream(ln.stream):
+                                ln.k2n2.copy_(torch.from_numpy(fs._k2n2_host(ctx.mesh, pr.IOR_dict, k)), non_blocking=True)
+                                if kind == "vector":
+                                    _lib.check(L.ws_assemble_vector_qd(prob.pattern.handle, _dev.ptr(prob.xy), _dev.ptr(prob.tris),
+                                                                       _dev.ptr(ln.k2n2), prob.Ntt, sigma, _dev.ptr(ln.M),
+                                                                       _dev.ptr(ln.B), _lib.ASM_FAST, dev.index, sp))
+                                    _lib.check(L.ws_solver_factor_begin(ln.solver.handle, _dev.ptr(ln.M), None, 0.0, dev.index, sp))
+                                else:
+                                    _lib.check(L.ws_assemble_scalar_p2(prob.pattern.handle, _dev.ptr(prob.xy), _dev.ptr(prob.dofs),
+                                                                       _dev.ptr(ln.k2n2), _dev.ptr(ln.M), _dev.ptr(ln.B),
+                                                                       _lib.ASM_FAST, dev.index, sp))
+                                    _lib.check(L.ws_solver_factor_begin(ln.solver.handle, _dev.ptr(ln.M), _dev.ptr(ln.B), sigma,
+                                                                        dev.index, sp))
+                            act.append((i, ln, k, sigma, wv, Vv))
                         except _lib.WavesolveB200Error as e:
-                            # per-problem failure (error code + partial results per problem):
-                            # no convergence keeps what the iteration wrote, anything else is marked NaN
-                            rc = e.rc or _lib.ERR_CUDA
-                            info = dict(e.info or {}, error=str(e))
-                            if rc != _lib.ERR_NOCONV:
-                                wv.fill_(float("nan"))
-                                Vv.fill_(float("nan"))
-                        w_host = wv.cpu().numpy()
-                        cnt = 0 if rc not in (0, _lib.ERR_NOCONV) else \
-                            fs._count_modes(w_host, k, pr.IOR_dict, always=(kind == "vector" and pr.target_neff is not None))
+                            local[i] = (wv, Vv, 0, fail(i, wv, Vv, e))
+                            infos[i] = {"error": str(e)}
+                    _t = _tick("assemble+factor_begin", _t)
+                    # ---- phase 2: read the pivot statistics / accuracy probe of every lane
+                    ready = []
+                    for (i, ln, k, sigma, wv, Vv) in act:
+                        try:
+                            _lib.check(L.ws_solver_factor_end(ln.solver.handle, dev.index, ln.stream.cuda_stream))
+                            ready.append((i, ln, k, sigma, wv, Vv))
+                        except _lib.WavesolveB200Error as e:
+                            local[i] = (wv, Vv, 0, fail(i, wv, Vv, e))
+                            infos[i] = {"error": str(e)}
+                    _t = _tick("factor_end", _t)
+                    if not ready:
+                        continue
+                    # ---- phase 3: the eigen-iterations of the lanes, interleaved by one host thread
+                    jobs = (_lib.EigJob * len(ready))()
+                    for J, (i, ln, k, sigma, wv, Vv) in zip(jobs, ready):
+                        J.pattern, J.solver, J.B_vals = prob.pattern.handle.value, ln.solver.handle.value, _dev.ptr(ln.B)
+                        J.sigma, J.kind, J.nev, J.ncv, J.maxit, J.tol, J.seed = sigma, (1 if kind == "vector" else 0), Nmax, 0, 0, 0.0, 0
+                        J.edges = _dev.ptr(prob.edges) if kind == "vector" else None
+                        J.xy = _dev.ptr(prob.xy) if kind == "vector" else None
+                        J.Ntt = prob.Ntt if kind == "vector" else 0
+                        J.w, J.V, J.stream, J.resid = _dev.ptr(wv), _dev.ptr(Vv), ln.stream.cuda_stream, None
+                        J.workspace = ln.workspace.value
+                    _lib.check(L.ws_eig_solve_batch(C.addressof(jobs), len(ready), dev.index))
+                    _t = _tick("eig_batch", _t)
+                    for J, (i, ln, k, sigma, wv, Vv) in zip(jobs, ready):
+                        pr = problems[i]
+                        rc = int(J.rc)
+                        info = dict(nconv=int(J.info[0]), n_op=int(J.info[1]), restarts=int(J.info[2]), ncomplex=int(J.info[3]),
+                                    N=N, sigma=sigma, factor=ln.solver.stats())
+                        cnt = 0
+                        if rc not in (0, _lib.ERR_NOCONV):
+                            wv.fill_(float("nan"))
+                            Vv.fill_(float("nan"))
+                        if rc:
+                            info["error"] = J.error.decode(errors="replace")
+                        if rc in (0, _lib.ERR_NOCONV):
+                            cnt = fs._count_modes(wv.cpu().numpy(), k, pr.IOR_dict,
+                                                  always=(kind == "vector" and pr.target_neff is not None))
                         local[i] = (wv, Vv, cnt, rc)
                         infos[i] = info
-                    if ctx is not None:
-                        ctx.close()
-                    stream.synchronize()
-            except BaseException as e:      # re-raised on the calling thread
-                errors.append(e)
-
-        if lanes == 1:
-            run_lane(lane_items[0], main_stream)
-        else:
-            streams = [torch.cuda.Stream(device=dev) for _ in range(lanes)]
-            for st_ in streams:
-                st_.wait_stream(main_stream)          # sendbuf is zero-filled on the caller's stream
-            threads = [threading.Thread(target=run_lane, args=(lane_items[l], streams[l]), daemon=True)
-                       for l in range(lanes)]
-            for t in threads:
-                t.start()
-            for t in threads:
-                t.join()
-            for st_ in streams:
-                main_stream.wait_stream(st_)
-        if errors:
-            raise errors[0]
-        local = {i: local[i] for i in mine}      # send-buffer order (the lanes finish in any order)
+                    _t = _tick("post", _t)
+            finally:
+                _t = _time.perf_counter()
+                for st_ in streams:
+                    st_.synchronize()
+                ctx.close()
+                _t = _tick("close", _t)
+        if _trace:
+            import sys as _sys
+            print("[solve_sweep] rank %d lanes %d problems %d: %s" % (rank, lanes, len(mine), {k_: round(v, 3) for k_, v in _tm.items()}),
+                  file=_sys.stderr, flush=True)
+        for st_ in streams:
+            main_stream.wait_stream(st_)
+        local = {i: local[i] for i in mine}      # send-buffer order
         torch.cuda.synchronize(dev)
         if not gather:
             return [SweepResult(i, local[i][0].cpu().numpy(), local[i][1].cpu().numpy() if with_vectors else None,
