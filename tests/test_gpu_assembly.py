@@ -283,3 +283,15 @@ def test_pinned_result_buffers_are_recycled(ws):
     assert len(d._pinned_free) <= d._PINNED_KEEP
     z = d.d2h_pinned(torch.view_as_complex(torch.ones(1 << 17, 2, dtype=torch.float64, device="cuda")))
     assert z.dtype == np.complex128 and z[5] == 1 + 1j
+
+
+def test_staged_d2h_of_a_large_result(ws):
+    """GB-scale gather payloads come back through two reusable pinned staging blocks into pageable memory."""
+    from wavesolve_b200 import device as d
+    n = (3 * d._STAGE_BYTES) // 8 + 12345
+    x = torch.arange(n, dtype=torch.float64, device="cuda") * 0.5
+    a = d.d2h_staged(x)
+    assert a.dtype == np.float64 and a.shape == (n,) and a[0] == 0.0 and a[-1] == (n - 1) * 0.5
+    assert np.array_equal(a[:: 1 << 16], (np.arange(n, dtype=np.float64) * 0.5)[:: 1 << 16])
+    z = d.d2h_staged(x[: 2 * (n // 2)].view(-1, 2))
+    assert z.shape == (n // 2, 2) and z[5, 1] == 5.5

@@ -515,6 +515,7 @@ int ws_assemble_scalar_p2(const ws_pattern* p, const double* xy, const int32_t* 
                           const double* elem_k2n2, double* A_vals, double* B_vals, int flags,
                           int device, void* stream) {
     WS_API_BEGIN
+    WS_NVTX("ws K3 assemble scalar P2");
     // WS_ASM_TRANSPOSE is a no-op here: P2 scalar element matrices are bit-symmetric
     WS_REQUIRE(p, "pattern == NULL");
     if (p->nnz == 0) return WS_OK;
@@ -554,6 +555,7 @@ int ws_assemble_vector_p1(const ws_pattern* p, const double* xy, const int32_t* 
                           const double* elem_k2n2, int64_t Ntt, double* A_vals, double* B_vals,
                           int flags, int device, void* stream) {
     WS_API_BEGIN
+    WS_NVTX("ws K4 assemble vector");
     WS_REQUIRE(p, "pattern == NULL");
     WS_REQUIRE(Ntt >= 0 && Ntt <= p->N, "0 <= Ntt <= N");
     if (p->nnz == 0) return WS_OK;
@@ -568,6 +570,7 @@ int ws_assemble_vector_qd(const ws_pattern* p, const double* xy, const int32_t* 
                           const double* elem_k2n2, int64_t Ntt, double sigma, double* M_vals,
                           double* B_vals, int flags, int device, void* stream) {
     WS_API_BEGIN
+    WS_NVTX("ws K4 assemble vector (quasi-definite)");
     WS_REQUIRE(p, "pattern == NULL");
     WS_REQUIRE(Ntt >= 0 && Ntt <= p->N, "0 <= Ntt <= N");
     if (p->nnz == 0) return WS_OK;

@@ -10,6 +10,8 @@
 #include <string>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>   // header-only NVTX v3: ranges show up in Nsight Systems / Compute, no link dependency
+
 #include "../../include/wavesolve_b200.h"
 
 namespace ws {
@@ -119,6 +121,13 @@ struct PerDeviceOnce {
 };
 
 inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// NVTX range around a phase of the hot path (pattern / assemble / symbolic / factor / iterate)
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
+#define WS_NVTX(name) ws::NvtxRange nvtx_range__(name)
 
 // keep freed stream-ordered allocations cached in the device's default pool (the solver
 // allocates ~12 GB per 1M-element problem; returning it to the OS after every solve costs

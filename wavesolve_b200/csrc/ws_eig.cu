@@ -1757,6 +1757,7 @@ int ws_eig_solve(const ws_pattern* p, ws_solver* s, const double* B_vals, double
                  double tol, int maxit, uint64_t seed, const int32_t* edges, const double* xy, int64_t Ntt,
                  double* w_out, double* V_out, int64_t* h_info, double* h_resid, int device, void* stream) {
     WS_API_BEGIN
+    WS_NVTX("ws K5-K10 Krylov iterate");
     WS_REQUIRE(kind == 0 || kind == 1 || kind == 2,
                "kind must be 0 (B-orthogonal, symmetric), 1 (Euclidean, non-symmetric) or 2 (as 1, block size 2)");
     DeviceGuard g(device);
@@ -1795,6 +1796,7 @@ int ws_eig_solve(const ws_pattern* p, ws_solver* s, const double* B_vals, double
 // gets its own rc / message; the others run to the end.  Returns WS_OK unless the arguments themselves are bad.
 int ws_eig_solve_batch(ws_eig_job* jobs, int njobs, int device) {
     WS_API_BEGIN
+    WS_NVTX("ws K5-K10 Krylov iterate (batch)");
     WS_REQUIRE(jobs && njobs >= 1, "bad arguments");
     DeviceGuard g(device);
     std::vector<std::unique_ptr<EigRun>> owned((size_t)njobs);

@@ -1845,6 +1845,7 @@ extern "C" {
 
 int ws_solver_create(const ws_pattern* p, const ws_symbolic* sym, ws_solver** out, int device, void* stream) {
     WS_API_BEGIN
+    WS_NVTX("ws K8 solver create");
     WS_REQUIRE(out, "out == NULL");
     *out = nullptr;
     WS_REQUIRE(p && sym, "null handle");
@@ -1977,6 +1978,7 @@ int ws_solver_factor(ws_solver* s, const double* A_vals, const double* B_vals, d
 int ws_solver_factor_begin(ws_solver* s, const double* A_vals, const double* B_vals, double sigma, int device,
                            void* stream) {
     WS_API_BEGIN
+    WS_NVTX("ws K8b factor");
     WS_REQUIRE(s && A_vals, "null pointer");
     DeviceGuard g(device);
     cudaStream_t st = (cudaStream_t)stream;
@@ -2092,6 +2094,7 @@ int ws_solver_factor_begin(ws_solver* s, const double* A_vals, const double* B_v
 
 int ws_solver_factor_end(ws_solver* s, int device, void* stream) {
     WS_API_BEGIN
+    WS_NVTX("ws K8b factor: statistics + accuracy probe");
     WS_REQUIRE(s, "solver == NULL");
     if (!s->factor_pending) throw Error(WS_ERR_STATE, "ws_solver_factor_end without ws_solver_factor_begin");
     s->factor_pending = false;
@@ -2191,6 +2194,7 @@ static void refined_solve(ws_solver* s, const double* b, double* x, cudaStream_t
 
 int ws_solver_solve(ws_solver* s, const double* b, double* x, int nrhs, int device, void* stream) {
     WS_API_BEGIN
+    WS_NVTX("ws K8c solve sweeps");
     WS_REQUIRE(s && b && x && nrhs >= 1, "bad arguments");
     if (!s->factored) throw Error(WS_ERR_STATE, "ws_solver_solve before a successful ws_solver_factor");
     DeviceGuard g(device);

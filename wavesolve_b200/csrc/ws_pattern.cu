@@ -254,6 +254,7 @@ long long ws_launch_count(void) { return ws::g_launches.load(std::memory_order_r
 int ws_edges_first_appearance(const int32_t* tris, int64_t Ne, int64_t Np, int32_t* edges,
                               int32_t* edge_idx, int64_t* h_Ntt, int device, void* stream) {
     WS_API_BEGIN
+    WS_NVTX("ws K1 unique edges");
     WS_REQUIRE(Ne >= 0 && Np >= 0 && h_Ntt, "Ne, Np >= 0 and h_Ntt != NULL");
     WS_REQUIRE(Ne * 3 < ((int64_t)1 << 31), "too many elements for 32-bit edge positions");
     *h_Ntt = 0;
@@ -306,6 +307,7 @@ int ws_edges_first_appearance(const int32_t* tris, int64_t Ne, int64_t Np, int32
 int ws_pattern_create(const int32_t* dofs, int64_t Ne, int64_t N, ws_pattern** out, int device,
                       void* stream) {
     WS_API_BEGIN
+    WS_NVTX("ws K2 pattern");
     WS_REQUIRE(out, "out == NULL");
     *out = nullptr;
     WS_REQUIRE(Ne >= 0 && N >= 0, "Ne, N >= 0");

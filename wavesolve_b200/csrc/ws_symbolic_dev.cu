@@ -457,6 +457,7 @@ extern "C" int ws_symbolic_create_device(const int32_t* dofs, int64_t Ne, int64_
                                          int vert_col, int64_t vert_offset, int64_t first_class_start, int leaf_elems,
                                          ws_symbolic** out, int device, void* stream) {
     WS_API_BEGIN
+    WS_NVTX("ws K8a symbolic analysis");
     WS_REQUIRE(out, "out == NULL");
     *out = nullptr;
     WS_REQUIRE(dofs && xy, "null pointer");

@@ -128,16 +128,17 @@ def _dist():
 
 
 def _to_host(t: torch.Tensor) -> np.ndarray:
-    """Device -> host through page-locked memory for CUDA tensors (a pageable .cpu() of a multi-GB gather
-    payload spends most of its time in page faults)."""
+    """Device -> host for the gather payload: page-locked block for moderate sizes, double-buffered staging into
+    pageable memory for GBs (device.d2h_staged)."""
     if t.is_cuda and t.numel() * t.element_size() >= (1 << 20):
         from . import device as _dev
-        return _dev.d2h_pinned(t)
+        return _dev.d2h_staged(t)
     return t.cpu().numpy()
 
 
 def gather_eigenpairs(local: Dict[int, tuple], n_problems: int, group=None, with_vectors=True,
-                      dst: Optional[int] = None, packed: Optional[torch.Tensor] = None, stats: Optional[dict] = None):
+                      dst: Optional[int] = None, packed: Optional[torch.Tensor] = None, stats: Optional[dict] = None,
+                      own_host: Optional[np.ndarray] = None):
     """Collect per-problem results from all ranks.
 
     ``local``: {problem index: (w tensor (k,), V tensor (k, N), mode_count int[, rc int])} -- tensors on the
@@ -150,7 +151,11 @@ def gather_eigenpairs(local: Dict[int, tuple], n_problems: int, group=None, with
     NVLink on GPUs), so only ``r`` receives and only ``r`` pays the device -> host copy (through pinned memory).
     ``packed``: the flat buffer [w_i | V_i ...] (in ``local``'s insertion order) the tensors of ``local`` are views
     of; it is sent as is (no staging copy).  ``stats``: if a dict, filled with ``bytes`` received / held on this
-    rank and ``seconds`` of the collective + host copy."""
+    rank and ``seconds`` of the collective + host copy.  ``own_host``: a host copy of this rank's packed payload, if the
+    caller already has one; used instead of copying the rank's own block again.  (Streaming the own results to the host
+    while later meshes are solved -- a helper thread, or a landing buffer page-locked in the background -- was measured
+    and is no faster than the staged copy at the end: 48.9 / 51.0 against 53.0 problems/s; both contend with the
+    launching thread for the driver.)"""
     import time as _time
     dist = _dist()
     multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
@@ -217,7 +222,7 @@ def gather_eigenpairs(local: Dict[int, tuple], n_problems: int, group=None, with
     out: List[Optional[tuple]] = [None] * n_problems
     nbytes = 0
     for r, m in enumerate(metas):
-        buf = _to_host(recv[r])
+        buf = own_host if (r == rank and own_host is not None and own_host.size == sizes[r]) else _to_host(recv[r])
         nbytes += buf.nbytes
         off = 0
         for (i, k, n, cnt, rc) in m:
