@@ -31,4 +31,14 @@ $BENCH > gpurun_out/plain_bench_$TAG.log 2>&1 &&
 timeout -s KILL 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 12000 --csv \
     --log-file gpurun_out/launches_$TAG.csv $BENCH > gpurun_out/ncu_bench_$TAG.log 2>&1
 echo "launch list rc=$?"; wc -l gpurun_out/launches_$TAG.csv
+# 4) wide Krylov basis (Nmax = 80): the restart rotation as a DMMA GEMM (k_rotate_mma) and the CGS kernels -- the fp64 / tensor
+#    pipe figures north_star asks for
+WIDE="python tools/wide_basis_solve.py"
+$WIDE > gpurun_out/plain_wide_$TAG.log 2>&1 &&
+timeout -s KILL 600 ncu --set full --clock-control none -k 'regex:k_rotate_mma|k_dots_partial|k_update' -c 12 --launch-skip 600 \
+    -f -o ${REP}_wide $WIDE > gpurun_out/ncu_wide_$TAG.log 2>&1
+echo "wide capture rc=$?"; cat gpurun_out/plain_wide_$TAG.log
+if [ -f ${REP}_wide.ncu-rep ]; then
+  ncu -i ${REP}_wide.ncu-rep --page raw --csv > gpurun_out/prof_${TAG}_wide_raw.csv 2>/dev/null
+fi
 du -sh gpurun_out

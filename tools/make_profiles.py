@@ -35,6 +35,10 @@ KEEP = [
     "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active",
     "smsp__issue_active.avg.pct_of_peak_sustained_active",
     "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
+    "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_tensor.sum",
+    "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_tensor_op_dmma.sum",
+    "sm__pipe_tensor_op_dmma_cycles_active.avg.pct_of_peak_sustained_active", "sm__inst_executed.sum",
+    "smsp__inst_executed_op_shared_ld.sum", "sm__cycles_elapsed.max",
 ]
 
 
@@ -85,14 +89,17 @@ def launches(tag):
     open(os.path.join(P, "%s_launches_by_kernel.txt" % tag), "w").write(out.getvalue())
 
 
-def hot(tag):
-    src = os.path.join(G, "prof_%s_raw.csv" % tag)
+def hot(tag, suffix="", keep_all_matching=None):
+    src = os.path.join(G, "prof_%s%s_raw.csv" % (tag, suffix))
     if not os.path.exists(src):
         return
     rows = list(csv.reader(open(src, newline="")))
     hdr, units = rows[0], rows[1]
-    idx = [hdr.index("Kernel Name"), hdr.index("Grid Size"), hdr.index("Block Size")] + [hdr.index(k) for k in KEEP if k in hdr]
-    with open(os.path.join(P, "%s_hot_kernels_ncu.csv" % tag), "w", newline="") as f:
+    keep = [k for k in KEEP if k in hdr]
+    if keep_all_matching:
+        keep += [h for h in hdr if re.search(keep_all_matching, h) and h not in keep]
+    idx = [hdr.index("Kernel Name"), hdr.index("Grid Size"), hdr.index("Block Size")] + [hdr.index(k) for k in keep]
+    with open(os.path.join(P, "%s%s_hot_kernels_ncu.csv" % (tag, suffix)), "w", newline="") as f:
         w = csv.writer(f)
         w.writerow([hdr[i] for i in idx])
         w.writerow([units[i] for i in idx])
@@ -163,6 +170,7 @@ if __name__ == "__main__":
     os.makedirs(P, exist_ok=True)
     launches(tag)
     hot(tag)
+    hot(tag, "_wide", keep_all_matching=r"tensor|dmma|fp64")
     solve_list(tag)
     bench_line(tag)
     print(sorted(os.listdir(P)))
