@@ -546,7 +546,11 @@ __global__ void __launch_bounds__(256) k_dots_partial(const double* __restrict__
     for (int i = threadIdx.x; i < DOT_CHUNK; i += 256) us[i] = (i < len) ? u[n0 + i] : 0.0;
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int v = warp; v < nvec; v += 8) {
+    // gridDim.y groups of basis vectors: a wide basis on a small problem (Nmax = 80 at N = 100k: 164 vectors, 50 chunks)
+    // would otherwise leave two thirds of the SMs idle while 50 CTAs walk 164 vectors each
+    const int per = (nvec + gridDim.y - 1) / gridDim.y;
+    const int v0 = blockIdx.y * per, v1 = min(nvec, v0 + per);
+    for (int v = v0 + warp; v < v1; v += 8) {
         const double* z = Z + (size_t)v * ldz + n0;
         double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
         int i = lane;
@@ -873,7 +877,9 @@ struct EigWork {
 };
 
 static void dots(EigWork& W, cudaStream_t q, const double* Zb, int nvec, const double* u, double* h, double* hacc) {
-    k_dots_partial<<<W.nchunks, 256, 0, q>>>(Zb, W.N, nvec, u, W.N, W.partial.get());
+    int groups = 1;
+    if (W.nchunks < 2 * kNumSMs && nvec > 8) groups = std::min((nvec + 7) / 8, (2 * kNumSMs + W.nchunks - 1) / W.nchunks);
+    k_dots_partial<<<dim3(W.nchunks, groups), 256, 0, q>>>(Zb, W.N, nvec, u, W.N, W.partial.get());
     k_dots_reduce<<<nvec, 32, 0, q>>>(W.partial.get(), W.nchunks, nvec, h, hacc);
     count_launch(2);
 }
