@@ -16,4 +16,12 @@ restated.py   numpy/scipy restatement of the reference algorithms
               reference file:line it follows.  Pinned against the literal reference by
               ``oracle/make_golden.py`` -> ``tests/golden/*.npz``.
 make_golden.py  regenerates the golden fixtures from the literal reference.
+make_golden_at_size.py  one-off CPU runs of the BASELINE configs at their STATED sizes (C2 50k and C4 1M triangles
+              through restated.py, C3 200k through the literal solve_waveguide): eigenvalues, mode count, mesh
+              digests and the CPU timing (1545 s for C4 -- the same-configuration CPU baseline) ->
+              tests/golden/c2_vec_50k.npz, c3_lantern_200k.npz, c4_vec_1M.npz.
+
+Parity status: PINNED -- restated.py is checked against fixtures the literal reference produced
+(tests/test_oracle_golden.py), against the literal reference run live on random meshes in the build container
+(tests/test_oracle_live_reference.py), and its at-size eigenvalues are what the GPU tests assert.
 """
