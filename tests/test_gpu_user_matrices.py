@@ -86,3 +86,36 @@ def test_misuse_is_refused(ws):
     with pytest.raises(TypeError):
         ws.solve_sparse(A.astype(np.complex128), B, mesh, K, ior)
     assert sp.issparse(A)
+
+
+def test_legacy_dense_solve_all_eigenpairs(ws):
+    """fe_solver.py:220-260: solve(A, B, mesh, k, IOR_dict) = scipy.linalg.eigh(A, B) for ALL eigenpairs, descending."""
+    import scipy.linalg as sla
+    from oracle import restated as R
+    mg = ws.meshgen
+    mesh = mg.fiber_disc(300, seed=4)
+    k = 2 * np.pi / 1.55
+    A, B = R.construct_AB_order2(mesh, mg.FIBER_IOR, k)
+    Ad, Bd = A.toarray(), B.toarray()
+    w, v, cnt = ws.solve(Ad.copy(), Bd.copy(), mesh, k, mg.FIBER_IOR)
+    wr, vr = sla.eigh(Ad, Bd)
+    wr, vr = wr[::-1], vr.T[::-1]
+    assert w.shape == wr.shape and v.shape == vr.shape
+    assert np.allclose(w, wr, rtol=1e-9, atol=1e-9 * abs(wr).max())
+    assert cnt == R.count_modes_scalar(wr, k, mg.FIBER_IOR)
+    G = v @ Bd @ v.T
+    assert np.allclose(G, np.eye(len(w)), atol=1e-8)                 # B-orthonormal like scipy's eigh
+    for i in range(3):                                               # the guided modes, up to sign
+        assert abs(v[i] @ Bd @ vr[i]) >= 1 - 1e-8 or abs(w[i] - w[i + 1]) < 1e-6 * abs(w[i]) or abs(w[i] - w[i - 1]) < 1e-6 * abs(w[i])
+    w2, v2, c2 = ws.solve(A, B, mesh, k, mg.FIBER_IOR)              # sparse inputs are densified
+    assert np.allclose(w2, w)
+
+
+def test_real_output_option(ws):
+    mg = ws.meshgen
+    mesh = mg.fiber_disc(3000, order=1, seed=5)
+    ws.get_unique_edges(mesh)
+    w, v, c = ws.solve_waveguide_vec(mesh, 1.55, mg.FIBER_IOR, Nmax=4, verbose=False)
+    wr, vr, cr = ws.solve_waveguide_vec(mesh, 1.55, mg.FIBER_IOR, Nmax=4, verbose=False, real_output=True)
+    assert w.dtype == np.complex128 and wr.dtype == np.float64 and vr.dtype == np.float64 and c == cr
+    assert np.array_equal(w.real, wr) and np.array_equal(v.real, vr)

@@ -620,6 +620,39 @@ def solve_sparse(A, B, mesh, k, IOR_dict, plot=False, num_modes=6, device=None, 
     return w, v, mode_count
 
 
+def solve(A, B, mesh, k, IOR_dict, plot=False, device=None):
+    """The legacy dense eigensolve (fe_solver.py:220-260): ALL eigenpairs of the dense pencil ``A v = w B v``
+    (``scipy.linalg.eigh(A, B)`` in the reference), returned as ``(w descending, v rows, mode_count)``.
+
+    Not part of the sparse hot path: a dense generalized symmetric eigenproblem for every eigenpair is a LAPACK job,
+    and on the device it is a library job too -- Cholesky ``B = L L^T``, ``C = L^-1 A L^-T``, ``eigh(C)``,
+    ``v = L^-T y`` through torch.linalg (cuSOLVER), so that the reference's full API is served from the GPU.  Like the
+    reference it is only sensible for small N (the reference warns above 2000 x 2000)."""
+    dev = _dev.require_cuda(device)
+    if sp.issparse(A):
+        A = A.toarray()
+    if sp.issparse(B):
+        B = B.toarray()
+    A = np.asarray(A, dtype=np.float64)
+    B = np.asarray(B, dtype=np.float64)
+    if A.ndim != 2 or A.shape[0] != A.shape[1] or A.shape != B.shape:
+        raise ValueError("A and B must be square matrices of the same shape")
+    with torch.cuda.device(dev):
+        Ad, Bd = _dev.h2d(A, dev), _dev.h2d(B, dev)
+        Ld = torch.linalg.cholesky(Bd)                            # eigh(A, B) requires B positive definite as well
+        Cd = torch.linalg.solve_triangular(Ld, Ad, upper=False)
+        Cd = torch.linalg.solve_triangular(Ld, Cd.T.contiguous(), upper=False).T
+        Cd = 0.5 * (Cd + Cd.T)
+        wd, Yd = torch.linalg.eigh(Cd)
+        Vd = torch.linalg.solve_triangular(Ld.T.contiguous(), Yd, upper=True)     # columns B-orthonormal, like scipy's eigh
+        w = _dev.d2h(wd)[::-1]
+        v = _dev.d2h(Vd).T[::-1]
+    mode_count = _count_modes(w, k, IOR_dict)
+    if plot:
+        _report_modes(2 * np.pi / k, w, k, IOR_dict, warn_always=True)
+    return w, v, mode_count
+
+
 def compute_IOR_arr(mesh, IOR_dict):
     """Refractive index per element in ``cells[1].data`` order (fe_solver.py:446-452); elements
     in no material set stay 0, a later set overwrites an earlier one."""
@@ -680,7 +713,7 @@ def solve_scalar_resident(prob, sigma, Nmax, leaf_elems=None, symbolic=None, sol
 
 def solve_waveguide_vec(mesh, wl, IOR_dict, plot=False, ignore_warning=False, sparse=True, Nmax=10,
                         target_neff=None, sparse_solve_mode='transform', verbose=True, device=None,
-                        leaf_elems=None):
+                        leaf_elems=None, real_output=False):
     """Vector modes with Whitney edge + P1 node elements (fe_solver.py:350-425).  Returns
     ``(w, v, N)``; ``v`` rows have unit 2-norm (edge unknowns first, then nodes).
 
@@ -690,7 +723,11 @@ def solve_waveguide_vec(mesh, wl, IOR_dict, plot=False, ignore_warning=False, sp
     dense N x N matrix C.  'transform'/'pardiso' return complex128 like scipy's eigs; 'straight'
     (eigsh on an indefinite B, which the reference's author documents as unreliable) returns
     float64 with the *correct* eigenpairs.  Eigenvalues are returned sorted by descending real
-    part (ARPACK's own order is not reproducible by any other implementation)."""
+    part (ARPACK's own order is not reproducible by any other implementation).
+
+    ``real_output=True`` (extension): return float64 ``w`` / ``v`` in every mode.  The complex128 container scipy's
+    ``eigs`` imposes carries a zero imaginary part (the iteration is real); at 1M triangles it doubles the result
+    to 320 MB and costs ~7 ms of the device -> host copy."""
     from . import solver as _sv
     assert mesh.cells[1].data.shape[1] == 3, "must use order 1 mesh for vectorial solver"
     assert sparse_solve_mode in ["straight", "transform", "pardiso"], "sparse solve mode must be `straight` (plug into eigenproblem into eigsh) or `transform` (use spsolve to convert into an ordinary eigenproblen, then use eigs)"
@@ -709,7 +746,7 @@ def solve_waveguide_vec(mesh, wl, IOR_dict, plot=False, ignore_warning=False, sp
         print("solving...")
     with torch.cuda.device(prob.dev):
         wd, Vd, info = solve_vector_resident(prob, est_eigval, Nmax, leaf_elems)
-        if sparse and sparse_solve_mode in ("transform", "pardiso"):
+        if sparse and sparse_solve_mode in ("transform", "pardiso") and not real_output:
             wd, Vd = _dev.as_complex(wd), _dev.as_complex(Vd)   # scipy.sparse.linalg.eigs returns complex arrays
         w = _dev.d2h(wd)
         v = _dev.d2h_pinned(Vd)
