@@ -10,7 +10,7 @@ ws.get_unique_edges(mesh)
 ior = mg.LANTERN_IOR
 k = 2*np.pi/1.55
 dev = torch.device("cuda", 0)
-nl = 4
+nl = int(os.environ.get("NL", "4"))
 ctxs = [sweep._MeshContext(mesh, "vector", ior, k, dev, None) for _ in range(nl)]
 sigma = float((k*max(ior.values()))**2)
 N = ctxs[0].prob.N
@@ -23,7 +23,7 @@ streams = [torch.cuda.Stream() for _ in range(nl)]
 bs = [torch.randn(N, dtype=torch.float64, device=dev) for _ in range(nl)]
 xs = [torch.empty_like(b) for b in bs]
 torch.cuda.synchronize()
-for n_act in (1, 2, 4):
+for n_act in [int(x) for x in os.environ.get("ACT", "1,2,4").split(",")]:
     for rep in range(2):
         torch.cuda.synchronize(); t0 = time.perf_counter()
         for it in range(100):
