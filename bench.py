@@ -291,7 +291,9 @@ def run_sweep_slice(args, dev, rank, world):
         ws.get_unique_edges(m)
     wls = np.linspace(1.0, 1.8, n_wl)
     probs = sweep.problem_grid(n_mesh, wls, mg.LANTERN_IOR, tags=[float(r) for r in radii])
-    sweep.solve_sweep(meshes[:1], probs[:2], Nmax=NMAX, kind="vector", dst=0)       # warm-up: kernels, pools, NCCL p2p
+    # warm-up: kernels, memory pools and the NCCL point-to-point connections of EVERY rank to rank 0 (set up lazily on
+    # first use, ~0.5 s per peer: a one-off per process, like the communicator itself) -- one problem per rank
+    sweep.solve_sweep(meshes[:1], probs[:max(2, world)], Nmax=NMAX, kind="vector", dst=0)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()

@@ -327,6 +327,12 @@ int ws_overlap(const ws_pattern* p, const double* vals, const double* U, int64_t
 int ws_bnormalize(const ws_pattern* p, const double* vals, double* U, int64_t ldu, int nu, double* d, int scale,
                   int device, void* stream);
 
+/* ---- K12, host side: device -> pageable host memory for GB-sized gather payloads --------------------------
+ * Two reusable page-locked staging blocks (64 MB each, kept for the life of the process); the DMA of chunk i+1
+ * overlaps `nthreads` host threads copying chunk i into h_dst (<= 0: a default from the core count).  Synchronous:
+ * returns when h_dst is complete.  (Page-locking a 2 GB landing buffer costs ~2 s; this path moves it in ~0.25 s.) */
+int ws_copy_to_host(const void* d_src, void* h_dst, int64_t nbytes, int nthreads, int device, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

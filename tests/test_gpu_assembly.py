@@ -288,7 +288,7 @@ def test_pinned_result_buffers_are_recycled(ws):
 def test_staged_d2h_of_a_large_result(ws):
     """GB-scale gather payloads come back through two reusable pinned staging blocks into pageable memory."""
     from wavesolve_b200 import device as d
-    n = (3 * d._STAGE_BYTES) // 8 + 12345
+    n = (3 * (64 << 20)) // 8 + 12345
     x = torch.arange(n, dtype=torch.float64, device="cuda") * 0.5
     a = d.d2h_staged(x)
     assert a.dtype == np.float64 and a.shape == (n,) and a[0] == 0.0 and a[-1] == (n - 1) * 0.5

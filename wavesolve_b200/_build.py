@@ -26,6 +26,7 @@ SOURCES = {
     "ws_eig.cu": [],
     "ws_interp.cu": ["-fmad=false"],
     "ws_overlap.cu": [],
+    "ws_hostcopy.cu": [],
 }
 
 

@@ -78,6 +78,7 @@ _SIGNATURES = {
     "ws_overlap": (c_int, [c_vp, c_vp, c_vp, c_i64, c_int, c_vp, c_i64, c_int, c_vp, c_int, c_vp]),
     "ws_bnormalize": (c_int, [c_vp, c_vp, c_vp, c_i64, c_int, c_vp, c_int, c_int, c_vp]),
     "ws_vector_T": (c_int, [c_vp, c_vp, c_vp, c_i64, c_int, c_vp, c_vp, c_int, c_vp]),
+    "ws_copy_to_host": (c_int, [c_vp, c_vp, c_i64, c_int, c_int, c_vp]),
 }
 
 

@@ -86,51 +86,26 @@ def d2h_pinned(t: torch.Tensor) -> np.ndarray:
     return arr
 
 
-_stage_lock = threading.Lock()
-_stage = []                # two page-locked staging blocks, created on first use and kept
-_STAGE_BYTES = 64 << 20
-
-
 def d2h_staged(t: torch.Tensor, out: np.ndarray = None) -> np.ndarray:
-    """Device -> host copy of a VERY large result (a gathered sweep: GBs) into ordinary pageable memory through two
-    reusable page-locked staging blocks: the DMA of chunk i+1 overlaps the host memcpy of chunk i.  Page-locking the
-    destination itself costs ~1 s per GB (measured: 2.0 s for the 2.06 GB of a 256-problem sweep), which is more
-    than the whole transfer at PCIe rate."""
+    """Device -> host copy of a VERY large result (a gathered sweep: GBs) into ordinary pageable memory through the
+    library's two reusable page-locked staging blocks (``ws_copy_to_host``): the DMA of chunk i+1 overlaps a few host
+    threads copying chunk i out.  Page-locking the destination itself costs ~1 s per GB (measured: 2.0 s for the
+    2.06 GB of a 256-problem sweep), more than the whole transfer at PCIe rate; a Python-level staged copy is bound by
+    numpy's single-threaded memcpy into freshly mapped pages (0.6 s)."""
     t = t.detach().contiguous()
     nbytes = t.numel() * t.element_size()
-    if out is None and nbytes < 2 * _STAGE_BYTES:
+    if out is None and nbytes < (128 << 20):
         return d2h_pinned(t)
-    if nbytes == 0:
-        return out if out is not None else np.empty(tuple(t.shape), dtype=np.dtype(str(t.dtype).replace("torch.", "")))
-    src = t.view(-1).view(torch.uint8) if t.dtype != torch.uint8 else t.view(-1)
+    dt = np.dtype(str(t.dtype).replace("torch.", ""))
     ret = out
     if out is None:
-        out = np.empty(nbytes, dtype=np.uint8)
-    else:                                    # caller-provided destination (any dtype, contiguous, same byte size)
+        out = np.empty(tuple(t.shape), dtype=dt)
+    else:
         assert out.flags.c_contiguous and out.nbytes == nbytes
-        out = out.reshape(-1).view(np.uint8)
-    with _stage_lock:
-        while len(_stage) < 2:
-            _stage.append(torch.empty(_STAGE_BYTES, dtype=torch.uint8, pin_memory=True))
-        evs = [torch.cuda.Event(), torch.cuda.Event()]
-        offs = list(range(0, nbytes, _STAGE_BYTES))
-        pending = None
-        for j, o in enumerate(offs):
-            n = min(_STAGE_BYTES, nbytes - o)
-            b = j & 1
-            _stage[b][:n].copy_(src[o:o + n], non_blocking=True)
-            evs[b].record()
-            if pending is not None:
-                po, pn, pb = pending
-                evs[pb].synchronize()
-                out[po:po + pn] = _stage[pb][:pn].numpy()
-            pending = (o, n, b)
-        po, pn, pb = pending
-        evs[pb].synchronize()
-        out[po:po + pn] = _stage[pb][:pn].numpy()
-    if ret is not None:
-        return ret
-    return out.view(np.dtype(str(t.dtype).replace("torch.", ""))).reshape(tuple(t.shape))
+    if nbytes:
+        _lib.check(_lib.lib().ws_copy_to_host(t.data_ptr(), out.ctypes.data, nbytes, 0, t.device.index,
+                                              torch.cuda.current_stream(t.device).cuda_stream))
+    return ret if ret is not None else out
 
 
 def as_complex(t: torch.Tensor) -> torch.Tensor:
