@@ -21,6 +21,7 @@
 #include <cstdlib>
 #include <memory>
 #include <numeric>
+#include <thread>
 
 #include "ws_solver.cuh"
 
@@ -1838,31 +1839,37 @@ int ws_eig_solve_batch(ws_eig_job* jobs, int njobs, int device) {
             runs[i]->init();
         });
     }
+    // Event-driven, not lockstep: whichever job's restart cycle has finished is analysed and gets its next cycle
+    // enqueued at once, so the jobs drift out of phase and the device always has the other jobs' cycles queued while
+    // the host works on one (a barrier per cycle left the GPU idle for the host analysis of every job in turn).
     const bool btrace = getenv("WS_BATCH_TRACE") != nullptr;
-    double t_enq = 0, t_fin = 0;
-    int ncycles = 0;
-    for (;;) {
-        bool any = false;
-        const double t0 = EigRun::now();
-        for (int i = 0; i < njobs; ++i)
-            if (state[i] == 0) any = guarded(i, [&] { runs[i]->enqueue_cycle(); }) || any;
-        if (!any) break;
-        const double t1 = EigRun::now();
-        for (int i = 0; i < njobs; ++i)
-            if (state[i] == 0)
-                guarded(i, [&] {
-                    if (runs[i]->finish_cycle()) {
-                        runs[i]->enqueue_results();
-                        state[i] = 1;
-                    }
-                });
-        t_enq += t1 - t0;
-        t_fin += EigRun::now() - t1;
-        ++ncycles;
+    const double tb0 = EigRun::now();
+    int ncycles = 0, active = 0;
+    for (int i = 0; i < njobs; ++i)
+        if (state[i] == 0 && guarded(i, [&] { runs[i]->enqueue_cycle(); })) ++active;
+    while (active > 0) {
+        bool progressed = false;
+        for (int i = 0; i < njobs; ++i) {
+            if (state[i] != 0) continue;
+            const cudaError_t q = cudaEventQuery(runs[i]->ev);
+            if (q == cudaErrorNotReady) continue;
+            progressed = true;
+            ++ncycles;
+            const bool ok = guarded(i, [&] {
+                if (q != cudaSuccess) throw Error(WS_ERR_CUDA, std::string("cudaEventQuery: ") + cudaGetErrorString(q));
+                if (runs[i]->finish_cycle()) {
+                    runs[i]->enqueue_results();
+                    state[i] = 1;
+                } else {
+                    runs[i]->enqueue_cycle();
+                }
+            });
+            if (!ok || state[i] != 0) --active;
+        }
+        if (!progressed) std::this_thread::yield();
     }
     if (btrace)
-        fprintf(stderr, "[ws_eig_solve_batch] %d jobs, %d cycles: host enqueue %.1f ms, wait + restart analysis %.1f ms\n", njobs, ncycles,
-                t_enq * 1e3, t_fin * 1e3);
+        fprintf(stderr, "[ws_eig_solve_batch] %d jobs, %d cycles, %.1f ms\n", njobs, ncycles, (EigRun::now() - tb0) * 1e3);
     for (int i = 0; i < njobs; ++i)
         if (state[i] == 1) {
             if (guarded(i, [&] { runs[i]->finish(jobs[i].info, jobs[i].resid); })) state[i] = 2;
