@@ -540,11 +540,11 @@ constexpr int MAX_NCV = 256;    // largest Krylov basis: Nmax = 100 (lantern-dem
 // partial[c*nvec + i] = sum over chunk c of Z_i[n] * u[n];  8 warps, warp w takes vectors w, w+8, ...
 __global__ void __launch_bounds__(256) k_dots_partial(const double* __restrict__ Z, int64_t ldz, int nvec,
                                                       const double* __restrict__ u, int64_t N,
-                                                      double* __restrict__ partial) {
+                                                      double* __restrict__ partial, int chunk) {
     __shared__ double us[DOT_CHUNK];
-    const int64_t n0 = (int64_t)blockIdx.x * DOT_CHUNK;
-    const int len = (int)min((int64_t)DOT_CHUNK, N - n0);
-    for (int i = threadIdx.x; i < DOT_CHUNK; i += 256) us[i] = (i < len) ? u[n0 + i] : 0.0;
+    const int64_t n0 = (int64_t)blockIdx.x * chunk;
+    const int len = (int)min((int64_t)chunk, N - n0);
+    for (int i = threadIdx.x; i < chunk; i += 256) us[i] = (i < len) ? u[n0 + i] : 0.0;
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // gridDim.y groups of basis vectors: a wide basis on a small problem (Nmax = 80 at N = 100k: 164 vectors, 50 chunks)
@@ -603,18 +603,18 @@ __global__ void __launch_bounds__(256) k_update(double* __restrict__ w, const do
 // with the updated entries, for the partial dots.  partial has the layout of k_dots_partial.
 constexpr int UD_TILE = 256;
 __global__ void __launch_bounds__(256) k_update_dots(double* __restrict__ w, const double* __restrict__ V, int64_t ldv, int nvec,
-                                                     const double* __restrict__ h, int64_t N, double* __restrict__ partial) {
+                                                     const double* __restrict__ h, int64_t N, double* __restrict__ partial, int chunk) {
     extern __shared__ double uds[];            // [nvec][UD_TILE] basis tile, then [UD_TILE] updated w
     __shared__ double hs[MAXV];
     double* Vs = uds;
     double* ws_ = uds + (size_t)nvec * UD_TILE;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid < nvec) hs[tid] = h[tid];
-    const int64_t c0 = (int64_t)blockIdx.x * DOT_CHUNK;
+    const int64_t c0 = (int64_t)blockIdx.x * chunk;
     double dsum[MAXV / 8];
 #pragma unroll
     for (int i = 0; i < MAXV / 8; ++i) dsum[i] = 0.0;
-    for (int t0 = 0; t0 < DOT_CHUNK; t0 += UD_TILE) {
+    for (int t0 = 0; t0 < chunk; t0 += UD_TILE) {
         const int64_t n0 = c0 + t0;
         if (n0 >= N) break;
         const int len = (int)min((int64_t)UD_TILE, N - n0);
@@ -875,12 +875,16 @@ struct EigWork {
     cudaStream_t st;
     DevBuf<double> V, Z, w, t1, t2, t3, partial, h, Hd, nrm, Q;
     int nchunks;
+    int chunk = DOT_CHUNK;      // rows per CTA of the dot kernels: 2048, or 512 for small problems (more CTAs than SMs)
 };
+// (wide bases get their parallelism from the vector groups of k_dots_partial and prefer the long chunk: Nmax = 80 at
+//  N = 100k runs 493 ms with 2048-row chunks, 531 ms with 512)
+static int dot_chunk_for(int64_t N, int m) { return (m <= 64 && N < 148 * 4 * (int64_t)DOT_CHUNK / 2) ? 512 : DOT_CHUNK; }
 
 static void dots(EigWork& W, cudaStream_t q, const double* Zb, int nvec, const double* u, double* h, double* hacc) {
     int groups = 1;
     if (W.nchunks < 2 * kNumSMs && nvec > 8) groups = std::min((nvec + 7) / 8, (2 * kNumSMs + W.nchunks - 1) / W.nchunks);
-    k_dots_partial<<<dim3(W.nchunks, groups), 256, 0, q>>>(Zb, W.N, nvec, u, W.N, W.partial.get());
+    k_dots_partial<<<dim3(W.nchunks, groups), 256, 0, q>>>(Zb, W.N, nvec, u, W.N, W.partial.get(), W.chunk);
     k_dots_reduce<<<nvec, 32, 0, q>>>(W.partial.get(), W.nchunks, nvec, h, hacc);
     count_launch(2);
 }
@@ -1340,7 +1344,7 @@ struct EigRun {
             // share one pass over the basis -- three basis reads per step instead of four
             dots(W, q, V, nv, W.w.get(), W.h.get(), Hcol);
             k_update_dots<<<W.nchunks, 256, (size_t)(nv + 1) * UD_TILE * sizeof(double), q>>>(W.w.get(), V, N, nv, W.h.get(), N,
-                                                                                         W.partial.get());
+                                                                                         W.partial.get(), W.chunk);
             k_dots_reduce<<<nv, 32, 0, q>>>(W.partial.get(), W.nchunks, nv, W.h.get(), Hcol);
             k_update<<<nb, T, (size_t)nv * sizeof(double), q>>>(W.w.get(), V, N, nv, W.h.get(), N);
             count_launch(3);
@@ -1407,7 +1411,8 @@ struct EigRun {
             for (auto& e : graphs.exec)
                 if (e) cudaGraphExecDestroy(e);
             W.N = N; W.ncv = m; W.st = st;
-            W.nchunks = ceil_div(N, DOT_CHUNK);
+            W.chunk = dot_chunk_for(N, m);
+            W.nchunks = ceil_div(N, W.chunk);
             W.V.alloc((size_t)(m + 1) * N, st);
             if (kind == 0) W.Z.alloc((size_t)(m + 1) * N, st);
             else W.Z.release();
@@ -1847,6 +1852,23 @@ int ws_eig_solve_batch(ws_eig_job* jobs, int njobs, int device) {
     int ncycles = 0, active = 0;
     for (int i = 0; i < njobs; ++i)
         if (state[i] == 0 && guarded(i, [&] { runs[i]->enqueue_cycle(); })) ++active;
+    static const bool lockstep = getenv("WS_BATCH_LOCKSTEP") && atoi(getenv("WS_BATCH_LOCKSTEP"));
+    while (active > 0 && lockstep) {
+        // (A/B switch: barrier per cycle -- wait for every job, then analyse and re-enqueue every job)
+        for (int i = 0; i < njobs; ++i)
+            if (state[i] == 0) {
+                ++ncycles;
+                const bool ok = guarded(i, [&] {
+                    if (runs[i]->finish_cycle()) {
+                        runs[i]->enqueue_results();
+                        state[i] = 1;
+                    }
+                });
+                if (!ok || state[i] != 0) --active;
+            }
+        for (int i = 0; i < njobs; ++i)
+            if (state[i] == 0 && !guarded(i, [&] { runs[i]->enqueue_cycle(); })) --active;
+    }
     while (active > 0) {
         bool progressed = false;
         for (int i = 0; i < njobs; ++i) {
