@@ -175,6 +175,20 @@ def test_sweep_matches_individual_solves():
         assert r.mode_count == cnt
         assert r.v.shape == v.shape
         assert np.allclose(np.linalg.norm(r.v, axis=1), 1.0, atol=1e-12)
+    # and against the ORACLE directly (not only against this package's single solves): first and last problem
+    from oracle import restated as R
+    from tests import util
+    for i in (0, len(probs) - 1):
+        pr = probs[i]
+        wr, vr, cr = R.solve_waveguide_vec(meshes[pr.mesh_id], pr.wl, pr.IOR_dict, Nmax=6)
+        order = np.argsort(-wr.real, kind="stable")
+        k = 2 * np.pi / pr.wl
+        assert np.allclose(np.sqrt(res3[i].w) / k, np.sqrt(wr.real[order]) / k, rtol=1e-10, atol=0)
+        assert res3[i].mode_count == R.count_modes_vec(wr.real[order], k, pr.IOR_dict, None)
+        for grp in util.group_degenerate(wr.real[order], rtol=1e-5):
+            if grp[-1] == 5:
+                continue
+            assert util.subspace_overlap(res3[i].v[grp], vr[order][grp].real) >= 1 - 1e-8
 
 
 @pytest.mark.gpu
