@@ -7,7 +7,7 @@ import wavesolve_b200 as ws
 from wavesolve_b200 import fe_solver as fs, solver as sv
 mg = ws.meshgen
 k = 2 * np.pi / 1.55
-for seed in (0, 1, 2):
+for seed in [int(x) for x in os.environ.get("WS_SEEDS", "0,1,2").split(",")]:
     mesh = mg.fiber_disc(1_000_000, order=1, seed=seed)
     ws.get_unique_edges(mesh)
     sigma = (k * max(mg.FIBER_IOR.values())) ** 2
