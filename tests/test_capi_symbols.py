@@ -35,6 +35,22 @@ def test_argument_errors_do_not_need_a_gpu():
     assert b"pattern" in L.ws_last_error()
 
 
+def test_batch_api_structs_and_argument_errors():
+    """ws_eig_job is mirrored field by field in _lib.EigJob (static_assert(sizeof == 400) on the C side); handles that
+    own no device memory can be created and destroyed without a GPU; bad arguments come back as status codes."""
+    from wavesolve_b200 import _lib
+    L = _lib.lib()
+    assert ctypes.sizeof(_lib.EigJob) == 400
+    assert _lib.EigJob.info.offset == 128 and _lib.EigJob.rc.offset == 168 and _lib.EigJob.error.offset == 172
+    h = ctypes.c_void_p()
+    assert L.ws_eig_workspace_create(ctypes.byref(h)) == 0 and h.value
+    assert L.ws_eig_workspace_destroy(h) == 0
+    assert L.ws_eig_solve_batch(None, 0, 0) < 0
+    assert L.ws_solver_quality(None, None, None) < 0 and b"solver" in L.ws_last_error()
+    assert L.ws_solver_factor_end(None, 0, None) < 0
+    assert L.ws_copy_to_host(None, None, -1, 0, 0, None) < 0
+
+
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
 def test_product_fails_loudly_without_cuda():
     import wavesolve_b200 as w

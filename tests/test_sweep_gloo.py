@@ -61,6 +61,10 @@ def test_problem_grid_is_mesh_major_and_carries_tags():
     assert sorted(len(t) for t in table) == [8, 8]
 
 
+def test_default_lanes_by_problem_size():
+    assert sweep.default_lanes(100_000) == 8 and sweep.default_lanes(500_000) == 2 and sweep.default_lanes(2_000_000) == 1
+
+
 def test_partition_edge_cases():
     assert sweep.partition([], [], 4) == [[], [], [], []]
     assert sweep.partition([3], [2.0], 1) == [[0]]

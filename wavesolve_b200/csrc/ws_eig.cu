@@ -1764,6 +1764,7 @@ void eig_configure(EigRun& R, const ws_pattern* p, ws_solver* s, const double* B
 struct ws_eig_workspace {
     EigRun run;
 };
+static_assert(sizeof(ws_eig_job) == 400, "ws_eig_job layout is mirrored by wavesolve_b200/_lib.py:EigJob");
 
 int ws_eig_solve(const ws_pattern* p, ws_solver* s, const double* B_vals, double sigma, int kind, int nev, int ncv,
                  double tol, int maxit, uint64_t seed, const int32_t* edges, const double* xy, int64_t Ntt,
