@@ -533,7 +533,9 @@ def run_ours(args):
         "spmv": {"kernel_ms": spmv_ms, "GBps": (12 * nnz + 20 * N) / (spmv_ms * 1e-3) / 1e9,
                  "frac_of_peak": (12 * nnz + 20 * N) / (spmv_ms * 1e-3) / 1e9 / peak},
         "factor": {"ms": factor_ms, "first_call_ms": factor_first_ms, "flops": fstat["flops"], "TFLOPs": fstat["flops"] / (factor_ms * 1e-3) / 1e12,
-                   "nnzL": fstat["nnzL"], "sweep_entries": sweep_entries, "fronts": fstat["fronts"], "max_front": fstat["maxfront"]},
+                   "nnzL": fstat["nnzL"], "sweep_entries": sweep_entries, "fronts": fstat["fronts"], "max_front": fstat["maxfront"],
+                   "accuracy_guard": {"probe_backward_error": fstat.get("backward_error"), "perturbed_pivots": fstat.get("perturbed_pivots"),
+                                      "refine_steps_per_solve": fstat.get("refine_steps"), "pivot_threshold": fstat.get("pivot_threshold")}},
         "eig": {"op_applications": n_op, "restarts": int(stats.get("restarts", 0)), "converged": int(stats.get("nconv", 0))},
         "roofline": {"bound": "hbm", "kernel": "k_fwd_front/k_fwd_tile + k_bwd_tile/k_bwd_front (one shift-invert solve = both sweeps "
                                                "over the inverted panels, one launch per tree level and direction; %d solves per "
