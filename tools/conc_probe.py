@@ -1,3 +1,7 @@
+#!/usr/bin/env python
+"""How many independent shift-invert solves of a ~100k-unknown problem a B200 overlaps when ONE host thread enqueues them
+round-robin on several streams (NL solvers, ACT = numbers of streams to try): 0.355 ms per solve alone, 0.112 ms with 4
+streams, 0.070 ms with 8 (then bound by the host's launch rate).  The measurement behind sweep.default_lanes."""
 import os, sys, time
 import numpy as np
 sys.path.insert(0, '/root/repo')
