@@ -173,7 +173,7 @@ int ws_symbolic_destroy(ws_symbolic* s);
  *                    1e-11 (never a silently inaccurate factorisation).  While refine steps > 0 the value
  *                    arrays must stay alive until the last solve (the residual b - M x is formed from them).
  * ws_solver_quality: h_info[4] = perturbed pivots, refinement steps per solve, refinement steps the probe
- *                    needed, 0;  h_dinfo[4] = probe backward error before / after refinement, max|M_ij|,
+ *                    needed, unique id of this solver object;  h_dinfo[4] = probe backward error before / after refinement, max|M_ij|,
  *                    pivot threshold.
  * ws_solver_solve  : x = M^-1 b, nrhs right-hand sides stored contiguously [nrhs*N]; asynchronous.
  *                    Right-hand sides are swept in pairs that share every load of the inverted

@@ -1223,6 +1223,7 @@ struct PinnedBuf {
     double* p = nullptr;
     size_t n = 0;
     void alloc(size_t n_) {
+        if (p && n == n_) return;           // (page-locking is slow: a work space that moves to the next mesh keeps its blocks)
         release();
         n = n_;
         if (n) WS_CUDA(cudaMallocHost((void**)&p, n * sizeof(double)));
@@ -1280,6 +1281,8 @@ struct EigRun {
     bool trace = false, etrace = false;
     std::vector<cudaEvent_t> evs;
     double wall0 = 0, tr_op = 0, tr_host = 0, tr_rot = 0, tr_t0 = 0;
+    double t_capture = 0;                   // host time spent capturing / instantiating step graphs (this work space's life)
+    int n_capture = 0;
 
     ~EigRun() {
         if (ev) cudaEventDestroy(ev);
@@ -1361,11 +1364,17 @@ struct EigRun {
     // (stream capture on a private stream) and replayed on the caller's stream, so an eigensolve costs ~10^2
     // host launches instead of ~7000 and does not depend on host latency
     void run_step(int j) {
-        if (!use_graphs) {
+        // Steps below nev only ever run in the first restart cycle of a problem (a thick restart keeps at least nev
+        // directions), so a graph of such a step is replayed once per problem: capturing + instantiating it (~0.4 ms
+        // of host time) costs more than launching its ~36 kernels directly (~0.08 ms).  Graphs pay for the steps
+        // that recur in every cycle.
+        static const int graph_from = getenv("WS_GRAPH_FROM") ? atoi(getenv("WS_GRAPH_FROM")) : -1;
+        if (!use_graphs || j < (graph_from >= 0 ? graph_from : nev)) {
             arnoldi_step(st, j);
             return;
         }
         if (!graphs.exec[j]) {
+            const double tc0 = now();
             cudaGraph_t g = nullptr;
             WS_CUDA(cudaStreamBeginCapture(graphs.cap, cudaStreamCaptureModeThreadLocal));
             try {
@@ -1379,6 +1388,8 @@ struct EigRun {
             cudaError_t e = cudaGraphInstantiate(&graphs.exec[j], g, 0);
             cudaGraphDestroy(g);
             if (e != cudaSuccess) throw Error(WS_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e));
+            t_capture += now() - tc0;
+            ++n_capture;
         }
         WS_CUDA(cudaGraphLaunch(graphs.exec[j], st));
         count_launch(1);
@@ -1390,11 +1401,11 @@ struct EigRun {
     // paid once per mesh instead of once per problem.
     struct Key {
         const void *p = nullptr, *s = nullptr, *B = nullptr, *edges = nullptr, *xy = nullptr, *st = nullptr;
-        int64_t N = 0, Ntt = 0;
+        int64_t N = 0, Ntt = 0, solver_uid = -1;
         int kind = -1, m = 0, refine = -1;
         bool operator==(const Key& o) const {
             return p == o.p && s == o.s && B == o.B && edges == o.edges && xy == o.xy && st == o.st && N == o.N && Ntt == o.Ntt &&
-                   kind == o.kind && m == o.m && refine == o.refine;
+                   solver_uid == o.solver_uid && kind == o.kind && m == o.m && refine == o.refine;
         }
     } key;
 
@@ -1407,6 +1418,7 @@ struct EigRun {
         Key k2;
         k2.p = p; k2.s = s; k2.B = B_vals; k2.edges = edges; k2.xy = xy; k2.st = st; k2.N = N; k2.Ntt = Ntt; k2.kind = kind; k2.m = m;
         k2.refine = (int)qi[1];
+        k2.solver_uid = qi[3];
         if (!(k2 == key)) {
             for (auto& e : graphs.exec)
                 if (e) cudaGraphExecDestroy(e);
@@ -1891,8 +1903,13 @@ int ws_eig_solve_batch(ws_eig_job* jobs, int njobs, int device) {
         }
         if (!progressed) std::this_thread::yield();
     }
-    if (btrace)
-        fprintf(stderr, "[ws_eig_solve_batch] %d jobs, %d cycles, %.1f ms\n", njobs, ncycles, (EigRun::now() - tb0) * 1e3);
+    if (btrace) {
+        double tc = 0;
+        int nc = 0;
+        for (int i = 0; i < njobs; ++i) { tc += runs[i]->t_capture; nc += runs[i]->n_capture; }
+        fprintf(stderr, "[ws_eig_solve_batch] %d jobs, %d cycles, %.1f ms; graph captures so far in these work spaces: %d, %.1f ms\n", njobs,
+                ncycles, (EigRun::now() - tb0) * 1e3, nc, tc * 1e3);
+    }
     for (int i = 0; i < njobs; ++i)
         if (state[i] == 1) {
             if (guarded(i, [&] { runs[i]->finish(jobs[i].info, jobs[i].resid); })) state[i] = 2;

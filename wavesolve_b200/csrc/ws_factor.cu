@@ -104,6 +104,8 @@ struct ws_solver {
     int probe_iters = 0;
     double h_eta0 = 0.0, h_eta = 0.0, h_maxabs = 0.0;   // probe backward error before / after refinement; max |M_ij|
     ws::DevBuf<double> rf_b, rf_r, rf_y, rf_dx, rf_x;
+    int64_t uid = 0;                        // unique per created solver (a work space that cached graphs for a solver must not
+                                            // mistake a new solver at a recycled address for it)
     unsigned long long* h_stats = nullptr;  // pinned landing buffer of the statistics (factor_begin -> factor_end)
     bool factor_pending = false;
     ~ws_solver() {
@@ -1854,6 +1856,10 @@ int ws_solver_create(const ws_pattern* p, const ws_symbolic* sym, ws_solver** ou
     configure_mempool(device);
     cudaStream_t st = (cudaStream_t)stream;
     auto* s = new ws_solver();
+    {
+        static std::atomic<int64_t> next_uid{1};
+        s->uid = next_uid.fetch_add(1);
+    }
     const bool trace = getenv("WS_TRACE") != nullptr;
     auto tnow = [&]() {
         if (trace) cudaStreamSynchronize(st);
@@ -2264,7 +2270,7 @@ int ws_solver_quality(const ws_solver* s, int64_t* h_info, double* h_dinfo) {
     WS_API_BEGIN
     WS_REQUIRE(s, "solver == NULL");
     if (h_info) {
-        h_info[0] = s->h_pert; h_info[1] = s->refine_steps; h_info[2] = s->probe_iters; h_info[3] = 0;
+        h_info[0] = s->h_pert; h_info[1] = s->refine_steps; h_info[2] = s->probe_iters; h_info[3] = s->uid;
     }
     if (h_dinfo) {
         h_dinfo[0] = s->h_eta0; h_dinfo[1] = s->h_eta; h_dinfo[2] = s->h_maxabs; h_dinfo[3] = PIV_REL * s->h_maxabs;

@@ -248,7 +248,7 @@ class _Lane:
     """One of the eigenproblems a GPU works on concurrently: its own CUDA stream, solver (front storage), material
     array and value arrays.  Everything that depends on the mesh only is shared through the _MeshContext."""
 
-    def __init__(self, ctx, stream):
+    def __init__(self, ctx, stream, workspace=None):
         from . import solver as sv
         self.ctx, self.stream = ctx, stream
         prob = ctx.prob
@@ -264,15 +264,18 @@ class _Lane:
             self.B = torch.empty(nnz, dtype=torch.float64, device=prob.dev)
         import ctypes as C
         from . import _lib
-        self.workspace = C.c_void_p()
-        _lib.check(_lib.lib().ws_eig_workspace_create(C.byref(self.workspace)))
+        self.own_workspace = workspace is None
+        if workspace is None:
+            workspace = C.c_void_p()
+            _lib.check(_lib.lib().ws_eig_workspace_create(C.byref(workspace)))
+        self.workspace = workspace
 
     def close(self):
         from . import _lib
         self.stream.synchronize()
-        if self.workspace is not None and self.workspace.value:
+        if self.own_workspace and self.workspace is not None and self.workspace.value:
             _lib.lib().ws_eig_workspace_destroy(self.workspace)
-            self.workspace = None
+        self.workspace = None
         self.solver.close()
 
 
@@ -280,7 +283,7 @@ class _MeshContext:
     """Everything that depends on the mesh only, resident on this rank's GPU: arrays, pattern, incidence lists,
     symbolic analysis (shared by the lanes), plus the lanes themselves."""
 
-    def __init__(self, mesh, kind, IOR_dict, k, device, leaf_elems, streams=None):
+    def __init__(self, mesh, kind, IOR_dict, k, device, leaf_elems, streams=None, workspaces=None):
         from . import fe_solver as fs, solver as sv
         self.kind = kind
         self.mesh = mesh
@@ -304,9 +307,9 @@ class _MeshContext:
                 # lanes (other streams) read them
                 self.prob.apply_T(torch.zeros(self.prob.N, dtype=torch.float64, device=self.prob.dev))
             cur = torch.cuda.current_stream(self.prob.dev)
-            for st in streams:
+            for li, st in enumerate(streams):
                 st.wait_stream(cur)
-                self.lanes.append(_Lane(self, st))
+                self.lanes.append(_Lane(self, st, workspaces[li] if workspaces else None))
 
     def close(self):
         for ln in self.lanes:
@@ -383,6 +386,13 @@ def solve_sweep(meshes: Sequence, problems: Sequence[SweepProblem], Nmax: int = 
             offsets[i] = off
             off += Nmax * (1 + sizes[problems[i].mesh_id])
         streams = [torch.cuda.Stream(device=dev) for _ in range(lanes)]
+        # one eigensolver work space per lane for the whole sweep: its pinned staging blocks survive the change of
+        # mesh (the basis and the step graphs are rebuilt when the sizes / handles change)
+        workspaces = []
+        for _ in range(lanes):
+            h_ = C.c_void_p()
+            _lib.check(L.ws_eig_workspace_create(C.byref(h_)))
+            workspaces.append(h_)
         # the problems of one mesh, in order; `lanes` of them are in flight at a time
         groups: List[List[int]] = []
         for i in mine:
@@ -407,102 +417,109 @@ def solve_sweep(meshes: Sequence, problems: Sequence[SweepProblem], Nmax: int = 
                 _tm[name] += _time.perf_counter() - t0
             return _time.perf_counter()
 
-        for grp in groups:
-            pr0 = problems[grp[0]]
-            _t = _time.perf_counter()
-            ctx = _MeshContext(meshes[pr0.mesh_id], kind, pr0.IOR_dict, 2 * np.pi / pr0.wl, dev, leaf_elems,
-                               streams=streams[:min(lanes, len(grp))])
-            prob = ctx.prob
-            N = prob.N
-            if _trace:
-                torch.cuda.synchronize(dev)
-            _t = _tick("context", _t)
-            try:
-                for r0 in range(0, len(grp), len(ctx.lanes)):
-                    batch = grp[r0:r0 + len(ctx.lanes)]
-                    _t = _time.perf_counter()
-                    act = []                                   # (problem index, lane, k, sigma, views)
-                    # ---- phase 1: new materials, re-assembly (K11) and factorisation of every lane, all enqueued
-                    for i, ln in zip(batch, ctx.lanes):
-                        pr = problems[i]
-                        k = 2 * np.pi / pr.wl
-                        o = offsets[i]
-                        wv = sendbuf[o:o + Nmax]
-                        Vv = sendbuf[o + Nmax:o + Nmax + Nmax * N].view(Nmax, N)
-                        nmax_ior = max(pr.IOR_dict.values())
-                        sigma = float(np.power(k * (nmax_ior if pr.target_neff is None else pr.target_neff), 2))
-                        sp = ln.stream.cuda_stream
-                        try:
-                            with torch.cuda.stream(ln.stream):
-                                ln.k2n2.copy_(torch.from_numpy(fs._k2n2_host(ctx.mesh, pr.IOR_dict, k)), non_blocking=True)
-                                if kind == "vector":
-                                    _lib.check(L.ws_assemble_vector_qd(prob.pattern.handle, _dev.ptr(prob.xy), _dev.ptr(prob.tris),
-                                                                       _dev.ptr(ln.k2n2), prob.Ntt, sigma, _dev.ptr(ln.M),
-                                                                       _dev.ptr(ln.B), _lib.ASM_FAST, dev.index, sp))
-                                    _lib.check(L.ws_solver_factor_begin(ln.solver.handle, _dev.ptr(ln.M), None, 0.0, dev.index, sp))
-                                else:
-                                    _lib.check(L.ws_assemble_scalar_p2(prob.pattern.handle, _dev.ptr(prob.xy), _dev.ptr(prob.dofs),
-                                                                       _dev.ptr(ln.k2n2), _dev.ptr(ln.M), _dev.ptr(ln.B),
-                                                                       _lib.ASM_FAST, dev.index, sp))
-                                    _lib.check(L.ws_solver_factor_begin(ln.solver.handle, _dev.ptr(ln.M), _dev.ptr(ln.B), sigma,
-                                                                        dev.index, sp))
-                            act.append((i, ln, k, sigma, wv, Vv))
-                        except _lib.WavesolveB200Error as e:
-                            local[i] = (wv, Vv, 0, fail(i, wv, Vv, e))
-                            infos[i] = {"error": str(e)}
-                    _t = _tick("assemble+factor_begin", _t)
-                    # ---- phase 2: read the pivot statistics / accuracy probe of every lane
-                    ready = []
-                    for (i, ln, k, sigma, wv, Vv) in act:
-                        try:
-                            _lib.check(L.ws_solver_factor_end(ln.solver.handle, dev.index, ln.stream.cuda_stream))
-                            ready.append((i, ln, k, sigma, wv, Vv))
-                        except _lib.WavesolveB200Error as e:
-                            local[i] = (wv, Vv, 0, fail(i, wv, Vv, e))
-                            infos[i] = {"error": str(e)}
-                    _t = _tick("factor_end", _t)
-                    if not ready:
-                        continue
-                    # ---- phase 3: the eigen-iterations of the lanes, interleaved by one host thread
-                    jobs = (_lib.EigJob * len(ready))()
-                    for J, (i, ln, k, sigma, wv, Vv) in zip(jobs, ready):
-                        J.pattern, J.solver, J.B_vals = prob.pattern.handle.value, ln.solver.handle.value, _dev.ptr(ln.B)
-                        J.sigma, J.kind, J.nev, J.ncv, J.maxit, J.tol, J.seed = sigma, (1 if kind == "vector" else 0), Nmax, 0, 0, 0.0, 0
-                        J.edges = _dev.ptr(prob.edges) if kind == "vector" else None
-                        J.xy = _dev.ptr(prob.xy) if kind == "vector" else None
-                        J.Ntt = prob.Ntt if kind == "vector" else 0
-                        J.w, J.V, J.stream, J.resid = _dev.ptr(wv), _dev.ptr(Vv), ln.stream.cuda_stream, None
-                        J.workspace = ln.workspace.value
-                    _lib.check(L.ws_eig_solve_batch(C.addressof(jobs), len(ready), dev.index))
-                    _t = _tick("eig_batch", _t)
-                    for J, (i, ln, k, sigma, wv, Vv) in zip(jobs, ready):
-                        pr = problems[i]
-                        rc = int(J.rc)
-                        info = dict(nconv=int(J.info[0]), n_op=int(J.info[1]), restarts=int(J.info[2]), ncomplex=int(J.info[3]),
-                                    N=N, sigma=sigma, factor=ln.solver.stats())
-                        cnt = 0
-                        if rc not in (0, _lib.ERR_NOCONV):
-                            wv.fill_(float("nan"))
-                            Vv.fill_(float("nan"))
-                        if rc:
-                            info["error"] = J.error.decode(errors="replace")
-                        if rc in (0, _lib.ERR_NOCONV):
-                            cnt = fs._count_modes(wv.cpu().numpy(), k, pr.IOR_dict,
-                                                  always=(kind == "vector" and pr.target_neff is not None))
-                        local[i] = (wv, Vv, cnt, rc)
-                        infos[i] = info
-                    _t = _tick("post", _t)
-            finally:
+        try:
+            for grp in groups:
+                pr0 = problems[grp[0]]
                 _t = _time.perf_counter()
-                for st_ in streams:
-                    st_.synchronize()
-                ctx.close()
-                _t = _tick("close", _t)
-        if _trace:
-            import sys as _sys
-            print("[solve_sweep] rank %d lanes %d problems %d: %s" % (rank, lanes, len(mine), {k_: round(v, 3) for k_, v in _tm.items()}),
-                  file=_sys.stderr, flush=True)
+                ctx = _MeshContext(meshes[pr0.mesh_id], kind, pr0.IOR_dict, 2 * np.pi / pr0.wl, dev, leaf_elems,
+                                   streams=streams[:min(lanes, len(grp))], workspaces=workspaces)
+                prob = ctx.prob
+                N = prob.N
+                if _trace:
+                    torch.cuda.synchronize(dev)
+                _t = _tick("context", _t)
+                try:
+                    for r0 in range(0, len(grp), len(ctx.lanes)):
+                        batch = grp[r0:r0 + len(ctx.lanes)]
+                        _t = _time.perf_counter()
+                        act = []                                   # (problem index, lane, k, sigma, views)
+                        # ---- phase 1: new materials, re-assembly (K11) and factorisation of every lane, all enqueued
+                        for i, ln in zip(batch, ctx.lanes):
+                            pr = problems[i]
+                            k = 2 * np.pi / pr.wl
+                            o = offsets[i]
+                            wv = sendbuf[o:o + Nmax]
+                            Vv = sendbuf[o + Nmax:o + Nmax + Nmax * N].view(Nmax, N)
+                            nmax_ior = max(pr.IOR_dict.values())
+                            sigma = float(np.power(k * (nmax_ior if pr.target_neff is None else pr.target_neff), 2))
+                            sp = ln.stream.cuda_stream
+                            try:
+                                with torch.cuda.stream(ln.stream):
+                                    ln.k2n2.copy_(torch.from_numpy(fs._k2n2_host(ctx.mesh, pr.IOR_dict, k)), non_blocking=True)
+                                    if kind == "vector":
+                                        _lib.check(L.ws_assemble_vector_qd(prob.pattern.handle, _dev.ptr(prob.xy), _dev.ptr(prob.tris),
+                                                                           _dev.ptr(ln.k2n2), prob.Ntt, sigma, _dev.ptr(ln.M),
+                                                                           _dev.ptr(ln.B), _lib.ASM_FAST, dev.index, sp))
+                                        _lib.check(L.ws_solver_factor_begin(ln.solver.handle, _dev.ptr(ln.M), None, 0.0, dev.index, sp))
+                                    else:
+                                        _lib.check(L.ws_assemble_scalar_p2(prob.pattern.handle, _dev.ptr(prob.xy), _dev.ptr(prob.dofs),
+                                                                           _dev.ptr(ln.k2n2), _dev.ptr(ln.M), _dev.ptr(ln.B),
+                                                                           _lib.ASM_FAST, dev.index, sp))
+                                        _lib.check(L.ws_solver_factor_begin(ln.solver.handle, _dev.ptr(ln.M), _dev.ptr(ln.B), sigma,
+                                                                            dev.index, sp))
+                                act.append((i, ln, k, sigma, wv, Vv))
+                            except _lib.WavesolveB200Error as e:
+                                local[i] = (wv, Vv, 0, fail(i, wv, Vv, e))
+                                infos[i] = {"error": str(e)}
+                        _t = _tick("assemble+factor_begin", _t)
+                        # ---- phase 2: read the pivot statistics / accuracy probe of every lane
+                        ready = []
+                        for (i, ln, k, sigma, wv, Vv) in act:
+                            try:
+                                _lib.check(L.ws_solver_factor_end(ln.solver.handle, dev.index, ln.stream.cuda_stream))
+                                ready.append((i, ln, k, sigma, wv, Vv))
+                            except _lib.WavesolveB200Error as e:
+                                local[i] = (wv, Vv, 0, fail(i, wv, Vv, e))
+                                infos[i] = {"error": str(e)}
+                        _t = _tick("factor_end", _t)
+                        if not ready:
+                            continue
+                        # ---- phase 3: the eigen-iterations of the lanes, interleaved by one host thread
+                        jobs = (_lib.EigJob * len(ready))()
+                        for J, (i, ln, k, sigma, wv, Vv) in zip(jobs, ready):
+                            J.pattern, J.solver, J.B_vals = prob.pattern.handle.value, ln.solver.handle.value, _dev.ptr(ln.B)
+                            J.sigma, J.kind, J.nev, J.ncv, J.maxit, J.tol, J.seed = sigma, (1 if kind == "vector" else 0), Nmax, 0, 0, 0.0, 0
+                            J.edges = _dev.ptr(prob.edges) if kind == "vector" else None
+                            J.xy = _dev.ptr(prob.xy) if kind == "vector" else None
+                            J.Ntt = prob.Ntt if kind == "vector" else 0
+                            J.w, J.V, J.stream, J.resid = _dev.ptr(wv), _dev.ptr(Vv), ln.stream.cuda_stream, None
+                            J.workspace = ln.workspace.value
+                        _lib.check(L.ws_eig_solve_batch(C.addressof(jobs), len(ready), dev.index))
+                        _t = _tick("eig_batch", _t)
+                        for J, (i, ln, k, sigma, wv, Vv) in zip(jobs, ready):
+                            pr = problems[i]
+                            rc = int(J.rc)
+                            info = dict(nconv=int(J.info[0]), n_op=int(J.info[1]), restarts=int(J.info[2]), ncomplex=int(J.info[3]),
+                                        N=N, sigma=sigma, factor=ln.solver.stats())
+                            cnt = 0
+                            if rc not in (0, _lib.ERR_NOCONV):
+                                wv.fill_(float("nan"))
+                                Vv.fill_(float("nan"))
+                            if rc:
+                                info["error"] = J.error.decode(errors="replace")
+                            if rc in (0, _lib.ERR_NOCONV):
+                                cnt = fs._count_modes(wv.cpu().numpy(), k, pr.IOR_dict,
+                                                      always=(kind == "vector" and pr.target_neff is not None))
+                            local[i] = (wv, Vv, cnt, rc)
+                            infos[i] = info
+                        _t = _tick("post", _t)
+                finally:
+                    _t = _time.perf_counter()
+                    for st_ in streams:
+                        st_.synchronize()
+                    ctx.close()
+                    _t = _tick("close", _t)
+            if _trace:
+                import sys as _sys
+                print("[solve_sweep] rank %d lanes %d problems %d: %s" % (rank, lanes, len(mine), {k_: round(v, 3) for k_, v in _tm.items()}),
+                      file=_sys.stderr, flush=True)
+        finally:
+            for st_ in streams:
+                st_.synchronize()
+            for h_ in workspaces:
+                L.ws_eig_workspace_destroy(h_)
         for st_ in streams:
+            st_.synchronize()
             main_stream.wait_stream(st_)
         local = {i: local[i] for i in mine}      # send-buffer order
         torch.cuda.synchronize(dev)
