@@ -538,13 +538,39 @@ constexpr int MAXV = 64;        // basis rows the FUSED CGS kernel and the block
 constexpr int MAX_NCV = 256;    // largest Krylov basis: Nmax = 100 (lantern-demo.ipynb cells 2, 4) needs ncv = 204
 
 // partial[c*nvec + i] = sum over chunk c of Z_i[n] * u[n];  8 warps, warp w takes vectors w, w+8, ...
+// Optional fused application of T (vector problem: w = T x, x the output of the solve sweeps): with tf.tin != nullptr the
+// chunk of u is formed on the fly as u[n] = tin[n] - (tin[Ntt + hi] - tin[Ntt + lo]) / len[n] for the edge rows (what
+// k_vector_T mode 0 computes) and also written to u -- one launch and one pass over the vector less per Arnoldi step.
+struct FusedT {
+    const double* tin = nullptr;
+    const int2* edges = nullptr;
+    const double* elen = nullptr;
+    int64_t Ntt = 0;
+    double* wout = nullptr;
+};
 __global__ void __launch_bounds__(256) k_dots_partial(const double* __restrict__ Z, int64_t ldz, int nvec,
                                                       const double* __restrict__ u, int64_t N,
-                                                      double* __restrict__ partial, int chunk) {
+                                                      double* __restrict__ partial, int chunk, FusedT tf) {
     __shared__ double us[DOT_CHUNK];
     const int64_t n0 = (int64_t)blockIdx.x * chunk;
     const int len = (int)min((int64_t)chunk, N - n0);
-    for (int i = threadIdx.x; i < chunk; i += 256) us[i] = (i < len) ? u[n0 + i] : 0.0;
+    if (tf.tin) {
+        for (int i = threadIdx.x; i < chunk; i += 256) {
+            double v = 0.0;
+            if (i < len) {
+                const int64_t n = n0 + i;
+                v = tf.tin[n];
+                if (n < tf.Ntt) {
+                    const int2 e = tf.edges[n];
+                    v -= (tf.tin[tf.Ntt + e.y] - tf.tin[tf.Ntt + e.x]) / tf.elen[n];
+                }
+                if (blockIdx.y == 0) tf.wout[n] = v;
+            }
+            us[i] = v;
+        }
+    } else {
+        for (int i = threadIdx.x; i < chunk; i += 256) us[i] = (i < len) ? u[n0 + i] : 0.0;
+    }
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // gridDim.y groups of basis vectors: a wide basis on a small problem (Nmax = 80 at N = 100k: 164 vectors, 50 chunks)
@@ -603,9 +629,12 @@ __global__ void __launch_bounds__(256) k_update(double* __restrict__ w, const do
 // with the updated entries, for the partial dots.  partial has the layout of k_dots_partial.
 constexpr int UD_TILE = 256;
 __global__ void __launch_bounds__(256) k_update_dots(double* __restrict__ w, const double* __restrict__ V, int64_t ldv, int nvec,
-                                                     const double* __restrict__ h, int64_t N, double* __restrict__ partial, int chunk) {
+                                                     const double* __restrict__ h, int64_t N, double* __restrict__ partial, int chunk,
+                                                     double* __restrict__ pnorm) {
     extern __shared__ double uds[];            // [nvec][UD_TILE] basis tile, then [UD_TILE] updated w
     __shared__ double hs[MAXV];
+    __shared__ double sqw[8];
+    double sq = 0.0;                           // sum of the squares of this thread's updated entries (pnorm != nullptr)
     double* Vs = uds;
     double* ws_ = uds + (size_t)nvec * UD_TILE;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -634,6 +663,7 @@ __global__ void __launch_bounds__(256) k_update_dots(double* __restrict__ w, con
             for (int v = 0; v < nvec; ++v) acc -= hs[v] * Vs[v * UD_TILE + tid];
             w[n0 + tid] = acc;
         }
+        sq += acc * acc;
         ws_[tid] = acc;
         __syncthreads();
         int slot = 0;
@@ -651,6 +681,71 @@ __global__ void __launch_bounds__(256) k_update_dots(double* __restrict__ w, con
         for (int o = 16; o; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
         if (lane == 0) partial[(size_t)blockIdx.x * nvec + v] = a;
     }
+    if (pnorm) {
+        // ||w'||^2 of this chunk (fixed shuffle / warp order: deterministic), for beta^2 = ||w'||^2 - ||h2||^2
+#pragma unroll
+        for (int o = 16; o; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+        if (lane == 0) sqw[warp] = sq;
+        __syncthreads();
+        if (tid == 0) {
+            double t = 0.0;
+            for (int k = 0; k < 8; ++k) t += sqw[k];
+            pnorm[blockIdx.x] = t;
+        }
+    }
+}
+
+// second reduction of the fused CGS2 step: h2[v] = sum_c partial[c][v] (also accumulated into the H column), and
+// nrm[0] = beta^2 = ||w'||^2 - ||h2||^2 -- the squared norm of w'' = w' - V h2 by Pythagoras (V orthonormal to rounding,
+// ||h2|| ~ 1e-16 ||w'||: no cancellation), so that the last update and the normalisation are ONE pass (k_update_normalize)
+__global__ void __launch_bounds__(256) k_dots_reduce_beta(const double* __restrict__ partial, const double* __restrict__ pnorm,
+                                                          int nchunks, int nvec, double* __restrict__ h, double* __restrict__ hacc,
+                                                          double* __restrict__ nrm) {
+    __shared__ double h2sq[MAXV];
+    __shared__ double pw[8];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int v = warp; v < nvec; v += 8) {
+        double sacc = 0.0;
+        for (int c = lane; c < nchunks; c += 32) sacc += partial[(size_t)c * nvec + v];
+#pragma unroll
+        for (int o = 16; o; o >>= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, o);
+        if (lane == 0) {
+            h[v] = sacc;
+            if (hacc) hacc[v] += sacc;
+            h2sq[v] = sacc * sacc;
+        }
+    }
+    double pn = 0.0;
+    for (int c = threadIdx.x; c < nchunks; c += 256) pn += pnorm[c];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) pn += __shfl_xor_sync(0xffffffffu, pn, o);
+    if (lane == 0) pw[warp] = pn;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0, hh = 0.0;
+        for (int k = 0; k < 8; ++k) t += pw[k];
+        for (int v = 0; v < nvec; ++v) hh += h2sq[v];
+        nrm[0] = t - hh;
+    }
+}
+
+// v_next = (w - V h) / beta, beta = sqrt(nrm[0]) also written to the H slot: last CGS2 update + normalisation in one pass
+__global__ void __launch_bounds__(256) k_update_normalize(const double* __restrict__ w, const double* __restrict__ V, int64_t ldv,
+                                                          int nvec, const double* __restrict__ h, int64_t N,
+                                                          const double* __restrict__ nrm, double* __restrict__ hslot,
+                                                          double* __restrict__ vnext) {
+    extern __shared__ double hs[];             // [nvec]
+    for (int i = threadIdx.x; i < nvec; i += blockDim.x) hs[i] = h[i];
+    __syncthreads();
+    const int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const double b2 = nrm[0];
+    const double beta = b2 > 0.0 ? sqrt(b2) : 0.0;
+    if (n == 0 && hslot) *hslot = beta;
+    if (n >= N) return;
+    const double inv = beta > 0.0 ? 1.0 / beta : 0.0;
+    double acc = w[n];
+    for (int i = 0; i < nvec; ++i) acc -= hs[i] * V[(size_t)i * ldv + n];
+    vnext[n] = acc * inv;
 }
 
 // two vectors against the same basis in one pass over it (block Arnoldi):
@@ -873,7 +968,7 @@ struct EigWork {
     int64_t N;
     int ncv;
     cudaStream_t st;
-    DevBuf<double> V, Z, w, t1, t2, t3, partial, h, Hd, nrm, Q;
+    DevBuf<double> V, Z, w, t1, t2, t3, partial, pnorm, h, Hd, nrm, Q;
     int nchunks;
     int chunk = DOT_CHUNK;      // rows per CTA of the dot kernels: 2048, or 512 for small problems (more CTAs than SMs)
 };
@@ -881,10 +976,11 @@ struct EigWork {
 //  N = 100k runs 493 ms with 2048-row chunks, 531 ms with 512)
 static int dot_chunk_for(int64_t N, int m) { return (m <= 64 && N < 148 * 4 * (int64_t)DOT_CHUNK / 2) ? 512 : DOT_CHUNK; }
 
-static void dots(EigWork& W, cudaStream_t q, const double* Zb, int nvec, const double* u, double* h, double* hacc) {
+static void dots(EigWork& W, cudaStream_t q, const double* Zb, int nvec, const double* u, double* h, double* hacc,
+                 FusedT tf = FusedT()) {
     int groups = 1;
     if (W.nchunks < 2 * kNumSMs && nvec > 8) groups = std::min((nvec + 7) / 8, (2 * kNumSMs + W.nchunks - 1) / W.nchunks);
-    k_dots_partial<<<dim3(W.nchunks, groups), 256, 0, q>>>(Zb, W.N, nvec, u, W.N, W.partial.get(), W.chunk);
+    k_dots_partial<<<dim3(W.nchunks, groups), 256, 0, q>>>(Zb, W.N, nvec, u, W.N, W.partial.get(), W.chunk, tf);
     k_dots_reduce<<<nvec, 32, 0, q>>>(W.partial.get(), W.nchunks, nvec, h, hacc);
     count_launch(2);
 }
@@ -1339,15 +1435,39 @@ struct EigRun {
     // primal one), normalise into slot j+1
     void arnoldi_step(cudaStream_t q, int j) {
         static const bool fuse_cgs = !(getenv("WS_NO_CGS_FUSE") && atoi(getenv("WS_NO_CGS_FUSE")));
-        apply_op(q, j);
+        static const bool fuse_glue = !(getenv("WS_NO_GLUE_FUSE") && atoi(getenv("WS_NO_GLUE_FUSE")));
         double* Hcol = W.Hd.get() + (size_t)j * (m + 1);
         const int nv = j + 1;
+        if (kind == 1 && fuse_cgs && fuse_glue && nv + 1 <= MAXV) {
+            // Fully fused vector step (7 launches around the solve instead of 12):
+            //   B v_j -> T^T -> solve  |  [T fused into the first products]  h1 = V^T w
+            //   |  w' = w - V h1, h2 = V^T w', ||w'||^2 in one pass over the basis
+            //   |  beta^2 = ||w'||^2 - ||h2||^2  |  v_{j+1} = (w' - V h2) / beta in one pass
+            spmv_launch(p, B_vals, V + (size_t)j * N, W.t1.get(), q);
+            vecT(q, 1, W.t1.get(), W.t2.get());
+            solve(q, W.t2.get(), W.t3.get());
+            FusedT tf;
+            tf.tin = W.t3.get();
+            tf.edges = (const int2*)edges;
+            tf.elen = p->vt_len.get();
+            tf.Ntt = Ntt;
+            tf.wout = W.w.get();
+            dots(W, q, V, nv, W.w.get(), W.h.get(), Hcol, tf);
+            k_update_dots<<<W.nchunks, 256, (size_t)(nv + 1) * UD_TILE * sizeof(double), q>>>(W.w.get(), V, N, nv, W.h.get(), N,
+                                                                                         W.partial.get(), W.chunk, W.pnorm.get());
+            k_dots_reduce_beta<<<1, 256, 0, q>>>(W.partial.get(), W.pnorm.get(), W.nchunks, nv, W.h.get(), Hcol, W.nrm.get());
+            k_update_normalize<<<nb, T, (size_t)nv * sizeof(double), q>>>(W.w.get(), V, N, nv, W.h.get(), N, W.nrm.get(),
+                                                                        Hcol + (j + 1), V + (size_t)(j + 1) * N);
+            count_launch(3);
+            return;
+        }
+        apply_op(q, j);
         if (kind == 1 && fuse_cgs && nv + 1 <= MAXV) {
             // Euclidean inner product (dual basis = basis): the update of pass 1 and the inner products of pass 2
             // share one pass over the basis -- three basis reads per step instead of four
             dots(W, q, V, nv, W.w.get(), W.h.get(), Hcol);
             k_update_dots<<<W.nchunks, 256, (size_t)(nv + 1) * UD_TILE * sizeof(double), q>>>(W.w.get(), V, N, nv, W.h.get(), N,
-                                                                                         W.partial.get(), W.chunk);
+                                                                                         W.partial.get(), W.chunk, nullptr);
             k_dots_reduce<<<nv, 32, 0, q>>>(W.partial.get(), W.nchunks, nv, W.h.get(), Hcol);
             k_update<<<nb, T, (size_t)nv * sizeof(double), q>>>(W.w.get(), V, N, nv, W.h.get(), N);
             count_launch(3);
@@ -1430,6 +1550,7 @@ struct EigRun {
             else W.Z.release();
             W.w.alloc(N, st); W.t1.alloc(N, st); W.t2.alloc(N, st); W.t3.alloc(N, st);
             W.partial.alloc((size_t)W.nchunks * (m + 1), st);
+            W.pnorm.alloc((size_t)W.nchunks, st);
             W.h.alloc(m + 1, st);
             W.Hd.alloc((size_t)(m + 1) * m, st);
             W.nrm.alloc(m + 1, st);
@@ -1463,6 +1584,14 @@ struct EigRun {
         normalize_into(st, 0, nullptr);
         // every kernel of a step has now run once outside stream capture, except the update:
         k_update<<<nb, T, 0, st>>>(W.w.get(), V, N, 0, W.h.get(), N);   // nvec = 0: no-op, loads the kernel
+        if (kind == 1) {
+            // the same for the kernels of the fused step (harmless with nvec = 0: w unchanged, scratch outputs)
+            k_update_dots<<<W.nchunks, 256, (size_t)UD_TILE * sizeof(double), st>>>(W.w.get(), V, N, 0, W.h.get(), N, W.partial.get(),
+                                                                                 W.chunk, W.pnorm.get());
+            k_dots_reduce_beta<<<1, 256, 0, st>>>(W.partial.get(), W.pnorm.get(), W.nchunks, 0, W.h.get(), nullptr, W.nrm.get());
+            k_update_normalize<<<nb, T, 0, st>>>(W.w.get(), V, N, 0, W.h.get(), N, W.nrm.get(), nullptr, W.t1.get());
+            count_launch(3);
+        }
         WS_CUDA(cudaMemsetAsync(W.Hd.get(), 0, W.Hd.bytes(), st));
         theta_r.assign(m, 0.0);
         theta_i.assign(m, 0.0);
