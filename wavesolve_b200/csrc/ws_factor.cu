@@ -1676,9 +1676,17 @@ static void launch_pdl(void (*kern)(KArgs...), unsigned grid, unsigned block, si
 
 struct SweepTuning {
     int kb, kb_leaf, cb, cb_leaf, rj, rj_leaf;
+    int kb_mid, cb_mid, rj_mid, mid_fronts;   // levels with at most mid_fronts fronts (about one wave of CTAs)
 };
+static SweepTuning sweep_tuning_read();
 static const SweepTuning& sweep_tuning() {
-    static const SweepTuning t = [] {
+    static SweepTuning t = sweep_tuning_read();
+    static const bool reload = getenv("WS_TUNE_RELOAD") && atoi(getenv("WS_TUNE_RELOAD"));   // experiments: re-read per solve
+    if (reload) t = sweep_tuning_read();
+    return t;
+}
+static SweepTuning sweep_tuning_read() {
+    {
         auto env = [](const char* n, int d) { const char* e = getenv(n); return e ? atoi(e) : d; };
         SweepTuning v;
         v.kb = env("WS_FWD_KB", 4);
@@ -1687,9 +1695,12 @@ static const SweepTuning& sweep_tuning() {
         v.cb_leaf = env("WS_BWD_CB_LEAF", 2);
         v.rj = env("WS_BWD_RJ", 4);
         v.rj_leaf = env("WS_BWD_RJ_LEAF", 2);
+        v.kb_mid = env("WS_FWD_KB_MID", v.kb);
+        v.cb_mid = env("WS_BWD_CB_MID", v.cb);
+        v.rj_mid = env("WS_BWD_RJ_MID", v.rj);
+        v.mid_fronts = env("WS_MID_FRONTS", 0);
         return v;
-    }();
-    return t;
+    }
 }
 
 // NR = 1: every (KB | CB, RJ) variant (experiments); NR = 2: the tuned defaults only (compile time)
@@ -1761,6 +1772,9 @@ static void sweep_launches(ws_solver* s, const double* bi, double* xi, cudaStrea
     if (flagsync) WS_CUDA(cudaMemsetAsync(s->sflags.get() + 1, 0, s->sflags.bytes() - sizeof(int32_t), st));
     const SweepTuning& tune = sweep_tuning();
     int nl = 0;
+    // experiments (tools/sweep_levels.py): stop after the first WS_SWEEP_STOP launches -- the time of a truncated solve,
+    // as a function of the cut, is the cost of each level INSIDE the overlapped pipeline (ncu serialises the launches)
+    const int stop_after = getenv("WS_SWEEP_STOP") ? atoi(getenv("WS_SWEEP_STOP")) : 1 << 30;
     // Optional (WS_SPLIT=1): every level launched in two halves (left / right subtree of the root).  With the
     // per-front flags the left half of level l-1 depends on the left half of level l only, so it can run while the
     // right half of level l drains.  Measured: 0.977 ms against 0.970 ms per solve -- the tails are not what is
@@ -1768,6 +1782,7 @@ static void sweep_launches(ws_solver* s, const double* bi, double* xi, cudaStrea
     static const bool halves_env = getenv("WS_SPLIT") && atoi(getenv("WS_SPLIT"));
     const bool halves = flagsync && halves_env;
     for (int l = Y.depth; l >= 0; --l) {
+        if (nl >= stop_after) break;
         const LevelPlan& LP = s->levels[l];
         const int hc = l < Y.depth ? 1 : 0;
         const int nparts = (halves && LP.nfronts >= 2) ? 2 : 1;
@@ -1776,7 +1791,8 @@ static void sweep_launches(ws_solver* s, const double* bi, double* xi, cudaStrea
                 const int64_t h = nparts == 2 ? LP.nfronts / 2 : LP.nfronts;
                 const int64_t f = LP.first_front + (part ? h : 0);
                 const int64_t n = nparts == 2 ? (part ? LP.nfronts - h : h) : LP.nfronts;
-                launch_fwd_front<NR>(LP.nt, l == Y.depth ? tune.kb_leaf : tune.kb, (unsigned)n, std::max(LP.maxp, 2), st, f, hc, cx, bi);
+                const bool mid = LP.nfronts <= tune.mid_fronts;
+                launch_fwd_front<NR>(LP.nt, l == Y.depth ? tune.kb_leaf : (mid ? tune.kb_mid : tune.kb), (unsigned)n, std::max(LP.maxp, 2), st, f, hc, cx, bi);
                 ++nl;
             } else if (LP.fwd.cnt) {
                 const int64_t o = LP.fwd.off + (nparts == 2 && part ? LP.fwd_mid : 0);
@@ -1794,6 +1810,7 @@ static void sweep_launches(ws_solver* s, const double* bi, double* xi, cudaStrea
         }
     }
     for (int l = 0; l <= Y.depth; ++l) {
+        if (nl >= stop_after) break;
         const LevelPlan& LP = s->levels[l];
         const int nparts = (halves && LP.nfronts >= 2) ? 2 : 1;
         for (int part = 0; part < nparts; ++part) {
@@ -1801,8 +1818,9 @@ static void sweep_launches(ws_solver* s, const double* bi, double* xi, cudaStrea
                 const int64_t h = nparts == 2 ? LP.nfronts / 2 : LP.nfronts;
                 const int64_t f = LP.first_front + (part ? h : 0);
                 const int64_t n = nparts == 2 ? (part ? LP.nfronts - h : h) : LP.nfronts;
-                launch_bwd_front<NR>(LP.nt, l == Y.depth ? tune.cb_leaf : tune.cb, l == Y.depth ? tune.rj_leaf : tune.rj,
-                                     (unsigned)n, std::max(LP.maxm, 2), st, f, cx, xi);
+                const bool mid = LP.nfronts <= tune.mid_fronts;
+                launch_bwd_front<NR>(LP.nt, l == Y.depth ? tune.cb_leaf : (mid ? tune.cb_mid : tune.cb),
+                                     l == Y.depth ? tune.rj_leaf : (mid ? tune.rj_mid : tune.rj), (unsigned)n, std::max(LP.maxm, 2), st, f, cx, xi);
                 ++nl;
             } else if (LP.bwd.cnt) {
                 const int64_t o = LP.bwd.off + (nparts == 2 && part ? LP.bwd_mid : 0);
