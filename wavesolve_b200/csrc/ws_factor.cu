@@ -45,7 +45,8 @@ struct LevelPlan {
     std::vector<Range> upd, pan, trail;   // per block column (upd: left-looking, trail: right-looking)
     Range syrk, ext_left, ext_right, fwd, bwd;
     int64_t first_front = 0, nfronts = 0;
-    bool small = false;                   // every front fits the one-CTA-per-front solve kernels
+    bool small = false;                   // the level goes through the one-CTA-per-front solve kernels
+    bool narrow_tiles = false;            // tile kernels in their 256-thread variants (a level of few fronts that would fit one CTA each)
     int nt = 32;                          // threads of those kernels: largest front rounded up to a warp
     int maxp = 0, maxm = 0;
     bool right_looking = false;
@@ -1334,7 +1335,16 @@ static void classify_levels(ws_solver* s) {
         LP.upd.assign(nkb, Range());
         LP.pan.assign(nkb, Range());
         LP.trail.assign(nkb, Range());
-        LP.small = maxm <= FRONT_MAX_M;
+        // One CTA per front means one THREAD per front row walking all p columns of its row: p / 8 dependent round trips.
+        // Near the root of a small problem (a ~50k-triangle mesh of a sweep: root front 600 x 300) that chain, not bytes,
+        // is the level's cost, and there are too few fronts to hide it; such levels (at most WS_TILE_TOP = 32 fronts, at least
+        // 64 pivots) take the tile kernels, which split a row's k range over the lanes of a warp / 8 warps: one solve of
+        // N = 100k goes from 0.297 to 0.138 ms (profiles/r02c_small_problem_top_levels.txt).  Levels whose fronts exceed one
+        // CTA are tiled as before.
+        static const int tile_top = getenv("WS_TILE_TOP") ? atoi(getenv("WS_TILE_TOP")) : 32;
+        const bool retile = maxm <= FRONT_MAX_M && (f1 - f0) <= tile_top && maxp >= 64;
+        LP.small = maxm <= FRONT_MAX_M && !retile;
+        LP.narrow_tiles = retile;
         LP.nt = std::max(32, (maxm + 31) & ~31);
         LP.maxp = maxp;
         LP.maxm = maxm;
@@ -1799,7 +1809,7 @@ static void sweep_launches(ws_solver* s, const double* bi, double* xi, cudaStrea
                 const int64_t n = nparts == 2 ? (part ? LP.fwd.cnt - LP.fwd_mid : LP.fwd_mid) : LP.fwd.cnt;
                 if (n <= 0) continue;
                 const int base = (LP.maxp + 1) & ~1;
-                if (LP.fwd.cnt >= 500)
+                if (LP.fwd.cnt >= 500 || LP.narrow_tiles)
                     launch_pdl(k_fwd_tile<8, NR>, (unsigned)n, 32 * 8, (size_t)NR * (base + 8 * 33) * sizeof(double), st,
                                s->fwd_tiles.get() + o, hc, cx, bi, base);
                 else
@@ -1827,7 +1837,7 @@ static void sweep_launches(ws_solver* s, const double* bi, double* xi, cudaStrea
                 const int64_t n = nparts == 2 ? (part ? LP.bwd.cnt - LP.bwd_mid : LP.bwd_mid) : LP.bwd.cnt;
                 if (n <= 0) continue;
                 const int base = (LP.maxm + 1) & ~1;
-                if (LP.bwd.cnt >= 430)
+                if (LP.bwd.cnt >= 430 || LP.narrow_tiles)
                     launch_pdl(k_bwd_tile<1, NR>, (unsigned)n, 32 * GEMVT_COLS, (size_t)NR * (base + GEMVT_COLS) * sizeof(double),
                                st, s->bwd_tiles.get() + o, cx, xi, base);
                 else
