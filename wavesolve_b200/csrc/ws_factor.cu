@@ -1342,7 +1342,8 @@ static void classify_levels(ws_solver* s) {
         // N = 100k goes from 0.297 to 0.138 ms (profiles/r02c_small_problem_top_levels.txt).  Levels whose fronts exceed one
         // CTA are tiled as before.
         static const int tile_top = getenv("WS_TILE_TOP") ? atoi(getenv("WS_TILE_TOP")) : 32;
-        const bool retile = maxm <= FRONT_MAX_M && (f1 - f0) <= tile_top && maxp >= 64;
+        static const int tile_minp = getenv("WS_TILE_MINP") ? atoi(getenv("WS_TILE_MINP")) : 64;
+        const bool retile = maxm <= FRONT_MAX_M && (f1 - f0) <= tile_top && maxp >= tile_minp;
         LP.small = maxm <= FRONT_MAX_M && !retile;
         LP.narrow_tiles = retile;
         LP.nt = std::max(32, (maxm + 31) & ~31);

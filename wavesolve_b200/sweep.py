@@ -324,6 +324,9 @@ def default_lanes(n_unknowns: int) -> int:
     """Problems a B200 works on concurrently: an eigensolve of ~100k unknowns is a chain of ~4000 small dependent
     kernels that fills a fraction of the GPU (4 streams finish 3.2 solves in the time of one); from ~1M unknowns
     on a single problem saturates it."""
+    import os
+    if os.environ.get("WS_SWEEP_LANES"):          # experiments (profiles/r02c_small_problem_top_levels.txt)
+        return max(1, int(os.environ["WS_SWEEP_LANES"]))
     if n_unknowns >= 1_000_000:
         return 1
     if n_unknowns >= 400_000:
