@@ -1,6 +1,16 @@
-import os, sys, time, cProfile, pstats, io
+#!/usr/bin/env python
+"""cProfile of the host side of a multi-lane sweep (4 lantern meshes of ~50k triangles x 16 wavelengths, 8 lanes):
+where the driving thread spends its time while the device works.  Diagnostic only."""
+import cProfile
+import io
+import os
+import pstats
+import sys
+import time
+
 import numpy as np
-sys.path.insert(0, "/root/repo")
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import wavesolve_b200 as ws
 from wavesolve_b200 import sweep
