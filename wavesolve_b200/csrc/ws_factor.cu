@@ -258,7 +258,8 @@ __global__ void __launch_bounds__(128) k_gemm_tiles(const GemmTask* __restrict__
 // 1 / d to within an ulp in six instructions (the reciprocal refinement div.rn.f64 itself starts with: MUFU.RCP64H seed, two
 // Newton steps).  k_panel scales by it instead of dividing: an inlined fp64 division is ~100 SASS instructions with its slow
 // path, and the kernel -- straight-line code that each of a few warps executes once -- runs at instruction-fetch speed
-// (13 824 -> 4 096 SASS instructions; profiles/r02c_factor_levels.txt).
+// (13 824 -> 12 656 SASS instructions, and warp 0's chain of 32 dependent divisions becomes one of 32 short reciprocals;
+// profiles/r02c_factor_levels.txt).  The pivot reciprocals of k_front_fused* use it too.
 __device__ __forceinline__ double fast_rcp(double d) {
     double y;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
@@ -621,7 +622,7 @@ __device__ __forceinline__ void front_fused_body(int64_t first, int has_children
         if (tid == 0 && p > 0) {
             const double pv = guarded(row[0]);
             dd[0] = pv;
-            rd[0] = 1.0 / pv;
+            rd[0] = fast_rcp(pv);
         }
 #pragma unroll
         for (int k = 0; k < PMAX; ++k) {
@@ -650,7 +651,7 @@ __device__ __forceinline__ void front_fused_body(int64_t first, int has_children
                 if (k + 1 < PMAX && tid == k + 1 && tid < p) {
                     const double pv = guarded(row[k + 1 < PMAX ? k + 1 : 0]);
                     dd[k + 1] = pv;
-                    rd[k + 1] = 1.0 / pv;
+                    rd[k + 1] = fast_rcp(pv);
                 }
             }
         }
@@ -664,7 +665,7 @@ __device__ __forceinline__ void front_fused_body(int64_t first, int has_children
         if (tid == 0 && p > 0) {
             const double pv = guarded(P[0]);
             dd[0] = pv;
-            rd[0] = 1.0 / pv;
+            rd[0] = fast_rcp(pv);
         }
         for (int k = 0; k < p; ++k) {
             double* buf = vb + (k & 1) * pe;
@@ -690,7 +691,7 @@ __device__ __forceinline__ void front_fused_body(int64_t first, int has_children
                 if (tid == k + 1 && tid < p) {
                     const double pv = guarded(P[tid + tid * ld]);
                     dd[tid] = pv;
-                    rd[tid] = 1.0 / pv;
+                    rd[tid] = fast_rcp(pv);
                 }
             }
         }
