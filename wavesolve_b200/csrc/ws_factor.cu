@@ -287,16 +287,23 @@ __global__ void __launch_bounds__(PANEL_ROWS) k_panel(const PanelTask* __restric
     }
     __syncthreads();
     if (tid < 32) {
-        // warp 0: lane r holds row r of the (symmetric) block in registers; column c is eliminated
-        // with shuffles: A[r][c2] -= (A[r][c] / A[c][c]) * A[c][c2]  for r, c2 > c.
+        // warp 0: lane r holds row r of the lower triangle in registers (statically indexed).  Step c: every lane publishes its
+        // entry of column c in shared memory (double-buffered: one __syncwarp per step), reads the pivot and -- as broadcast
+        // loads -- the unscaled column, and updates its row: a_r,c2 -= (a_rc / d_c) a_c2,c for c < c2 <= r.  (The first version
+        // fetched a_c,c2 from lane c with one 64-bit __shfl_sync per entry: eight SASS instructions each inside this
+        // divergent region, 8 600 of the kernel's 12 700 instructions -- and the kernel runs at instruction-fetch speed.)
         const int lane = tid;
         const double tau = pivot_tau(stats);
+        __shared__ __align__(16) double colbuf[2][NB];
         double row[NB];
 #pragma unroll
-        for (int c = 0; c < NB; ++c) row[c] = (lane >= c) ? Dg[lane][c] : Dg[c][lane];
+        for (int c = 0; c < NB; ++c) row[c] = (lane >= c) ? Dg[lane][c] : 0.0;
 #pragma unroll
         for (int c = 0; c < NB; ++c) {
-            double dc = __shfl_sync(0xffffffffu, row[c], c);
+            double* buf = colbuf[c & 1];
+            buf[lane] = row[c];
+            __syncwarp();
+            double dc = buf[c];
             if (c < t.nb && fabs(dc) < tau) {          // static pivot (uniform across the warp and across the CTAs of this block column)
                 dc = copysign(tau, dc);
                 if (lane == c && t.write_diag) atomicAdd(&stats[4], 1ull);
@@ -305,10 +312,7 @@ __global__ void __launch_bounds__(PANEL_ROWS) k_panel(const PanelTask* __restric
             const double rdc = fast_rcp(dc);
             const double lr = act ? row[c] * rdc : 0.0;
 #pragma unroll
-            for (int c2 = c + 1; c2 < NB; ++c2) {
-                const double pc = __shfl_sync(0xffffffffu, row[c2], c);
-                row[c2] -= lr * pc;
-            }
+            for (int c2 = c + 1; c2 < NB; ++c2) row[c2] -= lr * buf[c2];
             if (act) Dg[lane][c] = lr;
             if (lane == c) { dd[c] = dc; rdd[c] = rdc; }
         }
