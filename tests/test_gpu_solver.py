@@ -213,3 +213,49 @@ def test_flag_synchronised_sweeps_are_bitwise_reproducible(ws):
         assert torch.equal(o, ref)
         S.check()                                                             # no bounded spin gave up
         S.close()
+
+
+_RETILE_CHILD = r"""
+import sys, numpy as np, torch
+sys.path.insert(0, sys.argv[1])
+import wavesolve_b200 as ws
+from wavesolve_b200 import fe_solver as fs, solver as sv
+mg = ws.meshgen
+K0 = 2 * np.pi / 1.55
+mesh = mg.fiber_disc(50000, order=1, seed=21)
+ws.get_unique_edges(mesh)
+prob = fs.VectorProblem(mesh, mg.FIBER_IOR, K0)
+sigma = (K0 * max(mg.FIBER_IOR.values())) ** 2
+Mq = prob.assemble_qd(sigma)
+sym = sv.Symbolic.on_device(prob.dofs, prob.xy, prob.N, prob.Ntt)
+S = sv.Solver(prob.pattern, sym)
+S.factor(Mq)
+g = torch.Generator(device="cuda").manual_seed(5)
+b = torch.randn((2, prob.N), dtype=torch.float64, device="cuda", generator=g)
+x1 = S.solve(b[0].contiguous())
+x2 = S.solve(b)
+np.save(sys.argv[2], np.stack([x1.cpu().numpy(), x2[0].cpu().numpy(), x2[1].cpu().numpy(), b[0].cpu().numpy(), b[1].cpu().numpy()]))
+"""
+
+
+def test_top_levels_through_tile_kernels_agree_with_front_kernels(ws, tmp_path):
+    """Levels of few, wide fronts near the root of a small problem take the 256-thread tile kernels (LevelPlan::narrow_tiles)
+    instead of one thread per front row; WS_TILE_TOP=0 keeps them in the one-CTA-per-front kernels.  The choice is made once
+    per process, so each variant solves the same systems (one and two right-hand sides) in a process of its own: the
+    solutions agree to rounding (different summation order, same factors) and both satisfy M x = b."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = []
+    for tag, top in (("tiles", "32"), ("fronts", "0")):
+        path = str(tmp_path / ("x_%s.npy" % tag))
+        env = dict(os.environ, WS_TILE_TOP=top)
+        r = subprocess.run([sys.executable, "-c", _RETILE_CHILD, root, path], env=env, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs.append(np.load(path))
+    a, f = outs
+    assert np.array_equal(a[3:], f[3:])                                   # same right-hand sides
+    for i in range(3):
+        assert np.linalg.norm(a[i] - f[i]) <= 1e-11 * np.linalg.norm(f[i]), i
+    assert np.array_equal(a[0], a[1]) and np.array_equal(f[0], f[1])       # NR = 2 carries the same arithmetic per vector
