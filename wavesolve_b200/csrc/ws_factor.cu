@@ -251,10 +251,6 @@ __global__ void __launch_bounds__(128) k_gemm_tiles(const GemmTask* __restrict__
             }
 }
 
-// LDL^T of the nb x nb diagonal block (held in shared memory, redundantly per CTA) and
-// L_ik = F_ik L_kk^-T D^-1 for the task's rows.  The factored diagonal block goes to the solve
-// panel S (its diagonal blocks are free until the inversion phase), never back to L, so CTAs of
-// the same block column can read the un-factored block concurrently.
 // 1 / d to within an ulp in six instructions (the reciprocal refinement div.rn.f64 itself starts with: MUFU.RCP64H seed, two
 // Newton steps).  k_panel scales by it instead of dividing: an inlined fp64 division is ~100 SASS instructions with its slow
 // path, and the kernel -- straight-line code that each of a few warps executes once -- runs at instruction-fetch speed
@@ -270,6 +266,10 @@ __device__ __forceinline__ double fast_rcp(double d) {
     return __fma_rn(y, e, y);
 }
 
+// LDL^T of the nb x nb diagonal block (held in shared memory, redundantly per CTA) and
+// L_ik = F_ik L_kk^-T D^-1 for the task's rows.  The factored diagonal block goes to the solve
+// panel S (its diagonal blocks are free until the inversion phase), never back to L, so CTAs of
+// the same block column can read the un-factored block concurrently.
 __global__ void __launch_bounds__(PANEL_ROWS) k_panel(const PanelTask* __restrict__ tasks, double* __restrict__ Lbase,
                                                       double* __restrict__ Sbase, unsigned long long* __restrict__ stats) {
     const PanelTask t = tasks[blockIdx.x];
