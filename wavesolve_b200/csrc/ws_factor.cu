@@ -235,6 +235,20 @@ __global__ void __launch_bounds__(128) k_gemm_tiles(const GemmTask* __restrict__
         cp_async_commit();
     }
     const bool neg = (t.flags & GF_NEG) != 0, accum = (t.flags & GF_ACCUM) != 0;
+    // Epilogue in two passes: first ALL loads of the output tile, then the sums and the stores.  Written as one
+    // read-modify-write per entry the compiler must keep every load behind the previous store (they might alias), and a thread's
+    // 32 entries became 32 dependent global round trips -- 78 % of the samples of a small-grid launch sat on that line
+    // (profiles/r02c_factor_levels.txt).
+    double cold[4][NBLK][2];
+#pragma unroll
+    for (int mb = 0; mb < 4; ++mb)
+#pragma unroll
+        for (int nb = 0; nb < NBLK; ++nb)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int row = wm * 32 + mb * 8 + g, col = wn * WN + nb * 8 + 2 * tq + e;
+                cold[mb][nb][e] = (accum && row < t.m && col < t.n) ? t.C[row + (size_t)col * t.ldc] : 0.0;
+            }
 #pragma unroll
     for (int mb = 0; mb < 4; ++mb)
 #pragma unroll
@@ -243,10 +257,9 @@ __global__ void __launch_bounds__(128) k_gemm_tiles(const GemmTask* __restrict__
             for (int e = 0; e < 2; ++e) {
                 const int row = wm * 32 + mb * 8 + g, col = wn * WN + nb * 8 + 2 * tq + e;
                 if (row < t.m && col < t.n) {
-                    double* c = t.C + row + (size_t)col * t.ldc;
                     double v = neg ? -acc[mb][nb][e] : acc[mb][nb][e];
-                    if (accum) v += *c;
-                    *c = v;
+                    if (accum) v += cold[mb][nb][e];
+                    t.C[row + (size_t)col * t.ldc] = v;
                 }
             }
 }
@@ -512,14 +525,26 @@ __global__ void __launch_bounds__(256) k_extend_add(const ExtTask* __restrict__ 
     const int i = t.ti * 32 + tx;
     if (i >= qc) return;
     const int ri = rel[i];
-    for (int jj = ty; jj < 32; jj += 8) {
-        const int j = t.tj * 32 + jj;
-        if (j > i || j >= qc) continue;
-        const int rj = rel[j];
-        const double v = Uc[i + (size_t)j * qc];
-        if (rj < pp) Lp[ri + (size_t)rj * mp] += v;
-        else Up[(ri - pp) + (size_t)(rj - pp) * qp] += v;
+    // the thread's four entries: all loads first, then the four read-modify-writes (distinct targets: rel is injective), each in
+    // two passes -- one statement per entry would chain eight dependent global round trips behind stores that might alias
+    double* dst[4];
+    double v[4], old[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const int j = t.tj * 32 + ty + 8 * u;
+        dst[u] = nullptr;
+        v[u] = 0.0;
+        if (j <= i && j < qc) {
+            const int rj = rel[j];
+            v[u] = Uc[i + (size_t)j * qc];
+            dst[u] = rj < pp ? Lp + ri + (size_t)rj * mp : Up + (ri - pp) + (size_t)(rj - pp) * qp;
+        }
     }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) old[u] = dst[u] ? *dst[u] : 0.0;
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+        if (dst[u]) *dst[u] = old[u] + v[u];
 }
 
 // ---- small fronts: the whole front in one CTA -------------------------------------------------
