@@ -761,6 +761,14 @@ __device__ __forceinline__ void front_fused_body(int64_t first, int has_children
             if (a < b) continue;
             const double* la = P + p + a;
             const double* lb = P + p + b;
+            // the children's entries are requested before the k loop (read-only in this launch: ld.global.nc, so the loads of
+            // one entry do not queue behind the store of the previous one)
+            double g = 0.0;
+            if (has_children) {
+                const int ja0 = jm0[p + a], jb0 = jm0[p + b], ja1 = jm1[p + a], jb1 = jm1[p + b];
+                if (ja0 >= 0 && jb0 >= 0) g += __ldg(U0 + ja0 + (size_t)jb0 * qc0);
+                if (ja1 >= 0 && jb1 >= 0) g += __ldg(U1 + ja1 + (size_t)jb1 * qc1);
+            }
             double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
             int k = 0;
             for (; k + 3 < p; k += 4, la += 4 * ld, lb += 4 * ld) {
@@ -772,12 +780,6 @@ __device__ __forceinline__ void front_fused_body(int64_t first, int has_children
             for (; k < p; ++k, la += ld, lb += ld) acc0 += la[0] * (dd[k] * lb[0]);
             acc0 += acc2;
             acc1 += acc3;
-            double g = 0.0;
-            if (has_children) {
-                const int ja0 = jm0[p + a], jb0 = jm0[p + b], ja1 = jm1[p + a], jb1 = jm1[p + b];
-                if (ja0 >= 0 && jb0 >= 0) g += U0[ja0 + (size_t)jb0 * qc0];
-                if (ja1 >= 0 && jb1 >= 0) g += U1[ja1 + (size_t)jb1 * qc1];
-            }
             Ut[a + (size_t)b * q] = g - (acc0 + acc1);
         }
     };
