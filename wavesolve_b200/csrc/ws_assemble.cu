@@ -37,6 +37,7 @@ struct RowCtx {
     int64_t N;
     int64_t first_block;  // first 128-row block of this launch
     int cap;              // slots of the shared-memory tile (>= the largest block of the launch, if it fits)
+    int batch;            // 1 (default): the six slots of an incidence are read in one pass and written in a second (WS_ASM_BATCH=0: one by one)
 };
 
 // raw inputs of one element: vertex ids, vertex coordinates, k^2 n^2
@@ -374,6 +375,7 @@ k_assemble_rows(RowCtx cx, Op op, double* __restrict__ A, double* __restrict__ B
         __syncthreads();   // (global fallback: the zero-fill above is visible CTA-wide after the barrier)
     }
     const int64_t r = r0 + threadIdx.x;
+    const bool batch_rmw = cx.batch != 0;
     if (r < r1) {
         const int base = cx.rowptr[r] - s0;
         const int i0 = cx.incptr[r], i1 = cx.incptr[r + 1];
@@ -392,6 +394,31 @@ k_assemble_rows(RowCtx cx, Op op, double* __restrict__ A, double* __restrict__ B
                 double Av[6], Bv[6];
                 int cb[6];
                 op.row(cur, (int)(u & 7u), Av, Bv, cb);
+                if (FIRST && batch_rmw) {
+                    // the six targets of one incidence are distinct slots of the row (no element lists an unknown twice when
+                    // the first-touch flags are valid): all loads first, then the stores -- one dependent shared-memory round
+                    // trip per incidence instead of twelve
+                    int qs[6];
+                    double ob[6], oa[6];
+#pragma unroll
+                    for (int j = 0; j < 6; ++j) {
+                        const int h = cb[j] >> 1;
+                        const uint32_t w = h == 0 ? pk0 : (h == 1 ? pk1 : pk2);
+                        const uint32_t pq = (cb[j] & 1) ? (w >> 16) : (w & 0xffffu);
+                        const int q = base + (int)(pq & 0x7fffu);
+                        const bool fr = (pq & 0x8000u) != 0;
+                        qs[j] = fr ? ~q : q;
+                        ob[j] = fr ? 0.0 : tB[q];
+                        if (WRITE_A) oa[j] = fr ? 0.0 : tA[q];
+                    }
+#pragma unroll
+                    for (int j = 0; j < 6; ++j) {
+                        const bool fr = qs[j] < 0;
+                        const int q = fr ? ~qs[j] : qs[j];
+                        tB[q] = fr ? Bv[j] : ob[j] + Bv[j];
+                        if (WRITE_A) tA[q] = fr ? Av[j] : oa[j] + Av[j];
+                    }
+                } else
 #pragma unroll
                 for (int j = 0; j < 6; ++j) {
                     const int h = cb[j] >> 1;
@@ -489,7 +516,8 @@ static void launch_rows(const ws_pattern* p, const Op& op, double* A, double* B,
         int cap = 32;
         for (int gg = g; gg < g + groups_per_launch && gg < ws_pattern::NRANGE; ++gg) cap = std::max(cap, p->range_block_slots[gg]);
         cap = (cap + 31) & ~31;
-        RowCtx cx{p->rowptr.get(), p->incptr.get(), p->inc.get(), p->pos.get(), p->N, b0, cap};
+        static const int batch = getenv("WS_ASM_BATCH") ? atoi(getenv("WS_ASM_BATCH")) : 1;   // 0.277 -> 0.265 ms (vector), 0.271 -> 0.263 ms (scalar P2)
+        RowCtx cx{p->rowptr.get(), p->incptr.get(), p->inc.get(), p->pos.get(), p->N, b0, cap, batch};
         if ((size_t)cap * per_slot <= MAX_TILE_BYTES)
             kern<<<b1 - b0, ROWS_PER_CTA, (size_t)cap * per_slot, st>>>(cx, op, A, B);
         else
