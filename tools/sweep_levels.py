@@ -8,6 +8,7 @@ import sys
 
 import numpy as np
 
+os.environ["WS_TUNE_RELOAD"] = "1"          # WS_SWEEP_STOP is re-read per solve
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 

@@ -1833,7 +1833,11 @@ static void sweep_launches(ws_solver* s, const double* bi, double* xi, cudaStrea
     int nl = 0;
     // experiments (tools/sweep_levels.py): stop after the first WS_SWEEP_STOP launches -- the time of a truncated solve,
     // as a function of the cut, is the cost of each level INSIDE the overlapped pipeline (ncu serialises the launches)
-    const int stop_after = getenv("WS_SWEEP_STOP") ? atoi(getenv("WS_SWEEP_STOP")) : 1 << 30;
+    // (read once; WS_TUNE_RELOAD=1 re-reads it per solve, like the tuning knobs)
+    static const bool stop_reload = getenv("WS_TUNE_RELOAD") && atoi(getenv("WS_TUNE_RELOAD"));
+    static int stop_cached = getenv("WS_SWEEP_STOP") ? atoi(getenv("WS_SWEEP_STOP")) : 1 << 30;
+    if (stop_reload) stop_cached = getenv("WS_SWEEP_STOP") ? atoi(getenv("WS_SWEEP_STOP")) : 1 << 30;
+    const int stop_after = stop_cached;
     // Optional (WS_SPLIT=1): every level launched in two halves (left / right subtree of the root).  With the
     // per-front flags the left half of level l-1 depends on the left half of level l only, so it can run while the
     // right half of level l drains.  Measured: 0.977 ms against 0.970 ms per solve -- the tails are not what is
